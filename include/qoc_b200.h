@@ -1,0 +1,155 @@
+/*
+ * qoc_b200.h -- C ABI of the B200-native piecewise-constant GRAPE evaluator.
+ *
+ * Drop-in boundary for the exp-based GRAPE path of olof3/QuantumOptimalControl.jl.  The reference has no
+ * FFI of its own; the boundary is the set of Julia call signatures below, and every entry point names the
+ * reference function (file:line) it replaces.  INTEGRATION.md shows the Julia `ccall` shim a maintainer adds.
+ *
+ * Conventions (identical to what the reference passes around):
+ *   - all matrices are COLUMN-MAJOR; complex numbers are interleaved (re, im) doubles, i.e. Julia ComplexF64,
+ *     C `double _Complex`, `cuDoubleComplex`.  A "c128 d x d" argument is therefore `const double*` of
+ *     length 2*d*d.
+ *   - A0 and A[j] are ALREADY multiplied by dt ("propagation with unity time step",
+ *     src/gradient_computations.jl:1; callers pass A0dt.., examples/ipopt_callbacks_exp.jl:16).
+ *   - u is nc x Nt (x batch) Float64, column-major: u[j + nc*(k + Nt*b)].
+ *   - the caller owns every host buffer; the handle owns all device memory.
+ *   - a handle is not thread-safe (like the reference's `cache`); calls are synchronous on return unless the
+ *     name ends in _device (those enqueue on the given stream and return).
+ *   - no exceptions cross the ABI: every call returns a qoc_status; qoc_last_error() gives the detail text.
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device of compute capability 10.x.
+ */
+#ifndef QOC_B200_H
+#define QOC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qoc_handle qoc_handle;
+
+typedef enum {
+  QOC_OK = 0,
+  QOC_ERR_INVALID = 1,      /* bad argument (NULL pointer, non-positive size, unknown enum)                      */
+  QOC_ERR_DIMENSION = 2,    /* "A0 and x0 have incompatiable dimensions", src/gradient_computations.jl:84-87    */
+  QOC_ERR_STALE_CACHE = 3,  /* "Cache data from other control signal u", src/gradient_computations.jl:37-39     */
+  QOC_ERR_UNSUPPORTED = 4,  /* size / mode not covered by the kernels that exist (never a silent fallback)      */
+  QOC_ERR_CUDA = 5,         /* CUDA runtime failure; text in qoc_last_error                                      */
+  QOC_ERR_NO_DEVICE = 6,    /* no sm_100 device: the product path fails loudly                                   */
+  QOC_ERR_NOT_FINITE = 7,   /* J came out NaN/Inf                                                                */
+  QOC_ERR_SINGULAR = 8      /* Pade denominator numerically singular (pivot == 0)                               */
+} qoc_status;
+
+/* dUkdp_order of grape_sensitivity (src/gradient_computations.jl:35): 1..4 = the reference's truncated
+ * Taylor series of expm_jacobian! (:177-213); QOC_ORDER_FRECHET = exact Frechet derivative through the
+ * block-triangular augmented matrix [[X,A_j],[0,X]] (north-star mode; not available in the reference). */
+#define QOC_ORDER_FRECHET 0
+
+/* built-in terminal costs (so that J and the terminal costate are formed on the device) */
+typedef enum {
+  QOC_COST_INFIDELITY = 0, /* J = 1 - |tr(T'x)|^2/n^2, dJ_dx = (-2 Omega/n^2) T   src/penalty_fcns.jl:15-24         */
+  QOC_COST_ABS_TRACE = 1,  /* J = 1 - |tr(T'x)|,       dJ_dx = -(Omega/|Omega|) T  test/test_gradient_computation.jl:24-25 */
+  QOC_COST_NONE = 2        /* no built-in cost: caller evaluates Jfinal / dJfinal_dx (arbitrary closures) on the
+                              host from x_final and passes lambda_final to qoc_gradient                         */
+} qoc_cost;
+
+typedef struct {
+  int32_t d;        /* Hilbert-space dimension: A0, A[j] are d x d                                              */
+  int32_t m;        /* number of propagated state columns: x0 is d x m                                          */
+  int32_t nc;       /* number of controls: length(A)                                                            */
+  int32_t nt;       /* number of time slices: size(u, 2)                                                        */
+  int32_t batch;    /* number of independent pulses evaluated per call (1 = the reference's case)               */
+  int32_t order;    /* 1..4 or QOC_ORDER_FRECHET                                                                */
+  int32_t cost;     /* qoc_cost                                                                                 */
+  int32_t n;        /* normalisation n of setup_infidelity (src/penalty_fcns.jl:15); <= 0 means m               */
+  int32_t device;   /* CUDA device ordinal                                                                      */
+  /* running state penalty L(x) = mu * sum |x[pen_rows, pen_cols]|^2 summed over all Nt+1 states
+   * (src/penalty_fcns.jl:1-11, examples/ipopt_callbacks_exp.jl:18); n_pen_rows == 0 disables it.
+   * Index lists are 0-BASED here (the Julia shim subtracts 1).                                                  */
+  int32_t n_pen_rows;
+  int32_t n_pen_cols;
+  const int32_t* pen_rows;
+  const int32_t* pen_cols;
+  double mu;
+  int32_t store_costates; /* != 0: keep lambda_k for qoc_get_costates (debug / parity tests)                    */
+  int32_t reserved;
+} qoc_problem;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+
+/* replaces setup_grape_cache(A0, x0, u_size)  src/gradient_computations.jl:79-96.
+ * A0: c128 d x d; A: nc consecutive c128 d x d; x0: c128 d x m; T: c128 d x m target (may be NULL when
+ * cost == QOC_COST_NONE).  Uploads the constants and allocates x, lambda, U_k, dU_k/du_j, dJdu on the device. */
+int qoc_create(const qoc_problem* prob, const double* A0, const double* A, const double* x0, const double* T,
+               qoc_handle** out);
+int qoc_destroy(qoc_handle* h);
+
+/* grape_sensitivity takes dUkdp_order per call (src/gradient_computations.jl:35) and the cost closures are
+ * built after the cache (examples/ipopt_callbacks_exp.jl:9 vs examples/zz_coupling_ipopt_exp.jl:16): both can
+ * be changed on an existing handle.  Changing the order invalidates cached Jacobians (recomputed on demand
+ * from the cached u); changing the cost does not touch the cached propagation.                               */
+int qoc_set_order(qoc_handle* h, int order);
+int qoc_set_cost(qoc_handle* h, int cost, const double* T, int n);
+
+/* ---- the hot path, host buffers in / host buffers out ------------------------------------------------------ */
+
+/* replaces propagate(A0, A, u, x0, cache) + Jfinal(x[end]) + sum(L, x)
+ * (src/gradient_computations.jl:2-32; examples/ipopt_callbacks_exp.jl:16-18).
+ * J_out: batch doubles (may be NULL, and is left untouched when cost == QOC_COST_NONE and no penalty);
+ * x_final_out: c128 d x m x batch (may be NULL).  Records u as "the u used for the computations" (:12).       */
+int qoc_propagate(qoc_handle* h, const double* u, double* J_out, double* x_final_out);
+
+/* replaces grape_sensitivity(A0, A, dJfinal_dx, u, x0, cache; dUkdp_order, dL_dx)  (:35-77).
+ * u: if non-NULL it must equal the last propagated u, else QOC_ERR_STALE_CACHE (:37-39).
+ * lambda_final: c128 d x m x batch = dJfinal_dx(x[end]) evaluated by the caller; NULL selects the built-in
+ * cost of the handle.  dJdu_out: nc x Nt x batch doubles.                                                      */
+int qoc_gradient(qoc_handle* h, const double* u, const double* lambda_final, double* dJdu_out);
+
+/* propagate + gradient in one call (what f followed by f_grad computes, examples/ipopt_callbacks_exp.jl:11-31) */
+int qoc_eval(qoc_handle* h, const double* u, double* J_out, double* dJdu_out);
+
+/* ---- the same, device buffers (inputs already resident in HBM), asynchronous on `stream` ------------------ */
+/* d_u: nc x Nt x batch doubles in device memory; d_J: batch doubles; d_dJdu: nc x Nt x batch doubles.
+ * stream: a cudaStream_t cast to void* (NULL = default stream).  Skips the stale-u bookkeeping.              */
+int qoc_eval_device(qoc_handle* h, const double* d_u, double* d_J, double* d_dJdu, void* stream);
+
+/* ---- time-segment sharding of ONE long pulse across ranks (one process per GPU) --------------------------- */
+/* A handle created with nt = the LOCAL number of slices evaluates the slices [k_first, k_first+nt) of a longer
+ * pulse.  Phase 1 computes the local U_k, dU_k/du_j and the rank propagator S_p = U_last ... U_first
+ * (d x d, c128 column-major, device memory).  The caller all-gathers the S_p (NCCL), forms the boundary state
+ * x_start and boundary costate lambda_end for its segment, and phase 2 finishes the local sweeps.
+ * (src/gradient_computations.jl:27-29 and :52-58 are the serial loops this replaces.)                         */
+int qoc_shard_phase1_device(qoc_handle* h, const double* d_u, double* d_S_out, void* stream);
+/* d_x_start: c128 d x m (state entering the local segment); writes d_x_end: c128 d x m (state leaving it).   */
+int qoc_shard_forward_device(qoc_handle* h, const double* d_x_start, double* d_x_end, void* stream);
+/* d_lambda_end: c128 d x m costate at the end of the local segment; writes the local gradient columns
+ * d_dJdu (nc x nt_local) and d_lambda_start (c128 d x m, costate entering the segment from the right).       */
+int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_end, double* d_dJdu, double* d_lambda_start,
+                              void* stream);
+
+/* ---- cache getters (the reference returns x as its result, :31; parity tests read the rest) --------------- */
+int qoc_get_states(qoc_handle* h, double* x_out);        /* c128 d x m x (Nt+1) x batch  = cache.x              */
+int qoc_get_costates(qoc_handle* h, double* lam_out);    /* c128 d x m x (Nt+1) x batch  = cache.lambda          */
+int qoc_get_propagators(qoc_handle* h, double* U_out);   /* c128 d x d x Nt x batch      = cache.Uk_vec          */
+int qoc_get_jacobians(qoc_handle* h, double* dU_out);    /* c128 d x d x nc x Nt x batch = dUkdu of :61,:67      */
+
+/* ---- diagnostics ---------------------------------------------------------------------------------------- */
+const char* qoc_status_string(int status);
+const char* qoc_last_error(const qoc_handle* h); /* h may be NULL: error of the last failed qoc_create        */
+/* number of kernel launches issued by the last propagate/gradient/eval call on this handle                   */
+int qoc_last_launch_count(const qoc_handle* h);
+/* device time in ms of the named stage of the last *_device / eval call, measured with CUDA events on the
+ * launching stream; stage: 0 = K1 (expm + Jacobians + segment products), 1 = K2 (boundary scan + cost),
+ * 2 = K3 (sweeps + gradient contraction).  Requires qoc_set_profiling(h, 1).                                 */
+int qoc_set_profiling(qoc_handle* h, int on);
+double qoc_stage_ms(const qoc_handle* h, int stage);
+/* algorithmic flops (SURVEY.md 8d F_alg) of the last call, with the Pade degree / squarings actually chosen
+ * per slice, summed over slices and pulses.                                                                  */
+double qoc_last_alg_flops(const qoc_handle* h);
+int qoc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QOC_B200_H */

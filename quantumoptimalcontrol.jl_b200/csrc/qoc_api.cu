@@ -1,0 +1,628 @@
+// qoc_api.cu -- C ABI (include/qoc_b200.h) over the sm_100a kernels K1/K2/K3.  No CPU fallback: every compute
+// entry point requires a CUDA device and fails with QOC_ERR_NO_DEVICE / QOC_ERR_CUDA otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qoc_b200.h"
+#include "qoc_k1.cuh"
+#include "qoc_k23.cuh"
+
+using namespace qoc;
+
+static thread_local std::string g_create_error;
+
+struct qoc_handle {
+  qoc_problem prob;
+  int cfg;        // shape class index
+  int S;          // planar row stride
+  int slot_d;     // doubles per planar slot
+  int nsm;
+  int spp;        // segments per pulse
+  int nseg;
+  int seg_cap;    // max slices per segment
+  int k1_grid, k1_threads, k3_threads;
+  size_t k1_smem, k2_smem, k3_smem;
+  cudaStream_t stream;
+  // device buffers
+  double *dA0p = nullptr, *dAp = nullptr, *du = nullptr, *dU = nullptr, *dL = nullptr, *dQ = nullptr;
+  double *dx0 = nullptr, *dT = nullptr, *dxs = nullptr, *dle = nullptr, *dX = nullptr, *dLAM = nullptr;
+  double *dxf = nullptr, *dlam0 = nullptr, *dJ = nullptr, *dg = nullptr, *dflops = nullptr, *dlamf = nullptr;
+  double *dS = nullptr;
+  int* dstatus = nullptr;
+  int *dpen_rows = nullptr, *dpen_cols = nullptr;
+  // host state
+  std::vector<double> last_u;
+  bool have_u = false;       // a propagate() happened (cache valid)
+  bool have_jac = false;
+  bool states_valid = false, costates_valid = false;
+  int launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[4];
+  double stage_ms[3] = {0, 0, 0};
+  double alg_flops = 0.0;
+  std::string err;
+};
+
+#define QOC_CUDA(h, call)                                                                              \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      char buf__[512];                                                                                 \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+               __LINE__);                                                                              \
+      (h)->err = buf__;                                                                                \
+      return QOC_ERR_CUDA;                                                                             \
+    }                                                                                                  \
+  } while (0)
+
+// ---- shape classes ------------------------------------------------------------------------------------------
+typedef Cfg<1, 12, 2> Cfg0;  // d <= 8
+typedef Cfg<2, 12, 3> Cfg1;  // d <= 12
+typedef Cfg<2, 20, 4> Cfg2;  // d <= 16
+typedef Cfg<3, 20, 5> Cfg3;  // d <= 20
+typedef Cfg<3, 28, 6> Cfg4;  // d <= 24
+typedef Cfg<4, 28, 7> Cfg5;  // d <= 28
+
+static int pick_cfg(int d) {
+  if (d <= 8) return 0;
+  if (d <= 12) return 1;
+  if (d <= 16) return 2;
+  if (d <= 20) return 3;
+  if (d <= 24) return 4;
+  if (d <= 28) return 5;
+  return -1;
+}
+
+template <class F>
+static auto with_cfg(int cfg, F f) {
+  switch (cfg) {
+    case 0: return f(Cfg0());
+    case 1: return f(Cfg1());
+    case 2: return f(Cfg2());
+    case 3: return f(Cfg3());
+    case 4: return f(Cfg4());
+    default: return f(Cfg5());
+  }
+}
+
+static size_t k1_smem_bytes(int d, int nc, int S) {
+  const size_t slot = (size_t)2 * d * S * 8;
+  return (size_t)(K1_BASE_SLOTS + nc) * slot + (size_t)8 * S * 8 + (size_t)(4 * d + 32) * 16 + 32 * 8 + 64;
+}
+static size_t k2_smem_bytes(int d, int m, int S) {
+  const size_t slot = (size_t)2 * d * S * 8;
+  return (size_t)K2_NST * slot + (size_t)8 * S * 8 + (size_t)4 * d * m * 8 + 64;
+}
+static size_t k3_smem_bytes(int d, int m, int nc, int S, int NT, int seg_cap, bool grad) {
+  const size_t slot = (size_t)2 * d * S * 8;
+  const int nss = grad ? 1 + nc : 1;
+  return (size_t)K3_NST * nss * slot + (size_t)8 * S * 8 + (size_t)seg_cap * 2 * d * m * 8 + (size_t)4 * d * m * 8 +
+         (size_t)2 * nc * NT * 8 + 64;
+}
+
+static void to_planar(const double* M, int d, int S, double* out) {  // c128 col-major -> planar slot
+  memset(out, 0, sizeof(double) * 2 * d * S);
+  for (int c = 0; c < d; c++)
+    for (int r = 0; r < d; r++) {
+      out[r * S + c] = M[2 * (r + (size_t)d * c)];
+      out[d * S + r * S + c] = M[2 * (r + (size_t)d * c) + 1];
+    }
+}
+static void from_planar(const double* P, int d, int S, double* M) {
+  for (int c = 0; c < d; c++)
+    for (int r = 0; r < d; r++) {
+      M[2 * (r + (size_t)d * c)] = P[r * S + c];
+      M[2 * (r + (size_t)d * c) + 1] = P[d * S + r * S + c];
+    }
+}
+
+extern "C" const char* qoc_status_string(int s) {
+  switch (s) {
+    case QOC_OK: return "ok";
+    case QOC_ERR_INVALID: return "invalid argument";
+    case QOC_ERR_DIMENSION: return "Error when creating cache, A0 and x0 have incompatiable dimensions";
+    case QOC_ERR_STALE_CACHE: return "Cache data from other control signal u";
+    case QOC_ERR_UNSUPPORTED: return "size or mode not supported by the CUDA kernels";
+    case QOC_ERR_CUDA: return "CUDA runtime error";
+    case QOC_ERR_NO_DEVICE: return "no CUDA device of compute capability 10.x (no CPU fallback exists)";
+    case QOC_ERR_NOT_FINITE: return "J is not finite";
+    case QOC_ERR_SINGULAR: return "Pade denominator numerically singular";
+    default: return "unknown status";
+  }
+}
+extern "C" const char* qoc_last_error(const qoc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" int qoc_last_launch_count(const qoc_handle* h) { return h ? h->launches : 0; }
+extern "C" int qoc_version(void) { return 100; }
+extern "C" int qoc_set_profiling(qoc_handle* h, int on) {
+  if (!h) return QOC_ERR_INVALID;
+  h->profiling = on != 0;
+  return QOC_OK;
+}
+extern "C" double qoc_stage_ms(const qoc_handle* h, int stage) {
+  return (h && stage >= 0 && stage < 3) ? h->stage_ms[stage] : -1.0;
+}
+extern "C" double qoc_last_alg_flops(const qoc_handle* h) { return h ? h->alg_flops : 0.0; }
+
+extern "C" int qoc_destroy(qoc_handle* h) {
+  if (!h) return QOC_OK;
+  cudaSetDevice(h->prob.device);
+  double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
+                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS};
+  for (double* b : bufs)
+    if (b) cudaFree(b);
+  if (h->dstatus) cudaFree(h->dstatus);
+  if (h->dpen_rows) cudaFree(h->dpen_rows);
+  if (h->dpen_cols) cudaFree(h->dpen_cols);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return QOC_OK;
+}
+
+extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const double* A, const double* x0, const double* T,
+                          qoc_handle** out) {
+  g_create_error.clear();
+  if (!prob || !A0 || !x0 || !out || (prob->nc > 0 && !A)) { g_create_error = "NULL argument"; return QOC_ERR_INVALID; }
+  *out = nullptr;
+  const qoc_problem& p = *prob;
+  if (p.d <= 0 || p.m <= 0 || p.nc <= 0 || p.nt <= 0 || p.batch <= 0) { g_create_error = "non-positive size"; return QOC_ERR_DIMENSION; }
+  if (p.order < 0 || p.order > 4) { g_create_error = "order must be 0 (Frechet) or 1..4"; return QOC_ERR_INVALID; }
+  if (p.cost < 0 || p.cost > 2) { g_create_error = "unknown cost kind"; return QOC_ERR_INVALID; }
+  if (p.cost != QOC_COST_NONE && !T) { g_create_error = "built-in cost needs a target T"; return QOC_ERR_INVALID; }
+  if (p.m > 8) { g_create_error = "m > 8 state columns not supported yet"; return QOC_ERR_UNSUPPORTED; }
+  if (p.n_pen_rows > 0) { g_create_error = "running state penalty not supported yet"; return QOC_ERR_UNSUPPORTED; }
+  const int cfg = pick_cfg(p.d);
+  if (cfg < 0) { g_create_error = "d > 28 not supported yet by the shared-memory-resident kernels"; return QOC_ERR_UNSUPPORTED; }
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || p.device < 0 || p.device >= ndev) {
+    cudaGetLastError();
+    g_create_error = "no usable CUDA device (no CPU fallback exists)";
+    return QOC_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp dp;
+  if (cudaGetDeviceProperties(&dp, p.device) != cudaSuccess || dp.major != 10) {
+    g_create_error = "device is not compute capability 10.x (kernels are built for sm_100a only)";
+    return QOC_ERR_NO_DEVICE;
+  }
+  qoc_handle* h = new qoc_handle();
+  h->prob = p;
+  if (h->prob.n <= 0) h->prob.n = p.m;
+  h->prob.pen_rows = nullptr;
+  h->prob.pen_cols = nullptr;
+  h->cfg = cfg;
+  h->nsm = dp.multiProcessorCount;
+  h->stream = nullptr;
+  for (int i = 0; i < 4; i++) h->ev[i] = nullptr;
+  int rc = with_cfg(cfg, [&](auto c) -> int {
+    typedef decltype(c) C;
+    h->S = C::S;
+    h->slot_d = 2 * p.d * C::S;
+    h->k1_threads = C::NTHREADS;
+    h->k1_smem = k1_smem_bytes(p.d, p.nc, C::S);
+    h->k2_smem = k2_smem_bytes(p.d, p.m, C::S);
+    if (h->k1_smem > (size_t)dp.sharedMemPerBlockOptin) {
+      g_create_error = "K1 working set (16+nc matrices) exceeds shared memory for this d / nc";
+      return QOC_ERR_UNSUPPORTED;
+    }
+    QOC_CUDA(h, cudaSetDevice(p.device));
+    QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
+    QOC_CUDA(h, cudaFuncSetAttribute(k2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k2_smem));
+    int occ = 1;
+    QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C>, C::NTHREADS, h->k1_smem));
+    if (occ < 1) occ = 1;
+    const long long target = (long long)h->nsm * occ;
+    long long spp = (target + p.batch - 1) / p.batch;
+    if (spp < 1) spp = 1;
+    if (spp > p.nt) spp = p.nt;
+    // K3 keeps the forward states of a segment in shared memory: cap the segment length
+    const int ngrp = p.nc < 2 ? p.nc : 2;
+    h->k3_threads = C::NT * 32 * (1 + ngrp);
+    for (;;) {
+      h->seg_cap = (int)((p.nt + spp - 1) / spp);
+      h->k3_smem = k3_smem_bytes(p.d, p.m, p.nc, C::S, C::NT, h->seg_cap, true);
+      if (h->k3_smem <= (size_t)dp.sharedMemPerBlockOptin || spp >= p.nt) break;
+      spp = spp * 2 > p.nt ? p.nt : spp * 2;
+    }
+    if (h->k3_smem > (size_t)dp.sharedMemPerBlockOptin) {
+      g_create_error = "K3 working set exceeds shared memory";
+      return QOC_ERR_UNSUPPORTED;
+    }
+    QOC_CUDA(h, cudaFuncSetAttribute(k3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k3_smem));
+    h->spp = (int)spp;
+    h->nseg = (int)(spp * p.batch);
+    h->k1_grid = (int)(h->nseg < target ? h->nseg : target);
+    return QOC_OK;
+  });
+  if (rc != QOC_OK) { if (g_create_error.empty()) g_create_error = h->err; delete h; return rc; }
+
+  auto fail = [&](int code) { g_create_error = h->err; qoc_destroy(h); return code; };
+#define CR(call) do { int r__ = [&]() -> int { QOC_CUDA(h, call); return QOC_OK; }(); if (r__ != QOC_OK) return fail(r__); } while (0)
+  CR(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CR(cudaEventCreate(&h->ev[i]));
+  const size_t slotB = (size_t)h->slot_d * 8;
+  const size_t nsl = (size_t)p.batch * p.nt;
+  const size_t dmB = (size_t)2 * p.d * p.m * 8;
+  CR(cudaMalloc(&h->dA0p, slotB));
+  CR(cudaMalloc(&h->dAp, slotB * p.nc));
+  CR(cudaMalloc(&h->du, nsl * p.nc * 8));
+  CR(cudaMalloc(&h->dU, nsl * slotB));
+  CR(cudaMalloc(&h->dL, nsl * p.nc * slotB));
+  CR(cudaMalloc(&h->dQ, (size_t)h->nseg * slotB));
+  CR(cudaMalloc(&h->dx0, dmB));
+  CR(cudaMalloc(&h->dT, dmB));
+  CR(cudaMalloc(&h->dxs, (size_t)h->nseg * dmB));
+  CR(cudaMalloc(&h->dle, (size_t)h->nseg * dmB));
+  CR(cudaMalloc(&h->dX, (size_t)p.batch * (p.nt + 1) * dmB));
+  if (p.store_costates) CR(cudaMalloc(&h->dLAM, (size_t)p.batch * (p.nt + 1) * dmB));
+  CR(cudaMalloc(&h->dxf, (size_t)p.batch * dmB));
+  CR(cudaMalloc(&h->dlam0, (size_t)p.batch * dmB));
+  CR(cudaMalloc(&h->dlamf, (size_t)p.batch * dmB));
+  CR(cudaMalloc(&h->dJ, (size_t)p.batch * 8));
+  CR(cudaMalloc(&h->dg, nsl * p.nc * 8));
+  CR(cudaMalloc(&h->dflops, 8));
+  CR(cudaMalloc(&h->dS, slotB));
+  CR(cudaMalloc(&h->dstatus, 4));
+  CR(cudaMemset(h->dstatus, 0, 4));
+  CR(cudaMemset(h->dJ, 0, (size_t)p.batch * 8));
+  {
+    std::vector<double> tmp((size_t)h->slot_d * (1 + p.nc));
+    to_planar(A0, p.d, h->S, tmp.data());
+    for (int j = 0; j < p.nc; j++) to_planar(A + (size_t)j * 2 * p.d * p.d, p.d, h->S, tmp.data() + (size_t)(1 + j) * h->slot_d);
+    CR(cudaMemcpy(h->dA0p, tmp.data(), slotB, cudaMemcpyHostToDevice));
+    CR(cudaMemcpy(h->dAp, tmp.data() + h->slot_d, slotB * p.nc, cudaMemcpyHostToDevice));
+  }
+  CR(cudaMemcpy(h->dx0, x0, dmB, cudaMemcpyHostToDevice));
+  if (T) CR(cudaMemcpy(h->dT, T, dmB, cudaMemcpyHostToDevice));
+  else CR(cudaMemset(h->dT, 0, dmB));
+#undef CR
+  *out = h;
+  return QOC_OK;
+}
+
+extern "C" int qoc_set_order(qoc_handle* h, int order) {
+  if (!h) return QOC_ERR_INVALID;
+  if (order < 0 || order > 4) { h->err = "order must be 0 (Frechet) or 1..4"; return QOC_ERR_INVALID; }
+  if (order != h->prob.order) { h->prob.order = order; h->have_jac = false; }
+  return QOC_OK;
+}
+extern "C" int qoc_set_cost(qoc_handle* h, int cost, const double* T, int n) {
+  if (!h) return QOC_ERR_INVALID;
+  if (cost < 0 || cost > 2) { h->err = "unknown cost kind"; return QOC_ERR_INVALID; }
+  if (cost != QOC_COST_NONE && !T) { h->err = "built-in cost needs a target T"; return QOC_ERR_INVALID; }
+  QOC_CUDA(h, cudaSetDevice(h->prob.device));
+  if (T) QOC_CUDA(h, cudaMemcpy(h->dT, T, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyHostToDevice));
+  h->prob.cost = cost;
+  h->prob.n = n > 0 ? n : h->prob.m;
+  return QOC_OK;
+}
+
+// ---- launches -------------------------------------------------------------------------------------------------
+
+static K23Params base_k23(qoc_handle* h) {
+  const qoc_problem& p = h->prob;
+  K23Params q;
+  memset(&q, 0, sizeof q);
+  q.d = p.d; q.m = p.m; q.nc = p.nc; q.nt = p.nt; q.batch = p.batch; q.nseg = h->nseg; q.seg_per_pulse = h->spp;
+  q.cost = p.cost; q.n = p.n;
+  q.U = h->dU; q.L = h->dL; q.Q = h->dQ; q.x0 = h->dx0; q.T = h->dT;
+  q.xs_start = h->dxs; q.lam_end = h->dle; q.X = h->dX; q.LAM = h->dLAM; q.x_final = h->dxf; q.lam_start = h->dlam0;
+  q.J = h->dJ; q.dJdu = h->dg;
+  q.store_costates = p.store_costates;
+  return q;
+}
+
+static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_t st) {
+  const qoc_problem& p = h->prob;
+  K1Params k;
+  k.d = p.d; k.nc = p.nc; k.nt = p.nt; k.batch = p.batch; k.order = p.order;
+  k.nseg = h->nseg; k.seg_per_pulse = h->spp; k.want_jac = want_jac ? 1 : 0;
+  k.A0p = h->dA0p; k.Ap = h->dAp; k.u = d_u; k.U = h->dU; k.L = h->dL; k.Q = h->dQ;
+  k.flops = h->dflops; k.status = h->dstatus;
+  k.theta13 = (p.order == QOC_ORDER_FRECHET) ? 4.74 : 5.4;
+  QOC_CUDA(h, cudaMemsetAsync(h->dflops, 0, 8, st));
+  with_cfg(h->cfg, [&](auto c) {
+    typedef decltype(c) C;
+    k1_kernel<C><<<h->k1_grid, C::NTHREADS, h->k1_smem, st>>>(k);
+    return 0;
+  });
+  h->launches += 2;
+  QOC_CUDA(h, cudaGetLastError());
+  h->have_jac = want_jac;
+  return QOC_OK;
+}
+
+// phase: 0 forward + cost + backward, 1 forward only, 2 backward only (needs lam_final)
+static int launch_k2(qoc_handle* h, int phase, bool no_backward, const double* d_lam_final, const double* d_x_start,
+                     double* d_J, cudaStream_t st) {
+  K23Params q = base_k23(h);
+  q.k2_phase = phase;
+  q.skip_cost = no_backward ? 1 : 0;
+  q.lam_final = d_lam_final;
+  q.x_start_ext = d_x_start;
+  q.store_states = 1;
+  if (d_J) q.J = d_J;
+  with_cfg(h->cfg, [&](auto c) {
+    typedef decltype(c) C;
+    k2_kernel<C><<<h->prob.batch, C::NT * 32, h->k2_smem, st>>>(q);
+    return 0;
+  });
+  h->launches += 1;
+  QOC_CUDA(h, cudaGetLastError());
+  return QOC_OK;
+}
+
+static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d_dJdu, cudaStream_t st) {
+  K23Params q = base_k23(h);
+  q.want_grad = want_grad ? 1 : 0;
+  q.store_states = store_states ? 1 : 0;
+  if (d_dJdu) q.dJdu = d_dJdu;
+  const int grid = h->nseg < h->nsm * 2 ? h->nseg : h->nsm * 2;
+  with_cfg(h->cfg, [&](auto c) {
+    typedef decltype(c) C;
+    k3_kernel<C><<<grid, h->k3_threads, h->k3_smem, st>>>(q, h->seg_cap);
+    return 0;
+  });
+  h->launches += 1;
+  QOC_CUDA(h, cudaGetLastError());
+  if (store_states) h->states_valid = true;
+  if (want_grad && h->prob.store_costates) h->costates_valid = true;
+  return QOC_OK;
+}
+
+static int check_status(qoc_handle* h) {
+  int st = 0;
+  QOC_CUDA(h, cudaMemcpy(&st, h->dstatus, 4, cudaMemcpyDeviceToHost));
+  if (st != 0) {
+    cudaMemset(h->dstatus, 0, 4);
+    h->err = "zero pivot while inverting the Pade denominator";
+    return QOC_ERR_SINGULAR;
+  }
+  return QOC_OK;
+}
+
+static double sweep_flops(const qoc_problem& p, bool grad) {
+  const double d2 = (double)p.d * p.d;
+  const double per = grad ? 8.0 * d2 * p.m * (2 + p.nc) + 4.0 * p.nc * d2 : 8.0 * d2 * p.m;
+  return per * (double)p.nt * (double)p.batch;
+}
+
+extern "C" int qoc_eval_device(qoc_handle* h, const double* d_u, double* d_J, double* d_dJdu, void* stream) {
+  if (!h || !d_u) return QOC_ERR_INVALID;
+  if (h->prob.cost == QOC_COST_NONE) { h->err = "qoc_eval needs a built-in cost"; return QOC_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  QOC_CUDA(h, cudaSetDevice(h->prob.device));
+  h->launches = 0;
+  int rc;
+  if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[0], st));
+  if ((rc = launch_k1(h, d_u, true, st)) != QOC_OK) return rc;
+  if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[1], st));
+  if ((rc = launch_k2(h, 0, false, nullptr, nullptr, d_J, st)) != QOC_OK) return rc;
+  if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[2], st));
+  if ((rc = launch_k3(h, true, h->prob.store_costates != 0, d_dJdu, st)) != QOC_OK) return rc;
+  if (h->profiling) {
+    QOC_CUDA(h, cudaEventRecord(h->ev[3], st));
+    QOC_CUDA(h, cudaEventSynchronize(h->ev[3]));
+    for (int i = 0; i < 3; i++) {
+      float ms = 0;
+      QOC_CUDA(h, cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+      h->stage_ms[i] = ms;
+    }
+  }
+  return QOC_OK;
+}
+
+static int fetch_flops(qoc_handle* h, bool grad) {
+  double f = 0;
+  QOC_CUDA(h, cudaMemcpy(&f, h->dflops, 8, cudaMemcpyDeviceToHost));
+  h->alg_flops = f + sweep_flops(h->prob, grad);
+  return QOC_OK;
+}
+
+extern "C" int qoc_eval(qoc_handle* h, const double* u, double* J_out, double* dJdu_out) {
+  if (!h || !u) return QOC_ERR_INVALID;
+  const qoc_problem& p = h->prob;
+  const size_t nu = (size_t)p.nc * p.nt * p.batch;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  QOC_CUDA(h, cudaMemcpyAsync(h->du, u, nu * 8, cudaMemcpyHostToDevice, h->stream));
+  int rc = qoc_eval_device(h, h->du, nullptr, nullptr, h->stream);
+  if (rc != QOC_OK) return rc;
+  if (J_out) QOC_CUDA(h, cudaMemcpyAsync(J_out, h->dJ, (size_t)p.batch * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (dJdu_out) QOC_CUDA(h, cudaMemcpyAsync(dJdu_out, h->dg, nu * 8, cudaMemcpyDeviceToHost, h->stream));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->last_u.assign(u, u + nu);
+  h->have_u = true;
+  h->states_valid = p.store_costates != 0;
+  if ((rc = check_status(h)) != QOC_OK) return rc;
+  if ((rc = fetch_flops(h, true)) != QOC_OK) return rc;
+  if (J_out)
+    for (int b = 0; b < p.batch; b++)
+      if (!std::isfinite(J_out[b])) { h->err = "J is not finite"; return QOC_ERR_NOT_FINITE; }
+  return QOC_OK;
+}
+
+extern "C" int qoc_propagate(qoc_handle* h, const double* u, double* J_out, double* x_final_out) {
+  if (!h || !u) return QOC_ERR_INVALID;
+  const qoc_problem& p = h->prob;
+  const size_t nu = (size_t)p.nc * p.nt * p.batch;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  h->launches = 0;
+  h->states_valid = false;
+  h->costates_valid = false;
+  QOC_CUDA(h, cudaMemcpyAsync(h->du, u, nu * 8, cudaMemcpyHostToDevice, h->stream));
+  int rc;
+  // the Jacobians are produced together with U_k (they share the Pade powers): f_grad normally follows f
+  if ((rc = launch_k1(h, h->du, true, h->stream)) != QOC_OK) return rc;
+  const bool builtin = p.cost != QOC_COST_NONE;
+  if ((rc = launch_k2(h, builtin ? 0 : 1, true, nullptr, nullptr, nullptr, h->stream)) != QOC_OK) return rc;
+  if (J_out && builtin) QOC_CUDA(h, cudaMemcpyAsync(J_out, h->dJ, (size_t)p.batch * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (x_final_out)
+    QOC_CUDA(h, cudaMemcpyAsync(x_final_out, h->dxf, (size_t)p.batch * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost, h->stream));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->last_u.assign(u, u + nu);
+  h->have_u = true;
+  if ((rc = check_status(h)) != QOC_OK) return rc;
+  if ((rc = fetch_flops(h, false)) != QOC_OK) return rc;
+  if (J_out && builtin)
+    for (int b = 0; b < p.batch; b++)
+      if (!std::isfinite(J_out[b])) { h->err = "J is not finite"; return QOC_ERR_NOT_FINITE; }
+  return QOC_OK;
+}
+
+extern "C" int qoc_gradient(qoc_handle* h, const double* u, const double* lambda_final, double* dJdu_out) {
+  if (!h || !dJdu_out) return QOC_ERR_INVALID;
+  const qoc_problem& p = h->prob;
+  const size_t nu = (size_t)p.nc * p.nt * p.batch;
+  if (!h->have_u) { h->err = "qoc_gradient called before qoc_propagate"; return QOC_ERR_STALE_CACHE; }
+  if (u && memcmp(u, h->last_u.data(), nu * 8) != 0) {
+    h->err = "Cache data from other control signal u";  // src/gradient_computations.jl:37-39
+    return QOC_ERR_STALE_CACHE;
+  }
+  if (!lambda_final && p.cost == QOC_COST_NONE) { h->err = "no built-in cost: lambda_final required"; return QOC_ERR_INVALID; }
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  h->launches = 0;
+  int rc;
+  if (!h->have_jac) {  // order changed since the propagation: redo K1 on the cached u (h->du still holds it)
+    if ((rc = launch_k1(h, h->du, true, h->stream)) != QOC_OK) return rc;
+  }
+  if (lambda_final) {
+    QOC_CUDA(h, cudaMemcpyAsync(h->dlamf, lambda_final, (size_t)p.batch * 2 * p.d * p.m * 8, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_k2(h, 2, false, h->dlamf, nullptr, nullptr, h->stream)) != QOC_OK) return rc;
+  } else {
+    if ((rc = launch_k2(h, 0, false, nullptr, nullptr, nullptr, h->stream)) != QOC_OK) return rc;
+  }
+  if ((rc = launch_k3(h, true, true, nullptr, h->stream)) != QOC_OK) return rc;
+  QOC_CUDA(h, cudaMemcpyAsync(dJdu_out, h->dg, nu * 8, cudaMemcpyDeviceToHost, h->stream));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->alg_flops += sweep_flops(p, true) - sweep_flops(p, false);
+  return QOC_OK;
+}
+
+// ---- getters ----------------------------------------------------------------------------------------------------
+
+extern "C" int qoc_get_states(qoc_handle* h, double* x_out) {
+  if (!h || !x_out) return QOC_ERR_INVALID;
+  if (!h->have_u) { h->err = "no propagation cached"; return QOC_ERR_STALE_CACHE; }
+  const qoc_problem& p = h->prob;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  if (!h->states_valid) {
+    int rc = launch_k3(h, false, true, nullptr, h->stream);
+    if (rc != QOC_OK) return rc;
+  }
+  QOC_CUDA(h, cudaMemcpyAsync(x_out, h->dX, (size_t)p.batch * (p.nt + 1) * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost, h->stream));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return QOC_OK;
+}
+
+extern "C" int qoc_get_costates(qoc_handle* h, double* lam_out) {
+  if (!h || !lam_out) return QOC_ERR_INVALID;
+  if (!h->prob.store_costates || !h->costates_valid) { h->err = "costates not stored (store_costates=0 or no gradient yet)"; return QOC_ERR_STALE_CACHE; }
+  const qoc_problem& p = h->prob;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  QOC_CUDA(h, cudaMemcpy(lam_out, h->dLAM, (size_t)p.batch * (p.nt + 1) * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost));
+  return QOC_OK;
+}
+
+static int get_slots(qoc_handle* h, const double* dsrc, size_t nslots, double* out) {
+  const qoc_problem& p = h->prob;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  std::vector<double> tmp(nslots * h->slot_d);
+  QOC_CUDA(h, cudaMemcpy(tmp.data(), dsrc, tmp.size() * 8, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < nslots; i++) from_planar(tmp.data() + i * h->slot_d, p.d, h->S, out + i * 2 * p.d * p.d);
+  return QOC_OK;
+}
+extern "C" int qoc_get_propagators(qoc_handle* h, double* U_out) {
+  if (!h || !U_out) return QOC_ERR_INVALID;
+  if (!h->have_u) { h->err = "no propagation cached"; return QOC_ERR_STALE_CACHE; }
+  return get_slots(h, h->dU, (size_t)h->prob.batch * h->prob.nt, U_out);
+}
+extern "C" int qoc_get_jacobians(qoc_handle* h, double* dU_out) {
+  if (!h || !dU_out) return QOC_ERR_INVALID;
+  if (!h->have_u || !h->have_jac) { h->err = "no Jacobians cached"; return QOC_ERR_STALE_CACHE; }
+  return get_slots(h, h->dL, (size_t)h->prob.batch * h->prob.nt * h->prob.nc, dU_out);
+}
+
+// ---- time-segment sharding (phase API) ---------------------------------------------------------------------------
+// Sequential product of the local segment propagators: S = Q_{n-1} ... Q_0 (one CTA; the K1 tile machinery).
+template <class C>
+__global__ void __launch_bounds__(C::NTHREADS, 1) kq_reduce_kernel(const double* Q, int nq, int d, double* out_c128) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int S = C::S;
+  const int slot_d = 2 * d * S, n2 = slot_d / 2;
+  double* base = reinterpret_cast<double*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mi = warp / (C::NT / C::BN), nj0 = (warp % (C::NT / C::BN)) * C::BN;
+  {
+    double2* z = reinterpret_cast<double2*>(base);
+    for (int e = tid; e < (3 * slot_d + 8 * S) / 2; e += C::NTHREADS) z[e] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  Mat P, T, Qm;
+  P.re = base; P.im = P.re + d * S;
+  T.re = base + slot_d; T.im = T.re + d * S;
+  Qm.re = base + 2 * slot_d; Qm.im = Qm.re + d * S;
+  slot_copy(P.re, Q, n2, tid, C::NTHREADS);
+  __syncthreads();
+  for (int i = 1; i < nq; i++) {
+    slot_copy(Qm.re, Q + (size_t)i * slot_d, n2, tid, C::NTHREADS);
+    __syncthreads();
+    Acc<C::BN> acc; acc.zero();
+    mm_acc<C, false>(acc, Qm, P, mi, nj0, lane);
+    mm_store<C>(T, acc, d, mi, nj0, lane, NoEpi());
+    __syncthreads();
+    Mat t = P; P = T; T = t;
+  }
+  for (int e = tid; e < d * d; e += C::NTHREADS) {
+    const int c = e / d, r = e - c * d;
+    reinterpret_cast<double2*>(out_c128)[e] = make_double2(P.re[r * S + c], P.im[r * S + c]);
+  }
+}
+
+extern "C" int qoc_shard_phase1_device(qoc_handle* h, const double* d_u, double* d_S_out, void* stream) {
+  if (!h || !d_u || !d_S_out) return QOC_ERR_INVALID;
+  if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  QOC_CUDA(h, cudaSetDevice(h->prob.device));
+  h->launches = 0;
+  int rc = launch_k1(h, d_u, true, st);
+  if (rc != QOC_OK) return rc;
+  with_cfg(h->cfg, [&](auto c) {
+    typedef decltype(c) C;
+    const size_t smem = (size_t)(3 * h->slot_d + 8 * C::S) * 8;
+    cudaFuncSetAttribute(kq_reduce_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kq_reduce_kernel<C><<<1, C::NTHREADS, smem, st>>>(h->dQ, h->nseg, h->prob.d, d_S_out);
+    return 0;
+  });
+  h->launches += 1;
+  QOC_CUDA(h, cudaGetLastError());
+  h->have_u = true;
+  return QOC_OK;
+}
+
+extern "C" int qoc_shard_forward_device(qoc_handle* h, const double* d_x_start, double* d_x_end, void* stream) {
+  if (!h || !d_x_start) return QOC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  QOC_CUDA(h, cudaSetDevice(h->prob.device));
+  int rc = launch_k2(h, 1, true, nullptr, d_x_start, nullptr, st);
+  if (rc != QOC_OK) return rc;
+  if (d_x_end)
+    QOC_CUDA(h, cudaMemcpyAsync(d_x_end, h->dxf, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyDeviceToDevice, st));
+  return QOC_OK;
+}
+
+extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_end, double* d_dJdu, double* d_lambda_start,
+                                         void* stream) {
+  if (!h || !d_lambda_end) return QOC_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  QOC_CUDA(h, cudaSetDevice(h->prob.device));
+  int rc = launch_k2(h, 2, false, d_lambda_end, nullptr, nullptr, st);
+  if (rc != QOC_OK) return rc;
+  if ((rc = launch_k3(h, true, true, d_dJdu, st)) != QOC_OK) return rc;
+  if (d_lambda_start)
+    QOC_CUDA(h, cudaMemcpyAsync(d_lambda_start, h->dlam0, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyDeviceToDevice, st));
+  return QOC_OK;
+}
