@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- GRAPE fidelity+gradient throughput (slices*pulses/s) of the B200-native path, per BASELINE.json.
+
+A "step" is one full fidelity + gradient evaluation (qoc_eval: K1 expm + Jacobians + segment scan, K2 boundary scan +
+cost, K3 sweeps + gradient contraction) of the workload.  Workload at N = 1: BASELINE.json configs[1], the
+two_qubit_tunable_bus model (d = 27, m = 1, nc = 1) with 1e4 time slices, single pulse.  At N > 1 every rank
+evaluates its own pulse of that shape (multistart axis, no data-path collective) -> "scaling": "weak".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode frechet|taylor3] [--workload bus|zz_batch|cavity]
+  python bench.py --impl reference ...      # the CPU restatement of the reference (oracle/qoc_ref.c), all host threads
+
+value  : device-resident inputs (u already in HBM), CUDA events on the launching stream, max over ranks.
+e2e    : same metric through the host-buffer C-ABI call qoc_eval (pinned host u in, J and dJdu out, copies inside
+         the timed region).
+roofline: K1 (the dominant kernel): algorithmic FP64 flops (SURVEY.md 8d F_alg, Pade degree/squarings as executed)
+         / K1's CUDA-event duration, against the FP64 tensor-core (DMMA) peak measured on this pool's B200 by
+         tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl; MEASURED_PEAKS.json has no FP64 figure).
+cpu_baseline: oracle/qoc_ref.c ("port": the Julia reference cannot run here) on the box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GRAPE fidelity+gradient evals/s (slices*pulses/s)"
+UNIT = "slices*pulses/s"
+FP64_PEAK_FALLBACK_TFLOPS = 37.1  # measured DMMA m8n8k4 on this pool (profiles/r01_fp64_peak.jsonl)
+
+
+def fp64_peak_tflops():
+    """Measured FP64 (DMMA) peak: MEASURED_PEAKS.json carries none, so use the in-repo measurement."""
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "fp64_tflops" in mp:
+            return float(mp["fp64_tflops"]), "MEASURED_PEAKS.json fp64_tflops"
+    except Exception:
+        pass
+    try:
+        best = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r01_fp64_peak.jsonl")):
+            r = json.loads(line)
+            if r.get("test", "").startswith("dmma"):
+                best = max(best, float(r["tflops"]))
+        if best > 0:
+            return best, "measured in-repo: DMMA m8n8k4 loop on this pool's B200 (profiles/r01_fp64_peak.jsonl)"
+    except Exception:
+        pass
+    return FP64_PEAK_FALLBACK_TFLOPS, "fallback constant (DMMA m8n8k4 measured on this pool in round 1)"
+
+
+def build_workload(name, rank, mode):
+    from qoc_b200 import configs
+    if name == "bus":
+        cfg = configs.config_bus(Nt=10000)
+        if rank > 0:  # multistart: every rank its own pulse (small seeded perturbation of the envelope)
+            cfg["u"] = cfg["u"] + 1e-3 * np.random.default_rng(rank).standard_normal(cfg["u"].shape)
+        desc = "C2 two_qubit_tunable_bus d=27 m=1 nc=1 Nt=10000, single pulse per GPU"
+        batch, u = 1, cfg["u"]
+    elif name == "zz_batch":
+        nb = 4096
+        cfg = configs.config_zz_batch(nb, seed0=1 + rank * nb)
+        desc = "C4 zz_coupling d=9 m=4 nc=2 Nt=100, 4096 pulses per GPU"
+        batch, u = nb, cfg["u_batch"]
+    elif name == "cavity":
+        cfg = configs.config_cavity(12, Nt=550)
+        desc = "C3 cavity_qubit N_cavity=12 d=24 m=2 nc=2 Nt=550, single pulse per GPU"
+        batch, u = 1, cfg["u"]
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return cfg, u, batch, desc
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_run(cfg, u, batch, order, nthreads, reps):
+    """Times oracle/qoc_ref.c on `reps` full evaluations of (a bounded sample of) the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import qoc_ref
+    nth = qoc_ref.max_threads() if nthreads <= 0 else nthreads
+    if batch == 1:
+        pulses = [u]
+    else:  # bounded sample of the batch
+        pulses = [u[b] for b in range(min(batch, 64))]
+    qoc_ref.ref_eval(cfg, order=order, nthreads=nth, u=pulses[0])  # warm-up (page in, spin up the OpenMP team)
+    times, slices = [], 0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for up in pulses:
+            qoc_ref.ref_eval(cfg, order=order, nthreads=nth, u=up)
+        times.append(time.perf_counter() - t0)
+        slices = sum(p.shape[1] for p in pulses)
+    return slices, times, nth, len(pulses)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    order = 0 if args.mode == "frechet" else 3
+    cfg, u, batch, desc = build_workload(args.workload, 0, args.mode)
+    slices, times, nth, npulse = cpu_port_run(cfg, u, batch, order, 0, args.warmup + args.steps)
+    times = times[args.warmup:]
+    sec = sum(times)
+    val = slices * len(times) / sec
+    sample = f"{npulse} pulse(s) x {u.shape[-1]} slices of the workload per step, {len(times)} steps"
+    out = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(times), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": desc, "mode": args.mode,
+                      "note": "C restatement of the Julia reference (oracle/qoc_ref.c), not Julia: no julia toolchain in the image; "
+                              "OpenMP over the per-slice expm loop as Threads.@threads in the reference, serial sweeps"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="frechet", choices=["frechet", "taylor3"])
+    ap.add_argument("--workload", default="bus", choices=["bus", "zz_batch", "cavity"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import qoc_b200 as q
+    from qoc_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    order = 0 if args.mode == "frechet" else 3
+    cfg, u, batch, desc = build_workload(args.workload, rank, args.mode)
+    nc, nt = u.shape[-2], u.shape[-1]
+    lib = _lib.load()
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (nc, nt), batch=batch, device=local_rank, dUkdp_order=order,
+                                store_costates=False)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"]) if cfg["cost"] == 0 else q.setup_infidelity_abs_trace(cfg["T"])
+    # one host-API evaluation creates the handle, uploads constants and gives the numbers to sanity-check
+    J0, g0 = q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], cost[1], dUkdp_order=order)
+    h = cache.handle
+    launches_per_step = cache.launch_count()
+    alg_flops_total = cache.alg_flops()
+
+    from qoc_b200.grape import _u_arr
+    u_host = _u_arr(u, cache)
+    dev = torch.device("cuda", local_rank)
+    # a ring of input buffers resident in HBM; each step's working set (U_k + dU_k/du_j slots) is far larger than L2
+    d_us = [torch.from_numpy(u_host).to(dev) for _ in range(4)]
+    d_J = torch.zeros(batch, dtype=torch.float64, device=dev)
+    d_g = torch.zeros(u_host.shape, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device(i):
+        rc = lib.qoc_eval_device(h, C.c_void_p(d_us[i % 4].data_ptr()), C.c_void_p(d_J.data_ptr()),
+                                 C.c_void_p(d_g.data_ptr()), C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(lib.qoc_last_error(h).decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # sanity: the device path reproduces the host-API numbers
+    Jd = d_J.cpu().numpy()
+    assert np.allclose(Jd, np.atleast_1d(J0), atol=1e-12), "device-resident path disagrees with the host-API path"
+
+    # ---- e2e: host buffers through the C ABI (pinned), copies inside the timed region ----
+    u_pin = torch.from_numpy(u_host).pin_memory()
+    J_pin = torch.zeros(batch, dtype=torch.float64).pin_memory()
+    g_pin = torch.zeros(u_host.shape, dtype=torch.float64).pin_memory()
+    dp = C.POINTER(C.c_double)
+
+    def step_host():
+        rc = lib.qoc_eval(h, C.cast(u_pin.data_ptr(), dp), C.cast(J_pin.data_ptr(), dp), C.cast(g_pin.data_ptr(), dp))
+        if rc != 0:
+            raise RuntimeError(lib.qoc_last_error(h).decode())
+
+    for _ in range(3):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- per-stage device times of the dominant kernels (CUDA events inside the library, launching stream) ----
+    cache.set_profiling(True)
+    stage = np.zeros(3)
+    nprof = max(3, min(10, args.steps))
+    for i in range(nprof):
+        step_device(i)
+        torch.cuda.synchronize()
+        stage += np.array(cache.stage_ms())
+    stage /= nprof
+    cache.set_profiling(False)
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+
+    units_per_step = nt * batch * world
+    value = units_per_step * args.steps / (ms * 1e-3)
+    e2e_value = units_per_step * args.steps / e2e_s
+    peak, peak_src = fp64_peak_tflops()
+    sweep = (8.0 * cfg["A0"].shape[0] ** 2 * cfg["x0"].shape[1] * (2 + nc) + 4.0 * nc * cfg["A0"].shape[0] ** 2) * nt * batch
+    k1_flops = alg_flops_total - sweep
+    k1_tflops = k1_flops / (stage[0] * 1e-3) * 1e-12
+    roofline = {"bound": "tensor", "kernel": "k1_kernel (expm + Jacobians + segment scan)",
+                "achieved": k1_tflops, "peak": peak, "unit": "TFLOP/s", "frac": k1_tflops / peak, "traffic": None,
+                "peak_source": peak_src, "k1_ms": float(stage[0]), "k2_ms": float(stage[1]), "k3_ms": float(stage[2]),
+                "alg_flops_per_step": alg_flops_total, "k1_share_of_step": float(stage[0] / stage.sum()),
+                "whole_step_tflops": alg_flops_total * args.steps / (ms * 1e-3) * 1e-12 / world * world}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": desc, "mode": args.mode, "parallelism": f"pulse-sharded x{world}, no collective",
+                      "l2": "per-step working set (U_k and dU_k/du_j slots, %.0f MB) exceeds the 126 MB L2; 4 rotating input buffers"
+                            % (2 * nt * batch * (1 + nc) * 27 * 28 * 8 / 1e6 if args.workload == "bus" else 0)},
+           "clocks": clocks,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(u_host.nbytes),
+                   "d2h_bytes_per_step": int(J_pin.numel() * 8 + g_pin.numel() * 8), "ms_per_step": 1e3 * e2e_s / args.steps},
+           "gpu_launches": int(launches_per_step * args.steps),
+           "roofline": roofline}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        slices, times, nth, npulse = cpu_port_run(cfg, u, batch, order, 0, 3)
+        best = min(times)
+        out["cpu_baseline"] = {"value": slices / best, "unit": UNIT, "cores": nth, "kind": "port",
+                               "sample": f"{npulse} pulse(s) x {nt} slices, best of 3, oracle/qoc_ref.c (C restatement of the Julia "
+                                         f"reference, OpenMP over the expm loop), mode {args.mode}"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,261 @@
+"""Parity tests proper (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against
+(1) the committed golden fixtures, (2) the oracle on the same seeded inputs at sizes it finishes in seconds,
+(3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north star):
+  |dJ| <= 1e-10 * max(1, |J|)                       (relative on the fidelity, well-posed near J -> 0)
+  |dg_jk| <= 1e-8 * max_jk |g_jk|  per component     (same-order Taylor mode vs the reference formula;
+                                                      exact-Frechet mode vs the oracle's exact Frechet derivative)
+U_k, states and costates: 1e-12 absolute (unit-norm quantities).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import qoc_oracle as o
+import qoc_ref
+import qoc_b200 as q
+from qoc_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+TOL_J = 1e-10
+TOL_G = 1e-8
+
+
+def cost_of(cfg):
+    if cfg["cost"] == o.COST_INFIDELITY:
+        return q.setup_infidelity(cfg["T"], cfg["n"])
+    return q.setup_infidelity_abs_trace(cfg["T"])
+
+
+def gpu_eval(cfg, order, u=None, batch=1):
+    u = cfg["u"] if u is None else u
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], u.shape[-2:], batch=batch, dUkdp_order=order)
+    J, g = q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], cost_of(cfg)[1], dUkdp_order=order)
+    return J, g, cache
+
+
+def assert_parity(J, g, Jref, gref):
+    assert abs(J - Jref) <= TOL_J * max(1.0, abs(Jref))
+    assert np.abs(g - gref).max() <= TOL_G * np.abs(gref).max()
+
+
+def test_library_is_the_cuda_one():
+    lib = _lib.load()
+    assert lib.qoc_version() >= 100
+    import torch
+    assert torch.cuda.is_available() and torch.cuda.get_device_capability(0)[0] == 10
+
+
+# ---- (1) golden fixtures ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,cfgf,order", [
+    ("zz_order1", lambda: o.config_zz(), 1), ("zz_order2", lambda: o.config_zz(), 2),
+    ("zz_order3", lambda: o.config_zz(), 3), ("zz_order4", lambda: o.config_zz(), 4),
+    ("zz_order0", lambda: o.config_zz(), 0),
+    ("cavity12_nt100_order3", lambda: o.config_cavity(12, Nt=100), 3),
+    ("cavity12_nt550_order0", lambda: o.config_cavity(12, Nt=550), 0),
+    ("bus_nt500_order0", lambda: o.config_bus(Nt=500, tgate=17.5), 0),
+    ("synth16_nt64_order0", lambda: o.config_synthetic(16, 64), 0),
+])
+def test_golden(golden_dir, name, cfgf, order):
+    gd = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = cfgf()
+    assert np.array_equal(cfg["u"], gd["u"])
+    J, g, cache = gpu_eval(cfg, order)
+    assert_parity(J, g, float(gd["J"]), gd["dJdu"])
+    assert np.abs(cache.x[-1] - gd["x_final"]).max() < 1e-12
+    if "Uk" in gd:
+        assert np.abs(cache.Uk_vec - gd["Uk"]).max() < 1e-12
+        assert np.abs(cache.x - gd["x"]).max() < 1e-12
+        assert np.abs(cache.lam - gd["lam"]).max() < 1e-12
+
+
+def test_known_answers_full_size(golden_dir):
+    """The reference's two example known answers, computed by the CUDA path at full size."""
+    ka = np.load(os.path.join(golden_dir, "known_answers.npz"))
+    # cavity: examples/cavity_qubit.jl:80-81  "Should be about 0.999979"
+    H0, Tc, x0, theta = o.model_cavity_qubit(12)
+    cfg = o.config_cavity(12, Nt=550)
+    cache = q.propagate(cfg["A0"], cfg["A"], cfg["u"], x0.astype(complex).reshape(-1, 1))
+    tgt = np.kron([1, 0], np.exp(1j * theta))
+    tgt /= np.linalg.norm(tgt)
+    ov = abs(np.vdot(tgt, cache.x_final[:, 0]))
+    assert abs(ov - 0.999979) < 1e-6 and abs(ov - float(ka["cavity_overlap"])) < 1e-12
+    # bus: examples/two_qubit_tunable_bus.jl:66-67  "Should be something like 0.937218", Nt = 1e4 PWC
+    b = o.config_bus(Nt=10000)
+    cb = q.propagate(b["A0"], b["A"], b["u"], b["x0"])
+    pop = abs(np.vdot(b["T"], cb.x_final)) ** 2
+    assert abs(pop - 0.937218) < 1e-4 and abs(pop - float(ka["bus_population"])) < 1e-10
+    assert np.abs(cb.x_final - ka["bus_x_final"]).max() < 1e-11
+
+
+# ---- (2) oracle on the same seeded inputs ----------------------------------------------------------------------------
+@pytest.mark.parametrize("d,nt,nc,m,order", [
+    (3, 17, 1, 1, 0), (4, 9, 2, 4, 3), (8, 33, 2, 8, 0), (9, 100, 2, 4, 4), (12, 40, 3, 2, 0), (13, 21, 1, 3, 2),
+    (16, 50, 2, 4, 0), (17, 30, 2, 1, 3), (20, 25, 1, 5, 0), (21, 19, 2, 2, 1), (24, 60, 2, 2, 0), (25, 14, 2, 4, 0),
+    (27, 80, 1, 1, 0), (28, 31, 2, 7, 3), (27, 1, 1, 1, 0), (9, 2, 2, 4, 0),
+])
+def test_random_shapes_vs_oracle(d, nt, nc, m, order):
+    """Ragged sizes across every shape class, incl. d not a multiple of 4/8, Nt = 1, m up to 8."""
+    cfg = o.config_synthetic(d, nt, nc=nc, m=m, seed=1000 + d * 7 + nt)
+    Jo, go, co = o.evaluate(cfg, order=order)
+    J, g, cache = gpu_eval(cfg, order)
+    assert_parity(J, g, Jo, go)
+    assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-12
+    assert np.abs(cache.x - co["x"]).max() < 1e-12
+    assert np.abs(cache.lam - co["lam"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("scale", [1e-3, 0.3, 3.0, 11.0, 40.0])
+def test_norm_regimes_vs_oracle(scale):
+    """||X_k||_1 from tiny to large: 0..4 squarings, both threshold tables (Taylor mode 5.4, Frechet mode 4.74)."""
+    cfg = o.config_synthetic(12, 24, nc=2, m=3, seed=5)
+    cfg["A0"] = cfg["A0"] * scale
+    cfg["A"] = [a * scale for a in cfg["A"]]
+    for order in (0, 3):
+        Jo, go, co = o.evaluate(cfg, order=order)
+        J, g, cache = gpu_eval(cfg, order)
+        assert abs(J - Jo) <= TOL_J
+        # at large norm the truncated Taylor gradient is huge and ill-conditioned: compare relative to its scale
+        assert np.abs(g - go).max() <= TOL_G * max(np.abs(go).max(), 1e-300)
+        assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-11
+
+
+def test_nonnormal_generators_need_pivoting():
+    """Real non-normal matrices as in the reference's test/test_expm_jacobian.jl, and a rotation generator whose
+    Pade denominator has a (near-)zero leading entry: exercises the partial pivoting of the in-kernel inverse."""
+    rng = np.random.default_rng(0)
+    d = 6
+    A0 = (0.7 * rng.standard_normal((d, d))).astype(complex)
+    A1 = (0.5 * rng.standard_normal((d, d))).astype(complex)
+    cfg = dict(A0=A0, A=[A1], u=rng.uniform(-1, 1, (1, 12)), x0=np.eye(d, 2, dtype=complex),
+               T=np.eye(d, 2, dtype=complex), cost=o.COST_INFIDELITY, n=2)
+    for order in (0, 3):
+        Jo, go, co = o.evaluate(cfg, order=order)
+        J, g, cache = gpu_eval(cfg, order)
+        assert_parity(J, g, Jo, go)
+        assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-11 * max(1, np.abs(co["Uk"]).max())
+    G = np.array([[0, np.pi], [-np.pi, 0]], dtype=complex)   # exp(-G/2) has zero diagonal
+    cfg = dict(A0=G, A=[np.array([[0, 1], [1, 0]], dtype=complex) * 1j], u=np.array([[0.0, 0.3, -0.2]]),
+               x0=np.eye(2, dtype=complex), T=np.eye(2, dtype=complex), cost=o.COST_INFIDELITY, n=2)
+    Jo, go, co = o.evaluate(cfg, order=0)
+    J, g, cache = gpu_eval(cfg, 0)
+    assert_parity(J, g, Jo, go)
+    assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-12
+
+
+def test_reference_style_calls_and_host_closure(golden_dir):
+    """Mirrors test/test_gradient_computation.jl:27-35: propagate, then grape_sensitivity with an arbitrary host
+    closure dJfinal_dx (here the oracle's closure) -- the lambda_final path of the C ABI."""
+    cfg = o.config_cavity(12, Nt=100)
+    gd = np.load(os.path.join(golden_dir, "cavity12_nt100_order3.npz"))
+    Jf, dJf = o.setup_infidelity_abs_trace(cfg["T"])
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 100))
+    q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cache)
+    x = cache.x
+    assert abs(Jf(x[-1]) - float(gd["J"])) < TOL_J
+    g = q.grape_sensitivity(cfg["A0"], cfg["A"], dJf, cfg["u"], cfg["x0"], cache, dUkdp_order=3)
+    assert np.abs(g - gd["dJdu"]).max() <= TOL_G * np.abs(gd["dJdu"]).max()
+    # the same through the device-side built-in cost, and with another order on the same cache
+    g2 = q.grape_sensitivity(cfg["A0"], cfg["A"], q.setup_infidelity_abs_trace(cfg["T"])[1], cfg["u"], cfg["x0"], cache, dUkdp_order=3)
+    assert np.abs(g2 - g).max() < 1e-13
+    g4 = q.grape_sensitivity(cfg["A0"], cfg["A"], dJf, cfg["u"], cfg["x0"], cache, dUkdp_order=4)
+    _, go4, _ = o.evaluate(cfg, order=4)
+    assert np.abs(g4 - go4).max() <= TOL_G * np.abs(go4).max()
+    # stale cache error, src/gradient_computations.jl:37-39
+    with pytest.raises(q.QOCError, match="Cache data from other control signal u"):
+        q.grape_sensitivity(cfg["A0"], cfg["A"], dJf, cfg["u"] + 1e-9, cfg["x0"], cache)
+
+
+def test_gradient_vs_finite_differences_of_gpu_propagate():
+    """test/test_gradient_computation.jl:97-98: exact-Frechet gradient vs central differences of J through the
+    CUDA propagate itself (validates the exact mode independently of the oracle's Frechet code)."""
+    cfg = o.config_zz()
+    J, g, cache = gpu_eval(cfg, 0)
+    Jf = q.setup_infidelity(cfg["T"], cfg["n"])[0]
+    pc = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 100))
+    for (j, k) in ((0, 0), (1, 37), (0, 99), (1, 63)):
+        h = 1e-6
+        up, um = cfg["u"].copy(), cfg["u"].copy()
+        up[j, k] += h
+        um[j, k] -= h
+        Jp = q.propagate(cfg["A0"], cfg["A"], up, cfg["x0"], pc, Jfinal=Jf).J
+        Jm = q.propagate(cfg["A0"], cfg["A"], um, cfg["x0"], pc, Jfinal=Jf).J
+        assert abs((Jp - Jm) / (2 * h) - g[j, k]) < 2e-9
+    # order 4 -> exact convergence
+    _, g4, _ = gpu_eval(cfg, 4)
+    assert np.abs(g4 - g).max() / np.abs(g).max() == pytest.approx(9.77e-8, rel=0.02)
+
+
+def test_batch_equals_individual_pulses():
+    cfg = o.config_zz_batch(37)
+    ub = cfg["u_batch"]
+    Jb, gb, _ = gpu_eval(cfg, 3, u=ub, batch=37)
+    for b in (0, 5, 36):
+        Jo, go, _ = o.evaluate(cfg, order=3, u=ub[b])
+        assert_parity(Jb[b], gb[b], Jo, go)
+    J1, g1, _ = gpu_eval(cfg, 3, u=ub[11])
+    assert abs(J1 - Jb[11]) < 1e-14 and np.abs(g1 - gb[11]).max() < 1e-15
+
+
+def test_c_port_agrees_on_gpu_box():
+    """The timed CPU baseline (oracle/qoc_ref.c) computes the same thing as the CUDA path."""
+    cfg = o.config_bus(Nt=300, tgate=10.5)
+    J, g, _ = gpu_eval(cfg, 0)
+    out = qoc_ref.ref_eval(cfg, order=0)
+    assert_parity(J, g, out["J"], out["dJdu"])
+
+
+# ---- (3) size-independent properties at full size ----------------------------------------------------------------------
+def test_bus_full_size_properties():
+    """C2 at Nt = 1e4: unitarity of every U_k, norm preservation along the whole trajectory, costate norm
+    preservation, the exact-gradient identity sum_k over a doubled-slice refinement, and segment independence
+    (the parallel scan must give the same answer as a different segmentation = a shorter problem's prefix)."""
+    cfg = o.config_bus(Nt=10000)
+    J, g, cache = gpu_eval(cfg, 0)
+    U = cache.Uk_vec
+    err = np.abs(np.einsum("kji,kjl->kil", U.conj(), U) - np.eye(27)).max()
+    assert err < 5e-13
+    x = cache.x
+    assert np.abs(np.linalg.norm(x[:, :, 0], axis=1) - 1).max() < 1e-11
+    lam = cache.lam
+    assert np.abs(np.linalg.norm(lam[:, :, 0], axis=1) - np.linalg.norm(lam[-1, :, 0])).max() < 1e-11
+    # oracle on a strided sample of slices: U_k and the exact Frechet contraction
+    for k in range(0, 10000, 997):
+        X = o.generator(cfg["A0"], cfg["A"], cfg["u"][:, k])
+        R, L = o.expm_frechet_sps(X, cfg["A"][0])
+        assert np.abs(U[k] - R).max() < 1e-12
+        assert abs(o.compute_u_sensitivity(x[k], lam[k + 1], L) - g[0, k]) <= TOL_G * np.abs(g).max()
+    # prefix property: the first 2500 slices evaluated as their own problem give the same states
+    c2 = q.propagate(cfg["A0"], cfg["A"], cfg["u"][:, :2500], cfg["x0"])
+    assert np.abs(c2.x_final[:, 0] - x[2500, :, 0]).max() < 1e-11
+    # J from the C restatement's forward sweep (serial order) vs the parallel scan
+    ref = qoc_ref.ref_eval(cfg, order=0, want_grad=False)
+    assert abs(J - ref["J"]) <= TOL_J
+
+
+def test_linearity_in_terminal_costate():
+    """grape_sensitivity is linear in lambda_final: g(a*l1 + b*l2) = a*g(l1) + b*g(l2)."""
+    cfg = o.config_synthetic(16, 200, nc=2, m=4)
+    rng = np.random.default_rng(2)
+    l1 = rng.standard_normal((16, 4)) + 1j * rng.standard_normal((16, 4))
+    l2 = rng.standard_normal((16, 4)) + 1j * rng.standard_normal((16, 4))
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 200), dUkdp_order=0)
+    q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cache)
+    gs = [q.grape_sensitivity(cfg["A0"], cfg["A"], (lambda l: (lambda x: l))(l), cfg["u"], cfg["x0"], cache, dUkdp_order=0)
+          for l in (l1, l2, 0.3 * l1 - 1.7 * l2)]
+    assert np.abs(gs[2] - (0.3 * gs[0] - 1.7 * gs[1])).max() < 1e-12 * np.abs(gs[2]).max()
+
+
+def test_zz_batch_4096_properties():
+    """C4 shape: 4096 pulses in one call; spot-check pulses against the oracle and check J in [0, 1]."""
+    cfg = o.config_zz_batch(4096)
+    ub = cfg["u_batch"]
+    Jb, gb, cache = gpu_eval(cfg, 0, u=ub, batch=4096)
+    assert np.all(np.isfinite(Jb)) and np.all(Jb > -1e-12) and np.all(Jb < 1 + 1e-12)
+    for b in (0, 1234, 4095):
+        Jo, go, _ = o.evaluate(cfg, order=0, u=ub[b])
+        assert_parity(Jb[b], gb[b], Jo, go)
+    assert cache.launch_count() >= 3
