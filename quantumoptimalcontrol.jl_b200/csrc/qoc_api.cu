@@ -32,6 +32,8 @@ struct qoc_handle {
   double *dx0 = nullptr, *dT = nullptr, *dxs = nullptr, *dle = nullptr, *dX = nullptr, *dLAM = nullptr;
   double *dxf = nullptr, *dlam0 = nullptr, *dJ = nullptr, *dg = nullptr, *dflops = nullptr, *dlamf = nullptr;
   double *dS = nullptr;
+  long long* dbg = nullptr;  // developer timeline buffer (qoc_debug_k1_timeline)
+  int dbg_slices = 0;
   int* dstatus = nullptr;
   int *dpen_rows = nullptr, *dpen_cols = nullptr;
   // host state
@@ -91,7 +93,7 @@ static auto with_cfg(int cfg, F f) {
 
 static size_t k1_smem_bytes(int d, int nc, int S) {
   const size_t slot = (size_t)2 * d * S * 8;
-  return (size_t)(K1_BASE_SLOTS + nc) * slot + (size_t)8 * S * 8 + (size_t)(4 * d + 32) * 16 + 32 * 8 + 64;
+  return (size_t)k1_num_slots(nc) * slot + (size_t)8 * S * 8 + sizeof(SvcScratch) + 64;
 }
 static size_t k2_smem_bytes(int d, int m, int S) {
   const size_t slot = (size_t)2 * d * S * 8;
@@ -174,6 +176,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   if (p.cost < 0 || p.cost > 2) { g_create_error = "unknown cost kind"; return QOC_ERR_INVALID; }
   if (p.cost != QOC_COST_NONE && !T) { g_create_error = "built-in cost needs a target T"; return QOC_ERR_INVALID; }
   if (p.m > 8) { g_create_error = "m > 8 state columns not supported yet"; return QOC_ERR_UNSUPPORTED; }
+  if (p.nc > 8) { g_create_error = "nc > 8 controls not supported yet"; return QOC_ERR_UNSUPPORTED; }
   if (p.n_pen_rows > 0) { g_create_error = "running state penalty not supported yet"; return QOC_ERR_UNSUPPORTED; }
   const int cfg = pick_cfg(p.d);
   if (cfg < 0) { g_create_error = "d > 28 not supported yet by the shared-memory-resident kernels"; return QOC_ERR_UNSUPPORTED; }
@@ -206,14 +209,14 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     h->k1_smem = k1_smem_bytes(p.d, p.nc, C::S);
     h->k2_smem = k2_smem_bytes(p.d, p.m, C::S);
     if (h->k1_smem > (size_t)dp.sharedMemPerBlockOptin) {
-      g_create_error = "K1 working set (16+nc matrices) exceeds shared memory for this d / nc";
+      g_create_error = "K1 working set (16+2*nc matrices) exceeds shared memory for this d / nc";
       return QOC_ERR_UNSUPPORTED;
     }
     QOC_CUDA(h, cudaSetDevice(p.device));
     QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
     QOC_CUDA(h, cudaFuncSetAttribute(k2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k2_smem));
     int occ = 1;
-    QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C>, C::NTHREADS, h->k1_smem));
+    QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C>, C::NTHREADS + NSW * 32, h->k1_smem));
     if (occ < 1) occ = 1;
     const long long target = (long long)h->nsm * occ;
     long long spp = (target + p.batch - 1) / p.batch;
@@ -324,10 +327,11 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   k.A0p = h->dA0p; k.Ap = h->dAp; k.u = d_u; k.U = h->dU; k.L = h->dL; k.Q = h->dQ;
   k.flops = h->dflops; k.status = h->dstatus;
   k.theta13 = (p.order == QOC_ORDER_FRECHET) ? 4.74 : 5.4;
+  k.dbg = h->dbg; k.dbg_slices = h->dbg_slices;
   QOC_CUDA(h, cudaMemsetAsync(h->dflops, 0, 8, st));
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
-    k1_kernel<C><<<h->k1_grid, C::NTHREADS, h->k1_smem, st>>>(k);
+    k1_kernel<C><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);  // NW compute warps + 4 service warps
     return 0;
   });
   h->launches += 1;  // kernels only (the flop-counter memset is not counted)
@@ -625,4 +629,20 @@ extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_e
   if (d_lambda_start)
     QOC_CUDA(h, cudaMemcpyAsync(d_lambda_start, h->dlam0, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyDeviceToDevice, st));
   return QOC_OK;
+}
+
+// Developer aid (not part of include/qoc_b200.h): runs K1 once on the cached u with clock64() stamps recorded by CTA 0
+// at every hand-off between the compute warps and the service warp.  out: nslices x 16 long longs.
+extern "C" int qoc_debug_k1_timeline(qoc_handle* h, long long* out, int nslices, int want_jac) {
+  if (!h || !out || nslices <= 0 || !h->have_u) return QOC_ERR_INVALID;
+  QOC_CUDA(h, cudaSetDevice(h->prob.device));
+  QOC_CUDA(h, cudaMalloc(&h->dbg, sizeof(long long) * 16 * nslices));
+  QOC_CUDA(h, cudaMemset(h->dbg, 0, sizeof(long long) * 16 * nslices));
+  h->dbg_slices = nslices;
+  int rc = launch_k1(h, h->du, want_jac != 0, h->stream);
+  cudaStreamSynchronize(h->stream);
+  if (rc == QOC_OK) cudaMemcpy(out, h->dbg, sizeof(long long) * 16 * nslices, cudaMemcpyDeviceToHost);
+  cudaFree(h->dbg);
+  h->dbg = nullptr; h->dbg_slices = 0;
+  return rc;
 }

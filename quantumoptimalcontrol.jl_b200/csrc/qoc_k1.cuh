@@ -1,6 +1,6 @@
 // qoc_k1.cuh -- K1: per-slice generator assembly, scaling-and-squaring Pade expm, expm Jacobian
 // (exact block-triangular Frechet derivative or the reference's truncated Taylor series) and the level-1
-// propagator scan (running segment product), fused in one persistent kernel.
+// propagator scan (running segment product), fused in one persistent, warp-specialised kernel.
 //
 // Replaces, per slice k of the reference:
 //   X_k = A0 + sum_j u[j,k] A_j                          src/gradient_computations.jl:18-22
@@ -9,9 +9,16 @@
 // and produces the segment propagators Q_seg = U_{k1-1} ... U_{k0} that turn the serial sweeps of
 // :27-29 and :52-58 into a parallel scan (K2/K3 finish it).
 //
-// One CTA owns a contiguous run of slices (a segment); every matrix of a slice lives in shared memory as a
-// planar slot (qoc_tiles.cuh); every d^3 contraction is a DMMA.8x8x4 tile loop; only U_k, dU_k/du_j and Q_seg
-// go to HBM.
+// One CTA owns a contiguous run of slices (a segment).  Every matrix of a slice lives in shared memory as a
+// planar slot (qoc_tiles.cuh); every d^3 contraction is a DMMA.8x8x4 tile loop run by the NW "compute" warps.
+// Four extra "service" warps (one per SM sub-partition) invert the Pade denominator N = V - U in registers (one lane
+// per row, partial pivoting, in-place Gauss-Jordan).  That inverse is a 28-step latency chain whose FP64 instructions
+// must squeeze between the compute warps' DMMAs, so it is given a whole slice period: the compute warps are software
+// pipelined ACROSS slices,
+//      part1(k) -> build X(k+1) -> buildN(k+1) -> [wait N^-1(k)] -> tail(k)
+// (part1 = the 12 Frechet / 5 Taylor products per control that do not need N^-1; tail = R, rhs, L, squarings, stores,
+// segment product), with U and N double-buffered by slice parity.  Hand-over is by named barriers
+// (bar.arrive / bar.sync), alternating ids by parity.
 #pragma once
 #include "qoc_tiles.cuh"
 
@@ -30,7 +37,14 @@ struct K1Params {
   double* flops;           // accumulated algorithmic flops (F_alg) over slices
   int* status;             // set to QOC_ERR_SINGULAR (8) on a zero pivot
   double theta13;          // scaling threshold: 5.4 (Higham-2005 / reference) or 4.74 (Frechet, Al-Mohy-Higham)
+  long long* dbg;          // optional timeline of CTA 0: [slice][16] clock64 stamps (NULL in production)
+  int dbg_slices;
 };
+#define QOC_STAMP(idx)                                                                     \
+  do {                                                                                     \
+    if (p.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_i < p.dbg_slices)       \
+      p.dbg[dbg_i * 16 + (idx)] = clock64();                                               \
+  } while (0)
 
 // Pade-13 coefficients b0..b13
 __constant__ double c_b13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
@@ -38,24 +52,63 @@ __constant__ double c_b13[14] = {64764752532480000., 32382376266240000., 7771770
                                  1323241920.,        40840800.,          960960.,          16380.,
                                  182.,               1.};
 
-// slot roles; see the schedule in k1_slice_frechet13
-enum : int { sA = 0, sA2, sA4, sA6, sWZ, sW, sN, sP, sR, sM2, sM4, sM6, sT, sLw, sLv, sQ, sL0, K1_BASE_SLOTS = sL0 };
+// slot roles.  sX (unscaled generator) is only needed by the Taylor mode, where sLv is free: they alias.
+enum : int { sA = 0, sA2, sA4, sA6, sWZ, sW, sU0, sU1, sN0, sN1, sM2, sM4, sM6, sT, sLw, sLv, sQ, K1_FIXED_SLOTS, sX = sLv };
+// then nc slots E_j (control operators, resident for the whole kernel) and, for every control after the first, two
+// slots that carry (Lu - Lv, Lu + Lv) of that control from part1 to the tail
+__host__ __device__ constexpr int k1_num_slots(int nc) { return K1_FIXED_SLOTS + nc + 2 * (nc - 1); }
+
+// named barriers: 1 = compute warps, 7 = service warps, 2/3 = "N ready" (even/odd slice), 4/5 = "N^-1 ready"
+enum : int { BAR_C = 1, BAR_NREADY = 2, BAR_NINV = 4 };
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+// the sequence of (segment, slice) work items of one CTA; both roles walk it identically
+struct WorkIter {
+  int seg, k, k0, k1, b;
+  int nseg, spp, nt, stride;
+  __device__ __forceinline__ void load() {
+    b = seg / spp;
+    const int si = seg - b * spp;
+    k0 = (int)(((long long)si * nt) / spp);
+    k1 = (int)(((long long)(si + 1) * nt) / spp);
+    k = k0;
+  }
+  __device__ __forceinline__ void init(int first, int nseg_, int spp_, int nt_, int stride_) {
+    nseg = nseg_; spp = spp_; nt = nt_; stride = stride_; seg = first;
+    if (valid()) { load(); skip_empty(); }
+  }
+  __device__ __forceinline__ bool valid() const { return seg < nseg; }
+  __device__ __forceinline__ void skip_empty() {
+    while (valid() && k0 >= k1) { seg += stride; if (valid()) load(); }
+  }
+  __device__ __forceinline__ void next() {
+    if (++k >= k1) { seg += stride; if (valid()) { load(); skip_empty(); } }
+  }
+};
 
 template <class C>
 struct K1Ctx {
-  Mat s[K1_BASE_SLOTS + 8];  // slot table (pointer-swappable)
+  Mat s[K1_FIXED_SLOTS];
+  Mat E0, X0;                // first E slot / first extra (D,S) slot; slot j is at + j*slot_d
+  int slot_d;
   int d, n2;                 // n2 = double2 per slot
   int tid, lane, warp, mi, nj0;
-  double2* gjbuf;
-  double* scratch;
 
-  // dst = alpha * (sum of up to 3 products) + epilogue terms; one barrier at the end
+  __device__ __forceinline__ Mat E(int j) const { Mat m; m.re = E0.re + (size_t)j * slot_d; m.im = E0.im + (size_t)j * slot_d; return m; }
+  __device__ __forceinline__ Mat extra(int i) const { Mat m; m.re = X0.re + (size_t)i * slot_d; m.im = X0.im + (size_t)i * slot_d; return m; }
+  __device__ __forceinline__ void cbar() const { bar_sync(BAR_C, C::NTHREADS); }
+
+  // dst = epilogue(sum of products); one compute-warp barrier at the end
   template <class F>
   __device__ __forceinline__ void mm1(Mat dst, Mat a0, Mat b0, F f) {
     Acc<C::BN> acc; acc.zero();
     mm_acc<C, false>(acc, a0, b0, mi, nj0, lane);
     mm_store<C>(dst, acc, d, mi, nj0, lane, f);
-    __syncthreads();
+    cbar();
   }
   template <class F>
   __device__ __forceinline__ void mm2(Mat dst, Mat a0, Mat b0, Mat a1, Mat b1, F f) {
@@ -63,7 +116,7 @@ struct K1Ctx {
     mm_acc<C, false>(acc, a0, b0, mi, nj0, lane);
     mm_acc<C, false>(acc, a1, b1, mi, nj0, lane);
     mm_store<C>(dst, acc, d, mi, nj0, lane, f);
-    __syncthreads();
+    cbar();
   }
   template <class F>
   __device__ __forceinline__ void mm3(Mat dst, Mat a0, Mat b0, Mat a1, Mat b1, Mat a2, Mat b2, F f) {
@@ -72,7 +125,7 @@ struct K1Ctx {
     mm_acc<C, false>(acc, a1, b1, mi, nj0, lane);
     mm_acc<C, false>(acc, a2, b2, mi, nj0, lane);
     mm_store<C>(dst, acc, d, mi, nj0, lane, f);
-    __syncthreads();
+    cbar();
   }
   template <class F>
   __device__ __forceinline__ void mm4(Mat dst, Mat a0, Mat b0, Mat a1, Mat b1, Mat a2, Mat b2, Mat a3, Mat b3, F f) {
@@ -82,7 +135,7 @@ struct K1Ctx {
     mm_acc<C, false>(acc, a2, b2, mi, nj0, lane);
     mm_acc<C, false>(acc, a3, b3, mi, nj0, lane);
     mm_store<C>(dst, acc, d, mi, nj0, lane, f);
-    __syncthreads();
+    cbar();
   }
   __device__ __forceinline__ void lc(Mat dst, double c1, Mat m1, double c2, Mat m2, double c3, Mat m3, double cI) {
     lincomb<C::S>(dst, d, c1, m1, c2, m2, c3, m3, cI, tid, C::NTHREADS);
@@ -96,78 +149,308 @@ struct K1Ctx {
   __device__ __forceinline__ void swap(int a, int b) { Mat t = s[a]; s[a] = s[b]; s[b] = t; }
 };
 
-// R = exp(A) by the [13/13] Pade approximant; on entry s[sA] holds the (already scaled) generator.
-// On exit: s[sR] = r13(A), s[sN] = (V-U)^{-1}, and A2, A4, A6, W are kept for the Frechet part.
-template <class C>
-__device__ __forceinline__ bool pade13_expm(K1Ctx<C>& c) {
-  const double* b = c_b13;
-  Mat A = c.s[sA], A2 = c.s[sA2], A4 = c.s[sA4], A6 = c.s[sA6], WZ = c.s[sWZ], W = c.s[sW], N = c.s[sN], P = c.s[sP];
-  c.mm1(A2, A, A, NoEpi());
-  c.mm1(A4, A2, A2, NoEpi());
-  c.mm1(A6, A2, A4, NoEpi());
-  c.lc(WZ, b[13], A6, b[11], A4, b[9], A2, 0.0);  // W1
-  __syncthreads();
-  c.mm1(W, A6, WZ, c.epi(1.0, b[7], A6, b[5], A4, b[3], A2, b[1]));
-  c.lc(WZ, b[12], A6, b[10], A4, b[8], A2, 0.0);  // Z1
-  __syncthreads();
-  // V -> sN and U -> sP are independent: one barrier
-  {
-    Acc<C::BN> acc; acc.zero();
-    mm_acc<C, false>(acc, A6, WZ, c.mi, c.nj0, c.lane);
-    mm_store<C>(N, acc, c.d, c.mi, c.nj0, c.lane, c.epi(1.0, b[6], A6, b[4], A4, b[2], A2, b[0]));
-    acc.zero();
-    mm_acc<C, false>(acc, A, W, c.mi, c.nj0, c.lane);
-    mm_store<C>(P, acc, c.d, c.mi, c.nj0, c.lane, NoEpi());
-    __syncthreads();
+// epilogue that writes the product result AND a second matrix at the same position:
+//   dst  = acc + (c1 m1 + c2 m2 + cI I)         (via the wrapped LinEpi)
+//   dst2 = k0 * dst + k1 * n1 + k2 * n2
+template <int S>
+struct DualEpi {
+  LinEpi<S> base;
+  Mat dst2, n1, n2;
+  double k0, k1, k2;
+  int d;
+  __device__ __forceinline__ void operator()(int row, int col, double& r0, double& i0, double& r1, double& i1) const {
+    base(row, col, r0, i0, r1, i1);
+    const int o = row * S + col;
+    double2 a = *reinterpret_cast<const double2*>(n1.re + o), b = *reinterpret_cast<const double2*>(n1.im + o);
+    double2 c = *reinterpret_cast<const double2*>(n2.re + o), e = *reinterpret_cast<const double2*>(n2.im + o);
+    double2 wr, wi;
+    wr.x = k0 * r0 + k1 * a.x + k2 * c.x; wi.x = k0 * i0 + k1 * b.x + k2 * e.x;
+    wr.y = k0 * r1 + k1 * a.y + k2 * c.y; wi.y = k0 * i1 + k1 * b.y + k2 * e.y;
+    if (col + 1 >= d) { wr.y = 0.0; wi.y = 0.0; }
+    *reinterpret_cast<double2*>(dst2.re + o) = wr;
+    *reinterpret_cast<double2*>(dst2.im + o) = wi;
   }
-  // (N, P) <- (V - U, V + U)
-  diff_sum_inplace<C::S>(N, P, c.d, c.tid, C::NTHREADS);
-  __syncthreads();
-  bool ok = gj_inverse<C>(N, c.d, c.gjbuf, c.tid);
-  c.mm1(c.s[sR], N, P, NoEpi());
+};
+
+// epilogue for Lu: acc = Lu ;  writes D = Lu - Lv into dst (returned values) and S = Lu + Lv in place of Lv
+template <int S>
+struct DiffSumEpi {
+  Mat lv;
+  int d;
+  __device__ __forceinline__ void operator()(int row, int col, double& r0, double& i0, double& r1, double& i1) const {
+    const int o = row * S + col;
+    double2 a = *reinterpret_cast<const double2*>(lv.re + o), b = *reinterpret_cast<const double2*>(lv.im + o);
+    double2 sr = make_double2(r0 + a.x, r1 + a.y), si = make_double2(i0 + b.x, i1 + b.y);
+    if (col + 1 >= d) { sr.y = 0.0; si.y = 0.0; }
+    *reinterpret_cast<double2*>(lv.re + o) = sr;
+    *reinterpret_cast<double2*>(lv.im + o) = si;
+    r0 -= a.x; r1 -= a.y; i0 -= b.x; i1 -= b.y;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// service warps (4, one per SM sub-partition): in-register Gauss-Jordan inverse with partial pivoting.
+//  * Why four warps: every FP64 instruction of a service warp has to squeeze between the 16-cycle DMMAs that the
+//    compute warps of the same sub-partition keep back to back on its FP64 pipe (measured ~24 cycles per DP op with a
+//    single service warp).  Spreading the columns over the four sub-partitions divides that load by four.
+//  * lane = row; warp sw owns the columns c = sw (mod 4), i.e. DMAX/4 columns held in registers.
+//  * The matrix is padded to DMAX x DMAX with an identity block (inverse of blockdiag(N, I) is blockdiag(N^-1, I)), so
+//    trip counts are compile-time constants.
+//  * The owner of the current pivot column always finds it at register position 0: after a step it updates its
+//    window shifted by one (w[c-1] = w[c] - g r[c]) and appends the new column at the end, so all register indices
+//    are static while the outer loop stays ROLLED (small code, resident in the instruction cache).
+//  * No rows are physically swapped: lane p that supplies the pivot of step k remembers mycol = k.  With W the
+//    working array after the last step, A^-1[mycol_l][p_j] = W[l][j]   (p_j = the lane that pivoted column j).
+// Shared scratch: gbuf[2][32] multipliers, rowbuf[2][DMAX] pivot row, pinfo[2] = (1/pivot, p).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NSW = 4;  // service warps
+
+struct SvcScratch {
+  double2 gbuf[2][32];
+  double2 rowbuf[2][32];
+  double2 pinv[2];
+  int pidx[2];
+  int ok;             // cleared to 0 by a service warp that meets a zero pivot
+  int pad_;
+  float colsum[12][32];  // per-warp partial column sums of the generator build (compute warps)
+};
+
+__device__ __forceinline__ void bar_svc() { asm volatile("bar.sync %0, %1;" ::"r"(7), "r"(NSW * 32) : "memory"); }
+
+template <class C>
+__device__ __noinline__ bool service_inverse(Mat N, int d, SvcScratch* sc, int sw, int lane) {
+  constexpr int S = C::S;
+  constexpr int DM = C::DMAX;
+  constexpr int CL = DM / NSW;  // local columns; DMAX is a multiple of 4
+  double wr[CL], wi[CL];
+#pragma unroll
+  for (int c = 0; c < CL; c++) {
+    const int col = NSW * c + sw;
+    const bool v = (lane < d) && (col < d);
+    wr[c] = v ? N.re[lane * S + col] : ((lane == col && lane >= d) ? 1.0 : 0.0);
+    wi[c] = v ? N.im[lane * S + col] : 0.0;
+  }
+  bool used = lane >= DM;
+  int mycol = -1;
+  bool ok = true;
+  int par = 0;
+#pragma unroll 1
+  for (int kk = 0; kk < CL; kk++) {
+#pragma unroll
+    for (int o = 0; o < NSW; o++) {
+      if (sw == o) {  // owner of pivot column k = NSW*kk + o: it sits at local position 0
+        const double mag = wr[0] * wr[0] + wi[0] * wi[0];
+        // arg-max without touching the FP64 pipe: for mag >= 0 the high word of the double is a monotone key
+        // (sign 0, exponent, 20 mantissa bits -- plenty for a pivot choice); low 5 bits carry the lane.
+        const unsigned key = used ? 0u : (((unsigned)__double2hiint(mag) & ~31u) | (unsigned)(31 - lane));
+        const unsigned best = __reduce_max_sync(0xffffffffu, key);
+        const int p = 31 - (int)(best & 31u);
+        const bool okp = (best >> 5) != 0u;
+        // every lane inverts its own candidate concurrently with the reduction; the pivot lane's value is picked
+        const double den = 1.0 / mag;
+        const double ir = wr[0] * den, ii = -wi[0] * den;
+        const double pir = __shfl_sync(0xffffffffu, ir, p), pii = __shfl_sync(0xffffffffu, ii, p);  // 1/pivot
+        sc->gbuf[par][lane] = make_double2(wr[0] * pir - wi[0] * pii, wr[0] * pii + wi[0] * pir);
+        if (lane == 0) { sc->pinv[par] = make_double2(pir, pii); sc->pidx[par] = okp ? p : -1 - p; }
+      }
+      bar_svc();
+      int p = sc->pidx[par];
+      if (p < 0) { ok = false; p = -1 - p; }
+      const bool isp = (lane == p);
+      if (isp) {
+#pragma unroll
+        for (int c = 0; c < CL; c++) sc->rowbuf[par][NSW * c + sw] = make_double2(wr[c], wi[c]);
+        used = true;
+        mycol = NSW * kk + o;
+      }
+      bar_svc();
+      const double2 pinv = sc->pinv[par];
+      double2 g = sc->gbuf[par][lane];
+      // lanes != p: W[c] -= (W[k]/piv) * row[c];  lane p: W[c] = row[c]/piv  == 0 - (-1/piv) * row[c]
+      if (isp) {
+        g = make_double2(-pinv.x, -pinv.y);
+#pragma unroll
+        for (int c = 0; c < CL; c++) { wr[c] = 0.0; wi[c] = 0.0; }
+      }
+      if (sw == o) {
+        // note: the owner's rowbuf entries are indexed by CURRENT register position
+#pragma unroll
+        for (int c = 1; c < CL; c++) {
+          const double2 r = sc->rowbuf[par][NSW * c + sw];
+          wr[c - 1] = fma(-g.x, r.x, fma(g.y, r.y, wr[c]));
+          wi[c - 1] = fma(-g.x, r.y, fma(-g.y, r.x, wi[c]));
+        }
+        wr[CL - 1] = isp ? pinv.x : -g.x;
+        wi[CL - 1] = isp ? pinv.y : -g.y;
+      } else {
+#pragma unroll
+        for (int c = 0; c < CL; c++) {
+          const double2 r = sc->rowbuf[par][NSW * c + sw];
+          wr[c] = fma(-g.x, r.x, fma(g.y, r.y, wr[c]));
+          wi[c] = fma(-g.x, r.y, fma(-g.y, r.x, wi[c]));
+        }
+      }
+      par ^= 1;
+    }
+  }
+  // every window has rotated CL times: local position c holds column NSW*c + sw again.  Scatter into the slot
+  // (pad columns untouched: they are zero already).
+#pragma unroll
+  for (int c = 0; c < CL; c++) {
+    const int j = NSW * c + sw;
+    const unsigned bal = __ballot_sync(0xffffffffu, mycol == j);
+    const int pj = __ffs(bal) - 1;
+    if (j < d && mycol >= 0 && mycol < d && pj >= 0 && pj < d) {
+      N.re[mycol * S + pj] = wr[c];
+      N.im[mycol * S + pj] = wi[c];
+    }
+  }
   return ok;
 }
 
-// Exact Frechet derivative L(A, E) of the same Pade approximant (Al-Mohy & Higham 2009, Alg. 6.4), i.e. the
-// (1,2) block of r13([[A,E],[0,A]]) evaluated with the block-triangular structure made explicit: every
-// product of the augmented matrix costs the shared A-product (already done in pade13_expm) plus two d x d
-// products.  On entry s[sP] holds E (scaled like A); result -> s[sL0 + j].
+// ---------------------------------------------------------------------------------------------------------------------
+// compute warps
+// ---------------------------------------------------------------------------------------------------------------------
+
+// X = A0 + sum_j u_j E_j -> sA scaled by 2^-s (and unscaled -> sX for the Taylor mode); returns s (uniform).
+// A0 is constant over the whole launch: each thread keeps its elements in registers (a0r/a0i, one double2 of the real
+// and of the imaginary plane per iteration), the control operators are shared-memory resident, so assembling a
+// generator touches no global memory except the nc control amplitudes.
 template <class C>
-__device__ __forceinline__ void pade13_frechet(K1Ctx<C>& c, int j) {
+__device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, const double2 (&a0r)[2], const double2 (&a0i)[2],
+                                               size_t slice, bool need_x, SvcScratch* sc) {
+  constexpr int S = C::S;
+  const int d = c.d, nc = p.nc, h2 = c.n2 / 2;  // h2 = double2 per plane
+  double uj[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) uj[j] = (j < nc) ? __ldg(p.u + slice * nc + j) : 0.0;
+  // 1-norm in single precision (it only picks the number of squarings): every warp accumulates partial column sums
+  // of |x_ij| in its own row of the scratch (<= 3 lanes of a warp share a column), then all warps combine them
+  float* mycs = sc->colsum[c.warp];
+  mycs[c.lane] = 0.f;
+  __syncwarp();
+  double2 xr[2], xi[2];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    const int e = c.tid + t * C::NTHREADS;
+    xr[t] = a0r[t]; xi[t] = a0i[t];
+    if (e < h2) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < nc) {
+          const double2 wr = reinterpret_cast<const double2*>(c.E0.re + (size_t)j * c.slot_d)[e];
+          const double2 wi = reinterpret_cast<const double2*>(c.E0.im + (size_t)j * c.slot_d)[e];
+          xr[t].x = fma(uj[j], wr.x, xr[t].x); xr[t].y = fma(uj[j], wr.y, xr[t].y);
+          xi[t].x = fma(uj[j], wi.x, xi[t].x); xi[t].y = fma(uj[j], wi.y, xi[t].y);
+        }
+      const int col = (2 * e) % S;
+      const float ax = (float)xr[t].x, bx = (float)xi[t].x, ay = (float)xr[t].y, by = (float)xi[t].y;
+      if (col < d) atomicAdd(&mycs[col], sqrtf(ax * ax + bx * bx));
+      if (col + 1 < d) atomicAdd(&mycs[col + 1], sqrtf(ay * ay + by * by));
+    }
+  }
+  c.cbar();
+  int sq = 0;
+  {
+    constexpr int NP = C::NTHREADS / 32;
+    float ps = 0.f;
+#pragma unroll
+    for (int q = 0; q < NP; q++) ps += sc->colsum[q][c.lane];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ps = fmaxf(ps, __shfl_xor_sync(0xffffffffu, ps, off));
+    float t = (float)p.theta13;
+    while (ps > t && sq < 60) { t *= 2.f; sq++; }
+  }
+  const double scl = ldexp(1.0, -sq);
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    const int e = c.tid + t * C::NTHREADS;
+    if (e < h2) {
+      if (need_x) {
+        reinterpret_cast<double2*>(c.s[sX].re)[e] = xr[t];
+        reinterpret_cast<double2*>(c.s[sX].im)[e] = xi[t];
+      }
+      reinterpret_cast<double2*>(c.s[sA].re)[e] = make_double2(xr[t].x * scl, xr[t].y * scl);
+      reinterpret_cast<double2*>(c.s[sA].im)[e] = make_double2(xi[t].x * scl, xi[t].y * scl);
+    }
+  }
+  c.cbar();
+  return sq;
+}
+
+// [13/13] Pade: powers, W, U = A W, and N = V - U.  Leaves A2, A4, A6, W for the Frechet part.
+template <class C>
+__device__ __forceinline__ void pade13_build_N(K1Ctx<C>& c, Mat U, Mat N) {
   const double* b = c_b13;
-  Mat A = c.s[sA], A2 = c.s[sA2], A4 = c.s[sA4], A6 = c.s[sA6], WZ = c.s[sWZ], W = c.s[sW], Ninv = c.s[sN],
-      E = c.s[sP], R = c.s[sR], M2 = c.s[sM2], M4 = c.s[sM4], M6 = c.s[sM6], T = c.s[sT], Lw = c.s[sLw],
-      Lv = c.s[sLv];
+  Mat A = c.s[sA], A2 = c.s[sA2], A4 = c.s[sA4], A6 = c.s[sA6], WZ = c.s[sWZ], W = c.s[sW];
+  c.mm1(A2, A, A, NoEpi());
+  c.mm1(A4, A2, A2, NoEpi());
+  {  // A6 = A2 A4, and W1 = b13 A6 + b11 A4 + b9 A2 written by the same epilogue
+    DualEpi<C::S> e;
+    e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
+    e.dst2 = WZ; e.n1 = A4; e.n2 = A2; e.k0 = b[13]; e.k1 = b[11]; e.k2 = b[9]; e.d = c.d;
+    c.mm1(A6, A2, A4, e);
+  }
+  c.mm1(W, A6, WZ, c.epi(1.0, b[7], A6, b[5], A4, b[3], A2, b[1]));
+  {  // U = A W (independent of the Z1 lincomb that follows in the same phase)
+    Acc<C::BN> acc; acc.zero();
+    mm_acc<C, false>(acc, A, W, c.mi, c.nj0, c.lane);
+    mm_store<C>(U, acc, c.d, c.mi, c.nj0, c.lane, NoEpi());
+    c.lc(WZ, b[12], A6, b[10], A4, b[8], A2, 0.0);  // Z1
+    c.cbar();
+  }
+  // N = V - U with V = A6 Z1 + b6 A6 + b4 A4 + b2 A2 + b0 I
+  struct NEpi {
+    LinEpi<C::S> base; Mat U;
+    __device__ __forceinline__ void operator()(int row, int col, double& r0, double& i0, double& r1, double& i1) const {
+      base(row, col, r0, i0, r1, i1);
+      const int o = row * C::S + col;
+      double2 a = *reinterpret_cast<const double2*>(U.re + o), b2 = *reinterpret_cast<const double2*>(U.im + o);
+      r0 -= a.x; r1 -= a.y; i0 -= b2.x; i1 -= b2.y;
+    }
+  } ne;
+  ne.base = c.epi(1.0, b[6], A6, b[4], A4, b[2], A2, b[0]);
+  ne.U = U;
+  c.mm1(N, A6, WZ, ne);
+}
+
+// Exact Frechet derivative L(A, E) of the Pade approximant (Al-Mohy & Higham 2009, Alg. 6.4), i.e. the (1,2) block of
+// r13([[A,E],[0,A]]) with the block-triangular structure made explicit.  E is the UNSCALED control operator
+// (L is linear in E; the factor 2^-s is applied to the result).  part 1: everything that does not need N^-1.
+// On exit: Dst = Lu - Lv, Sst = Lu + Lv   (Sst doubles as the Lv workspace).
+template <class C>
+__device__ __forceinline__ void frechet13_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat Sst) {
+  const double* b = c_b13;
+  Mat A = c.s[sA], A2 = c.s[sA2], A4 = c.s[sA4], A6 = c.s[sA6], WZ = c.s[sWZ], W = c.s[sW], M2 = c.s[sM2],
+      M4 = c.s[sM4], M6 = c.s[sM6], T = c.s[sT], Lw = c.s[sLw], Lv = Sst;
   c.mm2(M2, A, E, E, A, NoEpi());
   c.mm2(M4, A2, M2, M2, A2, NoEpi());
-  c.mm2(M6, A4, M2, M4, A2, NoEpi());
-  c.lc(T, b[13], M6, b[11], M4, b[9], M2, 0.0);    // Lw1
-  c.lc(WZ, b[13], A6, b[11], A4, b[9], A2, 0.0);   // W1
-  __syncthreads();
+  {  // M6 = A4 M2 + M4 A2 ; T = Lw1 = b13 M6 + b11 M4 + b9 M2 from the same epilogue
+    DualEpi<C::S> e;
+    e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
+    e.dst2 = T; e.n1 = M4; e.n2 = M2; e.k0 = b[13]; e.k1 = b[11]; e.k2 = b[9]; e.d = c.d;
+    c.mm2(M6, A4, M2, M4, A2, e);
+  }
+  c.lc(WZ, b[13], A6, b[11], A4, b[9], A2, 0.0);  // W1 again (WZ held Z1)
+  c.cbar();
   c.mm2(Lw, A6, T, M6, WZ, c.epi(1.0, b[7], M6, b[5], M4, b[3], M2, 0.0));
   c.lc(T, b[12], M6, b[10], M4, b[8], M2, 0.0);    // Lz1
   c.lc(WZ, b[12], A6, b[10], A4, b[8], A2, 0.0);   // Z1
-  __syncthreads();
-  // Lv -> sLv and Lu -> sM2' are independent once Lw is known, but Lu's output slot must not alias inputs:
-  // Lv first (frees M2/M4/M6/T afterwards), then Lu into T.
+  c.cbar();
   c.mm2(Lv, A6, T, M6, WZ, c.epi(1.0, b[6], M6, b[4], M4, b[2], M2, 0.0));
-  c.mm2(T, A, Lw, E, W, NoEpi());  // Lu
-  // (T, Lv) <- (Lu - Lv, Lu + Lv)
-  diff_sum_inplace<C::S>(T, Lv, c.d, c.tid, C::NTHREADS);
-  __syncthreads();
-  // rhs = (Lu + Lv) + (Lu - Lv) R  -> M4 ;  L = Ninv rhs
-  c.mm1(M4, T, R, c.epi(1.0, 1.0, Lv, 0.0, Lv, 0.0, Lv, 0.0));
-  c.mm1(c.s[sL0 + j], Ninv, M4, NoEpi());
+  // Lu = A Lw + E W ; epilogue turns (Lu, Lv) into (D = Lu - Lv -> Dst, S = Lu + Lv -> in place of Lv)
+  DiffSumEpi<C::S> ds; ds.lv = Lv; ds.d = c.d;
+  c.mm2(Dst, A, Lw, E, W, ds);
 }
 
 // The reference's truncated Taylor series (src/gradient_computations.jl:177-213) with dt = 1.
-// X (unscaled generator) in s[sM6]; A_j in s[sP]; result -> s[sL0 + j].  Uses sM2, sM4, sT, sLw as scratch.
+// X (unscaled generator) in s[sX]; result -> out.  Uses sM2, sM4, sM6, sLw as scratch.
 template <class C>
-__device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, int j, int order) {
-  Mat X = c.s[sM6], Aj = c.s[sP], AjX = c.s[sM2], XAj = c.s[sM4], X2 = c.s[sT], out = c.s[sL0 + j];
+__device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, Mat Aj, Mat out, int order) {
+  Mat X = c.s[sX], AjX = c.s[sM2], XAj = c.s[sM4], X2 = c.s[sM6];
   if (order <= 1) {
     slot_copy(out.re, Aj.re, c.n2, c.tid, C::NTHREADS);
-    __syncthreads();
+    c.cbar();
     return;
   }
   {
@@ -182,167 +465,210 @@ __device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, int j, int order) {
       mm_acc<C, false>(acc, X, X, c.mi, c.nj0, c.lane);
       mm_store<C>(X2, acc, c.d, c.mi, c.nj0, c.lane, NoEpi());
     }
-    __syncthreads();
+    c.cbar();
   }
   if (order == 2) {
     c.lc(out, 1.0, Aj, 0.5, AjX, 0.5, XAj, 0.0);
-    __syncthreads();
+    c.cbar();
     return;
   }
-  // order >= 3:  out = Aj + (AjX + XAj)/2 + (AjX X + XAj X + X XAj)/6
   if (order == 3) {
     c.mm3(out, AjX, X, XAj, X, X, XAj, c.epi(1.0 / 6.0, 1.0, Aj, 0.5, AjX, 0.5, XAj, 0.0));
     return;
   }
-  // order 4: + (AjX X2 + XAj X2 + X2 AjX + X2 XAj)/24 ; two passes through the accumulator
   c.mm3(c.s[sLw], AjX, X, XAj, X, X, XAj, c.epi(1.0 / 6.0, 1.0, Aj, 0.5, AjX, 0.5, XAj, 0.0));
   c.mm4(out, AjX, X2, XAj, X2, X2, AjX, X2, XAj, c.epi(1.0 / 24.0, 1.0, c.s[sLw], 0.0, Aj, 0.0, Aj, 0.0));
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NTHREADS, 1) k1_kernel(K1Params p) {
+__global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int S = C::S;
+  constexpr int NALL = C::NTHREADS + NSW * 32;
   const int d = p.d, nc = p.nc;
   const int slot_d = 2 * d * S;  // doubles per slot
-  const int nslots = K1_BASE_SLOTS + nc;
+  const int nslots = k1_num_slots(nc);
   double* base = reinterpret_cast<double*>(smem_raw);
 
   K1Ctx<C> c;
   c.d = d;
+  c.slot_d = slot_d;
   c.n2 = slot_d / 2;
   c.tid = threadIdx.x;
   c.lane = threadIdx.x & 31;
   c.warp = threadIdx.x >> 5;
   c.mi = c.warp / (C::NT / C::BN);
   c.nj0 = (c.warp % (C::NT / C::BN)) * C::BN;
-  for (int i = 0; i < nslots; i++) { c.s[i].re = base + (size_t)i * slot_d; c.s[i].im = c.s[i].re + d * S; }
-  // tail: 8 rows of zero padding (fragment loads of the last tile row run past the last slot), then buffers
+  for (int i = 0; i < K1_FIXED_SLOTS; i++) { c.s[i].re = base + (size_t)i * slot_d; c.s[i].im = c.s[i].re + d * S; }
+  c.E0.re = base + (size_t)K1_FIXED_SLOTS * slot_d; c.E0.im = c.E0.re + d * S;
+  c.X0.re = base + (size_t)(K1_FIXED_SLOTS + nc) * slot_d; c.X0.im = c.X0.re + d * S;
+  // tail: 8 rows of zero padding (fragment loads of the last tile row run past the last slot), then small buffers
   double* tail = base + (size_t)nslots * slot_d;
-  c.gjbuf = reinterpret_cast<double2*>(tail + 8 * S);
-  c.scratch = reinterpret_cast<double*>(c.gjbuf + 4 * d + 32);
-  // zero everything once: pad columns must be exactly zero and all pad reads finite
+  SvcScratch* sc = reinterpret_cast<SvcScratch*>(tail + 8 * S);
+  const bool is_service = (c.warp >= C::NW);
+  const bool taylor = (p.order != 0);
+
+  // zero everything once (pad columns must be exactly zero, all pad reads finite), then load the control operators
   {
     const int total2 = (nslots * slot_d + 8 * S) / 2;
     double2* z = reinterpret_cast<double2*>(base);
-    for (int e = c.tid; e < total2; e += C::NTHREADS) z[e] = make_double2(0.0, 0.0);
+    for (int e = threadIdx.x; e < total2; e += NALL) z[e] = make_double2(0.0, 0.0);
+    if (threadIdx.x == 0) sc->ok = 1;
   }
   __syncthreads();
+  for (int j = 0; j < nc; j++) slot_copy(c.E0.re + (size_t)j * slot_d, p.Ap + (size_t)j * slot_d, c.n2, threadIdx.x, NALL);
+  __syncthreads();
 
+  WorkIter it;
+  it.init(blockIdx.x, p.nseg, p.seg_per_pulse, p.nt, gridDim.x);
+  const bool need_x = taylor && p.want_jac && p.order >= 2;
+
+  if (is_service) {
+    // =============================== service warps: one inverse per slice ===============================
+    const int lane = c.lane;
+    const int sw = c.warp - C::NW;
+    bool all_ok = true;
+    int par = 0;
+    int dbg_i = (sw == 0) ? 0 : (1 << 30);
+    while (it.valid()) {
+      QOC_STAMP(8);
+      bar_sync(BAR_NREADY + par, NALL);         // compute warps have formed N = V - U of this slice
+      QOC_STAMP(9);
+      all_ok &= service_inverse<C>(c.s[sN0 + par], d, sc, sw, lane);
+      QOC_STAMP(10);
+      bar_arrive(BAR_NINV + par, NALL);         // N^-1 is in place
+      dbg_i++;
+      par ^= 1;
+      it.next();
+    }
+    if (lane == 0 && !all_ok) atomicExch(p.status, 8);
+    return;
+  }
+
+  // =============================== compute warps ===============================
   double my_flops = 0.0;
-  bool all_ok = true;
   const double M = 8.0 * d * d * (double)d;
+  int dbg_i = (c.warp == 0) ? 0 : (1 << 30);
+  // A0 stays in registers for the whole launch
+  double2 a0r[2], a0i[2];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    const int e = c.tid + t * C::NTHREADS;
+    const bool v = e < c.n2 / 2;
+    a0r[t] = v ? reinterpret_cast<const double2*>(p.A0p)[e] : make_double2(0.0, 0.0);
+    a0i[t] = v ? reinterpret_cast<const double2*>(p.A0p + d * S)[e] : make_double2(0.0, 0.0);
+  }
+  // (D, S) = (Lu - Lv, Lu + Lv) homes per control: control 0 uses (sM2, sLv); control j >= 1 the extra slots.
+  // They are tracked by pointer because the squaring phase ping-pongs results through scratch slots.
+  Mat Dh[8], Sh[8];
+  for (int j = 1; j < nc && j < 8; j++) { Dh[j] = c.extra(2 * (j - 1)); Sh[j] = c.extra(2 * (j - 1) + 1); }
+  int par = 0;
+  int sq = 0;
+  if (it.valid()) {
+    sq = build_generator<C>(p, c, a0r, a0i, (size_t)it.b * p.nt + it.k, need_x, sc);
+    pade13_build_N<C>(c, c.s[sU0], c.s[sN0]);
+    bar_arrive(BAR_NREADY + 0, NALL);
+  }
 
-  for (int seg = blockIdx.x; seg < p.nseg; seg += gridDim.x) {
-    const int b = seg / p.seg_per_pulse, si = seg - b * p.seg_per_pulse;
-    const int k0 = (int)(((long long)si * p.nt) / p.seg_per_pulse);
-    const int k1 = (int)(((long long)(si + 1) * p.nt) / p.seg_per_pulse);
-    for (int k = k0; k < k1; k++) {
-      const size_t slice = (size_t)b * p.nt + k;
-      const double* uk = p.u + slice * nc;
-      // ---- S1: X = A0 + sum_j u_j A_j  (planar, coalesced from L2) ----
-      {
-        double2* x2 = reinterpret_cast<double2*>(c.s[sA].re);
-        const double2* a0 = reinterpret_cast<const double2*>(p.A0p);
-        for (int e = c.tid; e < c.n2; e += C::NTHREADS) {
-          double2 v = a0[e];
-          for (int j = 0; j < nc; j++) {
-            double2 w = reinterpret_cast<const double2*>(p.Ap + (size_t)j * slot_d)[e];
-            const double uj = uk[j];
-            v.x = fma(uj, w.x, v.x);
-            v.y = fma(uj, w.y, v.y);
-          }
-          x2[e] = v;
-        }
-      }
-      __syncthreads();
-      const double nrm = norm1<S>(c.s[sA], d, c.scratch, c.tid, C::NTHREADS);
-      int sq = 0;
-      if (nrm > p.theta13) {
-        sq = (int)ceil(log2(nrm / p.theta13));
-        if (sq < 0) sq = 0;
-        if (sq > 60) sq = 60;
-      }
-      const double sc = ldexp(1.0, -sq);
-      const bool taylor = (p.order != 0);
-      if (taylor && p.want_jac && p.order >= 2) {
-        // keep the unscaled generator for the reference's Taylor series
-        slot_copy(c.s[sM6].re, c.s[sA].re, c.n2, c.tid, C::NTHREADS);
-      }
-      if (sq > 0) {
-        double2* x2 = reinterpret_cast<double2*>(c.s[sA].re);
-        for (int e = c.tid; e < c.n2; e += C::NTHREADS) { double2 v = x2[e]; x2[e] = make_double2(v.x * sc, v.y * sc); }
-      }
-      __syncthreads();
+  while (it.valid()) {
+    const bool first_of_seg = (it.k == it.k0);
+    const bool last_of_seg = (it.k + 1 >= it.k1);
+    const int seg = it.seg;
+    const size_t slice = (size_t)it.b * p.nt + it.k;
+    const double scl = ldexp(1.0, -sq);
+    const int sq_cur = sq;
+    QOC_STAMP(0);
 
-      // ---- S2: U_k = r13(X / 2^s)^(2^s) ----
-      all_ok &= pade13_expm<C>(c);
-
-      // ---- S3: Jacobians ----
-      if (p.want_jac) {
-        if (!taylor) {
-          for (int j = 0; j < nc; j++) {
-            slot_copy_scaled(c.s[sP].re, p.Ap + (size_t)j * slot_d, sc, c.n2, c.tid, C::NTHREADS);
-            __syncthreads();
-            pade13_frechet<C>(c, j);
-          }
-          // squaring phase: L <- R L + L R ; R <- R R
-          for (int t = 0; t < sq; t++) {
-            for (int j = 0; j < nc; j++) {
-              c.mm2(c.s[sT], c.s[sR], c.s[sL0 + j], c.s[sL0 + j], c.s[sR], NoEpi());
-              c.swap(sT, sL0 + j);
-            }
-            c.mm1(c.s[sT], c.s[sR], c.s[sR], NoEpi());
-            c.swap(sT, sR);
-          }
-        } else {
-          for (int t = 0; t < sq; t++) {
-            c.mm1(c.s[sT], c.s[sR], c.s[sR], NoEpi());
-            c.swap(sT, sR);
-          }
-          for (int j = 0; j < nc; j++) {
-            slot_copy(c.s[sP].re, p.Ap + (size_t)j * slot_d, c.n2, c.tid, C::NTHREADS);
-            __syncthreads();
-            taylor_jacobian<C>(c, j, p.order);
-          }
+    // ---- part1(k): everything that does not need N^-1(k) ----
+    if (p.want_jac) {
+      if (taylor) {
+        for (int j = 0; j < nc; j++) {
+          taylor_jacobian<C>(c, c.E(j), c.s[sT], p.order);
+          slot_copy(p.L + (slice * nc + j) * slot_d, c.s[sT].re, c.n2, c.tid, C::NTHREADS);
+          c.cbar();
         }
       } else {
-        for (int t = 0; t < sq; t++) {
-          c.mm1(c.s[sT], c.s[sR], c.s[sR], NoEpi());
-          c.swap(sT, sR);
-        }
-      }
-
-      // ---- store U_k and dU_k/du_j (whole slots, coalesced; pads are zero) ----
-      slot_copy(p.U + slice * slot_d, c.s[sR].re, c.n2, c.tid, C::NTHREADS);
-      if (p.want_jac)
-        for (int j = 0; j < nc; j++)
-          slot_copy(p.L + (slice * nc + j) * slot_d, c.s[sL0 + j].re, c.n2, c.tid, C::NTHREADS);
-
-      // ---- level-1 scan: Q <- U_k Q ----
-      if (k == k0) {
-        slot_copy(c.s[sQ].re, c.s[sR].re, c.n2, c.tid, C::NTHREADS);
-        __syncthreads();
-      } else {
-        c.mm1(c.s[sT], c.s[sR], c.s[sQ], NoEpi());
-        c.swap(sT, sQ);
-      }
-
-      // F_alg bookkeeping: pi = 6 for q = 13
-      if (c.tid == 0) {
-        double G = 0.0;
-        if (p.want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0)
-                                   : (2.0 * 6 + 2.0 * sq + 2.0);
-        my_flops += M * ((6.0 + sq + 4.0 / 3.0) + nc * G);
+        // control 0 last: its (D, S) stay in (sM2, sLv), which the other controls' part1 uses as workspace (sM2)
+        for (int j = nc - 1; j >= 0; j--)
+          frechet13_part1<C>(c, c.E(j), j == 0 ? c.s[sM2] : Dh[j], j == 0 ? c.s[sLv] : Sh[j]);
       }
     }
-    slot_copy(p.Q + (size_t)seg * slot_d, c.s[sQ].re, c.n2, c.tid, C::NTHREADS);
-    __syncthreads();
+    QOC_STAMP(1);
+
+    // ---- software pipeline: generator and Pade denominator of the NEXT slice while N^-1(k) is being formed ----
+    WorkIter nx = it;
+    nx.next();
+    if (nx.valid()) {
+      sq = build_generator<C>(p, c, a0r, a0i, (size_t)nx.b * p.nt + nx.k, need_x, sc);
+      pade13_build_N<C>(c, c.s[sU0 + (par ^ 1)], c.s[sN0 + (par ^ 1)]);
+      bar_arrive(BAR_NREADY + (par ^ 1), NALL);
+    }
+    QOC_STAMP(2);
+
+    // ---- tail(k) ----
+    bar_sync(BAR_NINV + par, NALL);
+    QOC_STAMP(3);
+    Mat Ninv = c.s[sN0 + par], U = c.s[sU0 + par];
+    // R = N^-1 (V + U) = N^-1 (N + 2U) = I + 2 N^-1 U
+    Mat R = c.s[sT], tmp1 = c.s[sM6], tmp2 = c.s[sLw];
+    c.mm1(R, Ninv, U, c.epi(2.0, 0.0, U, 0.0, U, 0.0, U, 1.0));
+    if (p.want_jac && !taylor) {
+      Mat Lc[8];
+      for (int j = 0; j < nc; j++) {
+        Mat Dj = j == 0 ? c.s[sM2] : Dh[j], Sj = j == 0 ? c.s[sLv] : Sh[j];
+        // rhs = (Lu + Lv) + (Lu - Lv) R -> sM4 ;  L = 2^-s N^-1 rhs -> in place of D_j
+        c.mm1(c.s[sM4], Dj, R, c.epi(1.0, 1.0, Sj, 0.0, Sj, 0.0, Sj, 0.0));
+        c.mm1(Dj, Ninv, c.s[sM4], c.epi(scl, 0.0, Ninv, 0.0, Ninv, 0.0, Ninv, 0.0));
+        Lc[j] = Dj;
+      }
+      // squaring phase: L <- R L + L R ; R <- R R   (results ping-pong through tmp1 / tmp2)
+      for (int t = 0; t < sq_cur; t++) {
+        for (int j = 0; j < nc; j++) {
+          c.mm2(tmp1, R, Lc[j], Lc[j], R, NoEpi());
+          Mat x = tmp1; tmp1 = Lc[j]; Lc[j] = x;
+        }
+        c.mm1(tmp2, R, R, NoEpi());
+        Mat x = tmp2; tmp2 = R; R = x;
+      }
+      for (int j = 0; j < nc; j++) slot_copy(p.L + (slice * nc + j) * slot_d, Lc[j].re, c.n2, c.tid, C::NTHREADS);
+      // every slot touched here is dead once stored: hand the (permuted) physical slots back to their roles
+      c.s[sM2] = Lc[0];
+      for (int j = 1; j < nc; j++) Dh[j] = Lc[j];
+      c.s[sM6] = tmp1;
+    } else {
+      for (int t = 0; t < sq_cur; t++) {
+        c.mm1(tmp2, R, R, NoEpi());
+        Mat x = tmp2; tmp2 = R; R = x;
+      }
+    }
+    c.s[sT] = R; c.s[sLw] = tmp2;
+    slot_copy(p.U + slice * slot_d, R.re, c.n2, c.tid, C::NTHREADS);
+    QOC_STAMP(4);
+
+    // ---- level-1 scan: Q <- U_k Q ----
+    if (first_of_seg) {
+      slot_copy(c.s[sQ].re, R.re, c.n2, c.tid, C::NTHREADS);
+      c.cbar();
+    } else {
+      c.mm1(c.s[sM4], R, c.s[sQ], NoEpi());
+      c.swap(sM4, sQ);
+    }
+    if (last_of_seg) {
+      slot_copy(p.Q + (size_t)seg * slot_d, c.s[sQ].re, c.n2, c.tid, C::NTHREADS);
+      c.cbar();
+    }
+    if (c.tid == 0) {
+      double G = 0.0;
+      if (p.want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0)
+                                 : (2.0 * 6 + 2.0 * sq_cur + 2.0);
+      my_flops += M * ((6.0 + sq_cur + 4.0 / 3.0) + nc * G);
+    }
+    QOC_STAMP(5);
+    dbg_i++;
+    par ^= 1;
+    it = nx;
   }
-  if (c.tid == 0) {
-    if (my_flops != 0.0) atomicAdd(p.flops, my_flops);
-    if (!all_ok) atomicExch(p.status, 8);
-  }
+  if (c.tid == 0 && my_flops != 0.0) atomicAdd(p.flops, my_flops);
 }
 
 }  // namespace qoc

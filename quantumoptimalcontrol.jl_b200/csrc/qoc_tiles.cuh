@@ -34,7 +34,7 @@ struct Cfg {
   static constexpr int NBLK = NT_ * (NT_ / BN);       // warp blocks == warps that do DMMA work
   static constexpr int NW = NBLK;                      // warps per CTA in K1
   static constexpr int NTHREADS = NW * 32;
-  static constexpr int MAXE = (2 * NT_ * NT_ + NW - 1) / NW;  // matrix elements per thread in the GJ inverse
+  static constexpr int DMAX = (8 * NT_ < 4 * KS_) ? 8 * NT_ : 4 * KS_;  // largest d this class serves
 };
 
 template <int BN>
@@ -197,145 +197,6 @@ __device__ __forceinline__ void slot_copy_scaled(double* dst, const double* src,
     double2 v = ps[e];
     pd[e] = make_double2(v.x * sc, v.y * sc);
   }
-}
-
-// 1-norm (max column sum of |a_ij|) of a planar matrix; result broadcast to every thread.
-// scratch: >= 32 doubles of shared memory.  Contains two __syncthreads.
-template <int S>
-__device__ __forceinline__ double norm1(Mat a, int d, double* scratch, int tid, int nthreads) {
-  if (tid < 32) scratch[tid] = 0.0;
-  __syncthreads();
-  // thread handles (col, part): parts split the rows; columns up to 32
-  const int nparts = nthreads / 32 > 0 ? nthreads / 32 : 1;
-  const int col = tid & 31, part = tid >> 5;
-  double s = 0.0;
-  if (col < d) {
-    for (int r = part; r < d; r += nparts) {
-      double x = a.re[r * S + col], y = a.im[r * S + col];
-      s += sqrt(x * x + y * y);
-    }
-    // non-negative doubles order like their bit patterns, but we need a SUM over parts: use atomicAdd
-    atomicAdd(&scratch[col], s);
-  }
-  __syncthreads();
-  double mx = 0.0;
-  for (int c = 0; c < d; c++) mx = fmax(mx, scratch[c]);
-  return mx;
-}
-
-// In-place Gauss-Jordan inverse with partial (row) pivoting of a planar d x d matrix, CTA-wide.
-// The matrix lives in registers (MAXE elements per thread) for the whole elimination; per step only the pivot
-// row, the displaced row and the multiplier column are exchanged through shared memory (2 barriers / step).
-// buf: 5*d complex (rowbuf, oldk, colbuf[2]) + d ints.  Returns false (uniformly) if a pivot is exactly zero.
-template <class C>
-__device__ __forceinline__ bool gj_inverse(Mat a, int d, double2* buf, int tid) {
-  constexpr int S = C::S;
-  constexpr int NTH = C::NTHREADS;
-  constexpr int MAXE = C::MAXE;
-  double2* rowbuf = buf;
-  double2* oldk = buf + d;
-  double2* colbuf0 = buf + 2 * d;
-  int* idx = reinterpret_cast<int*>(buf + 4 * d);      // d ints: column bookkeeping
-  int* pivs = idx + 32;                                 // d ints
-  const int lane = tid & 31;
-
-  double vr[MAXE], vi[MAXE];
-  int ei[MAXE], ec[MAXE];
-#pragma unroll
-  for (int t = 0; t < MAXE; t++) {
-    int e = tid + t * NTH;
-    if (e < d * d) {
-      ei[t] = e / d;
-      ec[t] = e - ei[t] * d;
-      vr[t] = a.re[ei[t] * S + ec[t]];
-      vi[t] = a.im[ei[t] * S + ec[t]];
-    } else {
-      ei[t] = -1; ec[t] = -1; vr[t] = 0.0; vi[t] = 0.0;
-    }
-  }
-  bool ok = true;
-  for (int k = 0; k < d; k++) {
-    double2* colbuf = colbuf0 + (k & 1) * d;
-#pragma unroll
-    for (int t = 0; t < MAXE; t++)
-      if (ec[t] == k) colbuf[ei[t]] = make_double2(vr[t], vi[t]);
-    __syncthreads();
-    // every warp finds the pivot row redundantly (rows i >= k), d <= 32
-    double mag = -1.0;
-    int p = lane;
-    if (lane >= k && lane < d) {
-      double2 z = colbuf[lane];
-      mag = z.x * z.x + z.y * z.y;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      double om = __shfl_xor_sync(0xffffffffu, mag, off);
-      int op = __shfl_xor_sync(0xffffffffu, p, off);
-      if (om > mag || (om == mag && op < p)) { mag = om; p = op; }
-    }
-    if (!(mag > 0.0)) ok = false;
-    if (tid == 0) pivs[k] = p;
-    // publish pivot row (old row p) and the displaced row (old row k)
-#pragma unroll
-    for (int t = 0; t < MAXE; t++) {
-      if (ei[t] == p) rowbuf[ec[t]] = make_double2(vr[t], vi[t]);
-      if (ei[t] == k) oldk[ec[t]] = make_double2(vr[t], vi[t]);
-    }
-    __syncthreads();
-    const double2 pv = rowbuf[k];
-    const double den = 1.0 / (pv.x * pv.x + pv.y * pv.y);
-    const double pir = pv.x * den, pii = -pv.y * den;  // 1/pivot
-#pragma unroll
-    for (int t = 0; t < MAXE; t++) {
-      const int i = ei[t], c = ec[t];
-      if (i < 0) continue;
-      if (i == k) {
-        if (c == k) { vr[t] = pir; vi[t] = pii; }
-        else {
-          double2 r = rowbuf[c];
-          vr[t] = r.x * pir - r.y * pii;
-          vi[t] = r.x * pii + r.y * pir;
-        }
-      } else {
-        // after the swap row p holds old row k; every other row is itself
-        double sr = vr[t], si = vi[t];
-        double2 f = colbuf[i];
-        if (i == p) { double2 o = oldk[c]; sr = o.x; si = o.y; f = colbuf[k]; }
-        // g = f / pivot
-        const double gr = f.x * pir - f.y * pii, gi = f.x * pii + f.y * pir;
-        if (c == k) { vr[t] = -gr; vi[t] = -gi; }
-        else {
-          double2 r = rowbuf[c];
-          vr[t] = sr - (gr * r.x - gi * r.y);
-          vi[t] = si - (gr * r.y + gi * r.x);
-        }
-      }
-    }
-    // no barrier needed here: next step writes the other colbuf; rowbuf/oldk are rewritten only after the
-    // next step's first barrier, which every thread reaches after finishing this update.
-  }
-  __syncthreads();
-  // undo the row interchanges as column interchanges in reverse order: final column position of each column
-  if (tid == 0) {
-    for (int c = 0; c < d; c++) idx[c] = c;
-    for (int k = d - 1; k >= 0; k--) {
-      int p = pivs[k];
-      if (p != k) { int t = idx[k]; idx[k] = idx[p]; idx[p] = t; }
-    }
-    // idx[pos] = source column sitting at position pos; invert it in place into pivs
-    for (int pos = 0; pos < d; pos++) pivs[idx[pos]] = pos;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int t = 0; t < MAXE; t++) {
-    if (ei[t] >= 0) {
-      const int pos = pivs[ec[t]];
-      a.re[ei[t] * S + pos] = vr[t];
-      a.im[ei[t] * S + pos] = vi[t];
-    }
-  }
-  __syncthreads();
-  return ok;
 }
 
 }  // namespace qoc

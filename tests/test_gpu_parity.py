@@ -94,8 +94,8 @@ def test_known_answers_full_size(golden_dir):
 # ---- (2) oracle on the same seeded inputs ----------------------------------------------------------------------------
 @pytest.mark.parametrize("d,nt,nc,m,order", [
     (3, 17, 1, 1, 0), (4, 9, 2, 4, 3), (8, 33, 2, 8, 0), (9, 100, 2, 4, 4), (12, 40, 3, 2, 0), (13, 21, 1, 3, 2),
-    (16, 50, 2, 4, 0), (17, 30, 2, 1, 3), (20, 25, 1, 5, 0), (21, 19, 2, 2, 1), (24, 60, 2, 2, 0), (25, 14, 2, 4, 0),
-    (27, 80, 1, 1, 0), (28, 31, 2, 7, 3), (27, 1, 1, 1, 0), (9, 2, 2, 4, 0),
+    (16, 50, 2, 4, 0), (17, 30, 2, 1, 3), (20, 25, 1, 5, 0), (21, 19, 2, 2, 1), (24, 60, 2, 2, 0), (25, 14, 1, 4, 0), (23, 14, 2, 4, 0),
+    (27, 80, 1, 1, 0), (28, 31, 1, 7, 3), (24, 31, 2, 7, 3), (27, 1, 1, 1, 0), (9, 2, 2, 4, 0),
 ])
 def test_random_shapes_vs_oracle(d, nt, nc, m, order):
     """Ragged sizes across every shape class, incl. d not a multiple of 4/8, Nt = 1, m up to 8."""
@@ -106,6 +106,15 @@ def test_random_shapes_vs_oracle(d, nt, nc, m, order):
     assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-12
     assert np.abs(cache.x - co["x"]).max() < 1e-12
     assert np.abs(cache.lam - co["lam"]).max() < 1e-12
+
+
+def test_unsupported_sizes_fail_loudly():
+    """Sizes outside what the shared-memory-resident kernels cover must raise, never fall back."""
+    for d, nc in ((28, 2), (25, 2), (33, 1), (64, 2)):
+        cfg = o.config_synthetic(d, 4, nc=nc, m=2, seed=1)
+        with pytest.raises(q.QOCError) as ei:
+            gpu_eval(cfg, 0)
+        assert ei.value.status == _lib.ERR_UNSUPPORTED
 
 
 @pytest.mark.parametrize("scale", [1e-3, 0.3, 3.0, 11.0, 40.0])
