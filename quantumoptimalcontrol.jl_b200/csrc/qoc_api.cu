@@ -36,6 +36,8 @@ struct qoc_handle {
   int dbg_slices = 0;
   int* dstatus = nullptr;
   int *dpen_rows = nullptr, *dpen_cols = nullptr;
+  double *dcs = nullptr, *dJpen = nullptr;
+  unsigned row_mask = 0, col_mask = 0;
   // host state
   std::vector<double> last_u;
   bool have_u = false;       // a propagate() happened (cache valid)
@@ -153,7 +155,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
   cudaSetDevice(h->prob.device);
   double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
-                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS};
+                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->dstatus) cudaFree(h->dstatus);
@@ -177,7 +179,9 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   if (p.cost != QOC_COST_NONE && !T) { g_create_error = "built-in cost needs a target T"; return QOC_ERR_INVALID; }
   if (p.m > 8) { g_create_error = "m > 8 state columns not supported yet"; return QOC_ERR_UNSUPPORTED; }
   if (p.nc > 8) { g_create_error = "nc > 8 controls not supported yet"; return QOC_ERR_UNSUPPORTED; }
-  if (p.n_pen_rows > 0) { g_create_error = "running state penalty not supported yet"; return QOC_ERR_UNSUPPORTED; }
+  if ((p.n_pen_rows > 0) != (p.n_pen_cols > 0) || (p.n_pen_rows > 0 && (!p.pen_rows || !p.pen_cols))) {
+    g_create_error = "penalty index lists inconsistent"; return QOC_ERR_INVALID;
+  }
   const int cfg = pick_cfg(p.d);
   if (cfg < 0) { g_create_error = "d > 28 not supported yet by the shared-memory-resident kernels"; return QOC_ERR_UNSUPPORTED; }
 
@@ -195,6 +199,14 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   qoc_handle* h = new qoc_handle();
   h->prob = p;
   if (h->prob.n <= 0) h->prob.n = p.m;
+  for (int i = 0; i < p.n_pen_rows; i++) {
+    if (p.pen_rows[i] < 0 || p.pen_rows[i] >= p.d) { g_create_error = "penalty row index out of range"; delete h; return QOC_ERR_INVALID; }
+    h->row_mask |= 1u << p.pen_rows[i];
+  }
+  for (int i = 0; i < p.n_pen_cols; i++) {
+    if (p.pen_cols[i] < 0 || p.pen_cols[i] >= p.m) { g_create_error = "penalty column index out of range"; delete h; return QOC_ERR_INVALID; }
+    h->col_mask |= 1u << p.pen_cols[i];
+  }
   h->prob.pen_rows = nullptr;
   h->prob.pen_cols = nullptr;
   h->cfg = cfg;
@@ -269,6 +281,8 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   CR(cudaMalloc(&h->dg, nsl * p.nc * 8));
   CR(cudaMalloc(&h->dflops, 8));
   CR(cudaMalloc(&h->dS, slotB));
+  CR(cudaMalloc(&h->dcs, (size_t)h->nseg * dmB));
+  CR(cudaMalloc(&h->dJpen, (size_t)p.batch * 8));
   CR(cudaMalloc(&h->dstatus, 4));
   CR(cudaMemset(h->dstatus, 0, 4));
   CR(cudaMemset(h->dJ, 0, (size_t)p.batch * 8));
@@ -316,6 +330,8 @@ static K23Params base_k23(qoc_handle* h) {
   q.xs_start = h->dxs; q.lam_end = h->dle; q.X = h->dX; q.LAM = h->dLAM; q.x_final = h->dxf; q.lam_start = h->dlam0;
   q.J = h->dJ; q.dJdu = h->dg;
   q.store_costates = p.store_costates;
+  q.row_mask = h->row_mask; q.col_mask = h->col_mask; q.mu = p.mu; q.cs = h->dcs; q.Jpen = h->dJpen;
+  q.k3_mode = 0;
   return q;
 }
 
@@ -360,8 +376,9 @@ static int launch_k2(qoc_handle* h, int phase, bool no_backward, const double* d
   return QOC_OK;
 }
 
-static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d_dJdu, cudaStream_t st) {
+static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d_dJdu, cudaStream_t st, int mode = 0) {
   K23Params q = base_k23(h);
+  q.k3_mode = mode;
   q.want_grad = want_grad ? 1 : 0;
   q.store_states = store_states ? 1 : 0;
   if (d_dJdu) q.dJdu = d_dJdu;
@@ -376,6 +393,33 @@ static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d
   if (store_states) h->states_valid = true;
   if (want_grad && h->prob.store_costates) h->costates_valid = true;
   return QOC_OK;
+}
+
+static bool has_penalty(const qoc_handle* h) { return h->row_mask != 0u && h->col_mask != 0u && h->prob.mu != 0.0; }
+
+// Everything after K1.  Without a running penalty: K2 (forward, cost, backward) then K3.  With it the costate
+// recurrence is affine, lambda_k = U_k' lambda_{k+1} + dL_dx(x_k) (src/gradient_computations.jl:55-57), so the
+// segment-level scan needs the per-segment affine terms first:
+//   K2 forward -> K3 forward + pre-pass (c_s, sum L(x_k)) -> K2 cost + affine backward -> K3 forward + backward.
+static int run_sweeps(qoc_handle* h, bool want_grad, const double* d_lam_final, double* d_J, double* d_dJdu,
+                      bool store_states, cudaStream_t st) {
+  int rc;
+  const bool builtin = h->prob.cost != QOC_COST_NONE;
+  if (!has_penalty(h)) {
+    if (d_lam_final) rc = launch_k2(h, 2, false, d_lam_final, nullptr, nullptr, st);
+    else rc = launch_k2(h, builtin ? 0 : 1, !want_grad, nullptr, nullptr, d_J, st);
+    if (rc != QOC_OK) return rc;
+    if (want_grad || store_states) rc = launch_k3(h, want_grad, store_states, d_dJdu, st);
+    return rc;
+  }
+  QOC_CUDA(h, cudaMemsetAsync(h->dJpen, 0, (size_t)h->prob.batch * 8, st));
+  if ((rc = launch_k2(h, 1, true, nullptr, nullptr, nullptr, st)) != QOC_OK) return rc;      // forward boundary scan
+  if ((rc = launch_k3(h, false, store_states, nullptr, st, 1)) != QOC_OK) return rc;        // c_s and sum_k L(x_k)
+  if (d_lam_final) rc = launch_k2(h, 2, false, d_lam_final, nullptr, nullptr, st);           // affine backward
+  else rc = launch_k2(h, 3, !want_grad, nullptr, nullptr, d_J, st);                          // cost (+ affine backward)
+  if (rc != QOC_OK) return rc;
+  if (want_grad) rc = launch_k3(h, true, store_states, d_dJdu, st);
+  return rc;
 }
 
 static int check_status(qoc_handle* h) {
@@ -405,9 +449,14 @@ extern "C" int qoc_eval_device(qoc_handle* h, const double* d_u, double* d_J, do
   if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[0], st));
   if ((rc = launch_k1(h, d_u, true, st)) != QOC_OK) return rc;
   if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[1], st));
-  if ((rc = launch_k2(h, 0, false, nullptr, nullptr, d_J, st)) != QOC_OK) return rc;
-  if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[2], st));
-  if ((rc = launch_k3(h, true, h->prob.store_costates != 0, d_dJdu, st)) != QOC_OK) return rc;
+  if (!has_penalty(h)) {
+    if ((rc = launch_k2(h, 0, false, nullptr, nullptr, d_J, st)) != QOC_OK) return rc;
+    if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[2], st));
+    if ((rc = launch_k3(h, true, h->prob.store_costates != 0, d_dJdu, st)) != QOC_OK) return rc;
+  } else {
+    if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[2], st));  // K2 and K3 interleave: reported together as K3
+    if ((rc = run_sweeps(h, true, nullptr, d_J, d_dJdu, h->prob.store_costates != 0, st)) != QOC_OK) return rc;
+  }
   if (h->profiling) {
     QOC_CUDA(h, cudaEventRecord(h->ev[3], st));
     QOC_CUDA(h, cudaEventSynchronize(h->ev[3]));
@@ -461,8 +510,8 @@ extern "C" int qoc_propagate(qoc_handle* h, const double* u, double* J_out, doub
   int rc;
   // the Jacobians are produced together with U_k (they share the Pade powers): f_grad normally follows f
   if ((rc = launch_k1(h, h->du, true, h->stream)) != QOC_OK) return rc;
-  const bool builtin = p.cost != QOC_COST_NONE;
-  if ((rc = launch_k2(h, builtin ? 0 : 1, true, nullptr, nullptr, nullptr, h->stream)) != QOC_OK) return rc;
+  const bool builtin = p.cost != QOC_COST_NONE || has_penalty(h);  // J (or its penalty part) is formed on the device
+  if ((rc = run_sweeps(h, false, nullptr, nullptr, nullptr, false, h->stream)) != QOC_OK) return rc;
   if (J_out && builtin) QOC_CUDA(h, cudaMemcpyAsync(J_out, h->dJ, (size_t)p.batch * 8, cudaMemcpyDeviceToHost, h->stream));
   if (x_final_out)
     QOC_CUDA(h, cudaMemcpyAsync(x_final_out, h->dxf, (size_t)p.batch * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -493,13 +542,9 @@ extern "C" int qoc_gradient(qoc_handle* h, const double* u, const double* lambda
   if (!h->have_jac) {  // order changed since the propagation: redo K1 on the cached u (h->du still holds it)
     if ((rc = launch_k1(h, h->du, true, h->stream)) != QOC_OK) return rc;
   }
-  if (lambda_final) {
+  if (lambda_final)
     QOC_CUDA(h, cudaMemcpyAsync(h->dlamf, lambda_final, (size_t)p.batch * 2 * p.d * p.m * 8, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = launch_k2(h, 2, false, h->dlamf, nullptr, nullptr, h->stream)) != QOC_OK) return rc;
-  } else {
-    if ((rc = launch_k2(h, 0, false, nullptr, nullptr, nullptr, h->stream)) != QOC_OK) return rc;
-  }
-  if ((rc = launch_k3(h, true, true, nullptr, h->stream)) != QOC_OK) return rc;
+  if ((rc = run_sweeps(h, true, lambda_final ? h->dlamf : nullptr, nullptr, nullptr, true, h->stream)) != QOC_OK) return rc;
   QOC_CUDA(h, cudaMemcpyAsync(dJdu_out, h->dg, nu * 8, cudaMemcpyDeviceToHost, h->stream));
   QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   h->alg_flops += sweep_flops(p, true) - sweep_flops(p, false);

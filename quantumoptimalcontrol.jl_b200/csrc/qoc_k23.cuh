@@ -102,13 +102,46 @@ struct K23Params {
   double* J;                   // [batch]
   double* dJdu;                // nc x nt x batch
   int skip_cost;               // K2: forward only, J/lambda_N supplied later
-  int k2_phase;                // 0: forward + cost + backward; 1: forward only; 2: backward only
-  // running state penalty  src/penalty_fcns.jl:1-11
-  int n_pen_rows, n_pen_cols;
-  const int* pen_rows;
-  const int* pen_cols;
+  int k2_phase;                // 0: forward + cost + backward; 1: forward only; 2: backward only (lam_final);
+                               // 3: cost + backward starting from the stored x_final (penalty path)
+  // running state penalty  L(x) = mu * sum |x[pen_rows, pen_cols]|^2   src/penalty_fcns.jl:1-11
+  unsigned row_mask, col_mask;  // bit r / bit c set: row r / column c is penalised (d <= 32, m <= 8); 0 = no penalty
   double mu;
+  double* cs;                  // [nseg] d x m c128: affine term of the segment-level costate recurrence
+  double* Jpen;                // [batch] sum_k L(x_k), accumulated by K3 (atomicAdd)
+  int k3_mode;                 // 0: forward (+ backward + contraction if want_grad); 1: forward + penalty pre-pass
 };
+
+// mv_store variant that adds the penalty gradient 2 mu x[r][c] (src/penalty_fcns.jl:5-9) to the stored costate
+__device__ __forceinline__ void mv_store_pen(double* yr, double* yi, const double (&cr)[2], const double (&ci)[2], int d,
+                                             int m, int mi, int lane, const double* xr, const double* xi,
+                                             unsigned row_mask, unsigned col_mask, double two_mu) {
+  const int row = mi * 8 + (lane >> 2), col = 2 * (lane & 3);
+  if (row < d) {
+    const bool rp = (row_mask >> row) & 1u;
+    if (col < m) {
+      double a = cr[0], b = ci[0];
+      if (rp && ((col_mask >> col) & 1u)) { a = fma(two_mu, xr[row * m + col], a); b = fma(two_mu, xi[row * m + col], b); }
+      yr[row * m + col] = a; yi[row * m + col] = b;
+    }
+    if (col + 1 < m) {
+      double a = cr[1], b = ci[1];
+      if (rp && ((col_mask >> (col + 1)) & 1u)) { a = fma(two_mu, xr[row * m + col + 1], a); b = fma(two_mu, xi[row * m + col + 1], b); }
+      yr[row * m + col + 1] = a; yi[row * m + col + 1] = b;
+    }
+  }
+}
+
+// mu * sum |x[pen]|^2 of one state (thread-strided partial; caller reduces)
+__device__ __forceinline__ double penalty_partial(const double* xr, const double* xi, int d, int m, unsigned row_mask,
+                                                  unsigned col_mask, int tid, int nthreads) {
+  double s = 0.0;
+  for (int e = tid; e < d * m; e += nthreads) {
+    const int r = e / m, c = e - r * m;
+    if (((row_mask >> r) & 1u) && ((col_mask >> c) & 1u)) s += xr[e] * xr[e] + xi[e] * xi[e];
+  }
+  return s;
+}
 
 constexpr int K2_NST = 3;
 
@@ -138,7 +171,12 @@ __global__ void __launch_bounds__(C::NT * 32, 1) k2_kernel(K23Params p) {
   auto XR = [&](int w) { return xbuf + (size_t)w * 2 * dm; };
   auto XI = [&](int w) { return xbuf + (size_t)w * 2 * dm + dm; };
 
-  if (p.k2_phase != 2) {
+  const bool pen = (p.row_mask != 0u) && (p.col_mask != 0u);
+  if (p.k2_phase == 3) {
+    state_from_global(XR(0), XI(0), p.x_final + (size_t)b * 2 * dm, d, m, tid, NTH);
+    __syncthreads();
+  }
+  if (p.k2_phase != 2 && p.k2_phase != 3) {
     // ---------------- forward over segments ----------------
     const double* xin = p.x_start_ext ? p.x_start_ext + (size_t)b * 2 * dm : p.x0;
     state_from_global(XR(0), XI(0), xin, d, m, tid, NTH);
@@ -170,42 +208,64 @@ __global__ void __launch_bounds__(C::NT * 32, 1) k2_kernel(K23Params p) {
   if (p.k2_phase == 1) return;
 
   // ---------------- terminal cost and costate ----------------
-  // lambda_N -> buffer cur^1, then make it current
-  if (p.k2_phase == 2 || p.lam_final) {
-    state_from_global(XR(cur ^ 1), XI(cur ^ 1), p.lam_final + (size_t)b * 2 * dm, d, m, tid, NTH);
-  }
-  if (p.k2_phase != 2 && p.cost != 2) {
-    // Omega = tr(T' x) = sum conj(T) .* x      src/penalty_fcns.jl:16,20
+  // x_N is in buffer `cur`; lambda_N is assembled in buffer cur^1, which then becomes current.
+  //   lambda_N = dJfinal_dx(x_N) (+ dL_dx(x_N))                     src/gradient_computations.jl:46-49
+  //   J        = Jfinal(x_N) + sum_{k=0..N} L(x_k)                  examples/ipopt_callbacks_exp.jl:18
+  {
+    const bool have_x = (p.k2_phase != 2);                 // phase 2 has no forward pass in this launch
+    const bool builtin = have_x && p.cost != 2;
     if (tid < 4) red[tid] = 0.0;
+    if (!have_x && pen) state_from_global(XR(cur), XI(cur), p.x_final + (size_t)b * 2 * dm, d, m, tid, NTH);
     __syncthreads();
-    double orr = 0.0, oii = 0.0;
-    for (int e = tid; e < dm; e += NTH) {
-      const int c = e / d, r = e - c * d;
-      double2 t = reinterpret_cast<const double2*>(p.T)[e];
-      const double xr = XR(cur)[r * m + c], xi = XI(cur)[r * m + c];
-      orr += t.x * xr + t.y * xi;
-      oii += t.x * xi - t.y * xr;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      orr += __shfl_xor_sync(0xffffffffu, orr, off);
-      oii += __shfl_xor_sync(0xffffffffu, oii, off);
-    }
-    if (lane == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
-    __syncthreads();
-    const double Or = red[0], Oi = red[1];
-    const double nn = (double)p.n * (double)p.n;
-    double J, cr_, ci_;
-    if (p.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
-    else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
-    if (tid == 0 && p.J) p.J[b] = J;
-    if (!p.lam_final) {
+    double J = 0.0, cr_ = 0.0, ci_ = 0.0;
+    if (builtin) {
+      // Omega = tr(T' x) = sum conj(T) .* x      src/penalty_fcns.jl:16,20
+      double orr = 0.0, oii = 0.0;
       for (int e = tid; e < dm; e += NTH) {
         const int c = e / d, r = e - c * d;
         double2 t = reinterpret_cast<const double2*>(p.T)[e];
-        XR(cur ^ 1)[r * m + c] = cr_ * t.x - ci_ * t.y;
-        XI(cur ^ 1)[r * m + c] = cr_ * t.y + ci_ * t.x;
+        const double xr = XR(cur)[r * m + c], xi = XI(cur)[r * m + c];
+        orr += t.x * xr + t.y * xi;
+        oii += t.x * xi - t.y * xr;
       }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        orr += __shfl_xor_sync(0xffffffffu, orr, off);
+        oii += __shfl_xor_sync(0xffffffffu, oii, off);
+      }
+      if (lane == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
+    }
+    if (pen && p.k2_phase == 3) {
+      double ps = penalty_partial(XR(cur), XI(cur), d, m, p.row_mask, p.col_mask, tid, NTH);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+      if (lane == 0) atomicAdd(&red[2], ps);
+    }
+    __syncthreads();
+    if (builtin) {
+      const double Or = red[0], Oi = red[1];
+      const double nn = (double)p.n * (double)p.n;
+      if (p.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
+      else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
+    }
+    if (pen && p.k2_phase == 3) J += p.mu * red[2] + p.Jpen[b];
+    if (tid == 0 && p.J && (builtin || (pen && p.k2_phase == 3))) p.J[b] = J;
+    // terminal costate
+    if (p.lam_final) state_from_global(XR(cur ^ 1), XI(cur ^ 1), p.lam_final + (size_t)b * 2 * dm, d, m, tid, NTH);
+    for (int e = tid; e < dm; e += NTH) {
+      const int c = e / d, r = e - c * d;
+      double lr = 0.0, li = 0.0;
+      if (p.lam_final) { lr = XR(cur ^ 1)[r * m + c]; li = XI(cur ^ 1)[r * m + c]; }   // same thread wrote it above
+      else if (builtin) {
+        double2 t = reinterpret_cast<const double2*>(p.T)[e];
+        lr = cr_ * t.x - ci_ * t.y; li = cr_ * t.y + ci_ * t.x;
+      }
+      if (pen && ((p.row_mask >> r) & 1u) && ((p.col_mask >> c) & 1u)) {
+        lr = fma(2.0 * p.mu, XR(cur)[r * m + c], lr);
+        li = fma(2.0 * p.mu, XI(cur)[r * m + c], li);
+      }
+      XR(cur ^ 1)[r * m + c] = lr;
+      XI(cur ^ 1)[r * m + c] = li;
     }
   }
   cur ^= 1;
@@ -231,6 +291,14 @@ __global__ void __launch_bounds__(C::NT * 32, 1) k2_kernel(K23Params p) {
     Mat Qm; Qm.re = ring + (size_t)(i % K2_NST) * slot_d; Qm.im = Qm.re + d * S;
     double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
     mv_acc<C, true>(cr, ci, Qm, XR(cur), XI(cur), d, m, mi, lane);
+    if (pen && p.cs) {  // lambda_{k0} = Q' lambda_{k1} + c_s : the segment-level recurrence is affine with a penalty
+      const int row = mi * 8 + (lane >> 2), col = 2 * (lane & 3);
+      const double* cs = p.cs + (seg0 + sgi) * 2 * dm;
+      if (row < d) {
+        if (col < m) { cr[0] += cs[2 * (row + d * col)]; ci[0] += cs[2 * (row + d * col) + 1]; }
+        if (col + 1 < m) { cr[1] += cs[2 * (row + d * (col + 1))]; ci[1] += cs[2 * (row + d * (col + 1)) + 1]; }
+      }
+    }
     mv_store(XR(cur ^ 1), XI(cur ^ 1), cr, ci, d, m, mi, lane);
     cur ^= 1;
   }
@@ -251,7 +319,10 @@ __global__ void __launch_bounds__(C::NT * 32 * 3, 1) k3_kernel(K23Params p, int 
   const int d = p.d, m = p.m, nc = p.nc;
   const int slot_d = 2 * d * S, n2 = slot_d / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nstage_slots = p.want_grad ? (1 + nc) : 1;
+  const bool pen = (p.row_mask != 0u) && (p.col_mask != 0u);
+  const bool prepass = (p.k3_mode == 1);               // penalty pre-pass: affine term c_s and sum_k L(x_k)
+  const bool contract = p.want_grad && !prepass;        // full backward sweep with the gradient contraction
+  const int nstage_slots = contract ? (1 + nc) : 1;
   const int dm = d * m;
   double* ring = reinterpret_cast<double*>(smem_raw);
   double* tail = ring + (size_t)K3_NST * nstage_slots * slot_d;
@@ -304,13 +375,26 @@ __global__ void __launch_bounds__(C::NT * 32 * 3, 1) k3_kernel(K23Params p, int 
       const double* xr = xs + (size_t)(len - 1) * 2 * dm;
       state_to_global(p.X + ((size_t)b * (p.nt + 1) + k1 - 1) * 2 * dm, xr, xr + dm, d, m, tid, NTH);
     }
-    if (!p.want_grad) { __syncthreads(); continue; }
+    if (prepass) {
+      // sum_{k in segment} L(x_k), L(x) = mu sum |x[pen]|^2     src/penalty_fcns.jl:2-4
+      double ps = 0.0;
+      for (int i = 0; i < len; i++) {
+        const double* xr = xs + (size_t)i * 2 * dm;
+        ps += penalty_partial(xr, xr + dm, d, m, p.row_mask, p.col_mask, tid, NTH);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+      if (lane == 0 && ps != 0.0) atomicAdd(&p.Jpen[b], p.mu * ps);
+    }
+    if (!contract && !prepass) { __syncthreads(); continue; }
 
-    // ---------------- backward sweep + gradient contraction ----------------
+    // ---------------- backward sweep (+ gradient contraction) ----------------
+    // prepass: lambda' from a ZERO terminal value with the penalty source terms -> c_s = lambda'_{k0}
     int cur = 0;
     auto LR = [&](int w) { return lbuf + (size_t)w * 2 * dm; };
-    state_from_global(LR(0), LR(0) + dm, p.lam_end + (size_t)seg * 2 * dm, d, m, tid, NTH);
-    if (p.store_costates && p.LAM && k1 == p.nt)
+    if (prepass) { for (int e = tid; e < 2 * dm; e += NTH) LR(0)[e] = 0.0; }
+    else state_from_global(LR(0), LR(0) + dm, p.lam_end + (size_t)seg * 2 * dm, d, m, tid, NTH);
+    if (contract && p.store_costates && p.LAM && k1 == p.nt)
       for (int e = tid; e < dm; e += NTH)
         reinterpret_cast<double2*>(p.LAM + ((size_t)b * (p.nt + 1) + p.nt) * 2 * dm)[e] =
             reinterpret_cast<const double2*>(p.lam_end + (size_t)seg * 2 * dm)[e];
@@ -318,7 +402,8 @@ __global__ void __launch_bounds__(C::NT * 32 * 3, 1) k3_kernel(K23Params p, int 
       double* dst = ring + (size_t)(it % K3_NST) * nstage_slots * slot_d;
       const size_t sl = sl0 + (len - 1 - it);
       stage_slot(dst, p.U + sl * slot_d, n2, tid, NTH);
-      for (int j = 0; j < nc; j++) stage_slot(dst + (size_t)(1 + j) * slot_d, p.L + (sl * nc + j) * slot_d, n2, tid, NTH);
+      if (contract)
+        for (int j = 0; j < nc; j++) stage_slot(dst + (size_t)(1 + j) * slot_d, p.L + (sl * nc + j) * slot_d, n2, tid, NTH);
     };
     for (int i = 0; i < K3_NST - 1; i++) {
       if (i < len) stage_bwd(i);
@@ -328,7 +413,7 @@ __global__ void __launch_bounds__(C::NT * 32 * 3, 1) k3_kernel(K23Params p, int 
       const int k = k1 - 1 - it;
       cp_async_wait<K3_NST - 2>();
       __syncthreads();
-      if (it > 0 && tid < nc) {
+      if (contract && it > 0 && tid < nc) {
         double g = 0.0;
         for (int q = 0; q < NT; q++) g += part[(((it - 1) & 1) * nc + tid) * NT + q];
         p.dJdu[((size_t)b * p.nt + (k + 1)) * nc + tid] = g;
@@ -345,8 +430,13 @@ __global__ void __launch_bounds__(C::NT * 32 * 3, 1) k3_kernel(K23Params p, int 
         double cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
         mv_acc<C, true>(cr, ci, Um, lr, lr + dm, d, m, warp, lane);
         double* yr = LR(cur ^ 1);
-        mv_store(yr, yr + dm, cr, ci, d, m, warp, lane);
-      } else {
+        if (pen) {  // lambda_k = U_k' lambda_{k+1} + dL_dx(x_k)     src/gradient_computations.jl:55-57
+          const double* xk = xs + (size_t)(k - k0) * 2 * dm;
+          mv_store_pen(yr, yr + dm, cr, ci, d, m, warp, lane, xk, xk + dm, p.row_mask, p.col_mask, 2.0 * p.mu);
+        } else {
+          mv_store(yr, yr + dm, cr, ci, d, m, warp, lane);
+        }
+      } else if (contract) {
         const int ngrp = (NTH >> 5) / NT - 1, grp = warp / NT - 1, mi = warp - (grp + 1) * NT;
         const double* xr = xs + (size_t)(k - k0) * 2 * dm;
         const int row = mi * 8 + (lane >> 2), col = 2 * (lane & 3);
@@ -365,7 +455,7 @@ __global__ void __launch_bounds__(C::NT * 32 * 3, 1) k3_kernel(K23Params p, int 
           if (lane == 0) part[((it & 1) * nc + j) * NT + mi] = s;
         }
       }
-      if (p.store_costates && p.LAM) {
+      if (contract && p.store_costates && p.LAM) {
         // lambda_{k+1} is final; write it (lambda_{k1} was written above / by the next segment)
         if (it > 0) state_to_global(p.LAM + ((size_t)b * (p.nt + 1) + k + 1) * 2 * dm, lr, lr + dm, d, m, tid, NTH);
       }
@@ -373,6 +463,12 @@ __global__ void __launch_bounds__(C::NT * 32 * 3, 1) k3_kernel(K23Params p, int 
     }
     cp_async_wait<0>();
     __syncthreads();
+    if (prepass) {
+      const double* lr = LR(cur);
+      state_to_global(p.cs + (size_t)seg * 2 * dm, lr, lr + dm, d, m, tid, NTH);
+      __syncthreads();
+      continue;
+    }
     if (tid < nc) {
       double g = 0.0;
       for (int q = 0; q < NT; q++) g += part[(((len - 1) & 1) * nc + tid) * NT + q];

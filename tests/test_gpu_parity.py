@@ -268,3 +268,35 @@ def test_zz_batch_4096_properties():
         Jo, go, _ = o.evaluate(cfg, order=0, u=ub[b])
         assert_parity(Jb[b], gb[b], Jo, go)
     assert cache.launch_count() >= 3
+
+
+# ---- running state penalty (src/penalty_fcns.jl:1-11; affine costate recurrence, gradient_computations.jl:47-57) -------
+def test_state_penalty_golden_and_variants(golden_dir):
+    """test/test_gradient_computation.jl:105-132 set-up (zz_coupling, guard rows "20","21","22", order 4)."""
+    gd = np.load(os.path.join(golden_dir, "zz_penalty_order4.npz"))
+    cfg = o.config_zz()
+    rows, cols, mu = [6, 7, 8], [0, 1, 2, 3], 0.22
+    pen = q.setup_state_penalty(rows, cols, mu)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"])
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 100), dUkdp_order=4)
+    J, g = q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cost[1], dUkdp_order=4, penalty=pen)
+    assert_parity(J, g, float(gd["J"]), gd["dJdu"])
+    # reference-style two-step call with host closures for both the cost and the penalty
+    Jf, dJf = o.setup_infidelity(cfg["T"], cfg["n"])
+    c2 = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 100))
+    q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], c2, penalty=pen)
+    x = c2.x
+    Jtot = Jf(x[-1]) + sum(pen[0](xk) for xk in x)          # Jfinal(x[end]) + sum(L, x)
+    assert abs(Jtot - float(gd["J"])) <= TOL_J * max(1, abs(Jtot))
+    assert abs(c2.J - sum(pen[0](xk) for xk in x)) < 1e-12   # device-side running sum of the penalty alone
+    g2 = q.grape_sensitivity(cfg["A0"], cfg["A"], dJf, cfg["u"], cfg["x0"], c2, dUkdp_order=4, dL_dx=pen[1])
+    assert np.abs(g2 - gd["dJdu"]).max() <= TOL_G * np.abs(gd["dJdu"]).max()
+    # exact-Frechet mode with penalty, longer pulse split over many segments, vs the oracle
+    cfg = o.config_synthetic(12, 700, nc=2, m=3, seed=9)
+    pen2 = ([1, 5, 11], [0, 2], 0.37)
+    Jo, go, co = o.evaluate(cfg, order=0, penalty=pen2)
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 700), dUkdp_order=0)
+    J, g = q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], q.setup_infidelity(cfg["T"], cfg["n"])[1],
+                      dUkdp_order=0, penalty=q.setup_state_penalty(*pen2))
+    assert_parity(J, g, Jo, go)
+    assert np.abs(cache.lam - co["lam"]).max() < 1e-11
