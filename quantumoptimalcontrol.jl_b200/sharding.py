@@ -1,0 +1,205 @@
+"""Multi-GPU partitioning of the GRAPE evaluation: one process per GPU, torch.distributed (NCCL over NVLink on
+GPUs, gloo in the CPU tests) for the plumbing.  Two natural axes:
+
+  * pulse batch (multistart / parameter batch): pulses are block-partitioned over ranks, every rank evaluates its
+    block with its own handle; NO data-path collective (results are gathered only if the caller asks).
+  * one long pulse: contiguous time segments, slices [p*Nt/P, (p+1)*Nt/P) on rank p.
+        phase 1 (local)   U_k, dU_k/du_j for the local slices and the rank propagator S_p = U_last ... U_first
+        exchange          all-gather of the S_p  (P x 16 d^2 bytes)
+        phase 2 (local, boundary algebra redundant on every rank)
+                          x_start(p) = S_{p-1} ... S_0 x0,  x_N,  J,  lambda_N = dJ(x_N),
+                          lambda_end(p) = S_{p+1}' ... S_{P-1}' lambda_N,
+                          local forward / backward sweeps and the local gradient columns
+        exchange          all-gather of the nc x Nt/P gradient segments
+    This replaces the reference's serial loops src/gradient_computations.jl:27-29, :52-58, :65-74.
+    (The running state penalty makes the segment recurrence affine and needs a second exchange; it is supported
+    single-GPU only, as SURVEY.md section 7 plans.)
+
+The compute is delegated to a *segment engine* (phase1 / forward / backward).  The product engine is
+CudaSegmentEngine (C ABI, device pointers, no host round trip); the CPU tests plug in an oracle-backed engine to
+exercise exactly this host logic with world_size 2 under gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .grape import GrapeCache, QOCError, _BuiltinCost, COST_INFIDELITY, COST_ABS_TRACE
+
+__all__ = ["block_partition", "time_partition", "CudaSegmentEngine", "TimeShardedEvaluator", "evaluate_batch_sharded"]
+
+
+def block_partition(n: int, world: int, rank: int):
+    """Contiguous block [lo, hi) of n items for `rank` (sizes differ by at most one)."""
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    return lo, hi
+
+
+def time_partition(nt: int, world: int, rank: int):
+    """Slices [lo, hi) of a pulse of nt slices owned by `rank` ([p*Nt/P, (p+1)*Nt/P))."""
+    return block_partition(nt, world, rank)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# engines
+# ----------------------------------------------------------------------------------------------------------------------
+class CudaSegmentEngine:
+    """Local time segment on one B200 through the C ABI (qoc_shard_*_device).  Tensors stay in HBM."""
+
+    def __init__(self, A0, A, nt_local, m, device_index=0, order=0):
+        self.d, self.m, self.nc, self.nt = A0.shape[0], m, len(A), nt_local
+        self.device = torch.device("cuda", device_index)
+        self.cache = GrapeCache(A0, np.zeros((self.d, m), dtype=np.complex128), (self.nc, nt_local), batch=1,
+                                device=device_index, dUkdp_order=order, store_costates=False)
+        self.cache._ensure(A0, A, np.zeros((self.d, m), dtype=np.complex128))
+        self.lib = _lib.load()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise QOCError(rc, self.lib.qoc_last_error(self.cache.handle).decode())
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr())
+
+    def phase1(self, u_local):
+        """u_local: (nc, nt_local) float64 (numpy or tensor).  -> S_p as a (d, d) complex128 tensor on the GPU."""
+        u = torch.as_tensor(np.ascontiguousarray(np.asarray(u_local, dtype=np.float64).T)).to(self.device)  # [k][j]
+        S_cm = torch.empty((self.d, self.d), dtype=torch.complex128, device=self.device)  # column-major memory
+        self._check(self.lib.qoc_shard_phase1_device(self.cache.handle, self._ptr(u), self._ptr(S_cm),
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self._u = u
+        return S_cm.t()  # logical (row, col) view of the column-major buffer
+
+    def forward(self, x_start):
+        xs = x_start.t().contiguous()  # (m, d) row-major == d x m column-major
+        xe = torch.empty_like(xs)
+        self._check(self.lib.qoc_shard_forward_device(self.cache.handle, self._ptr(xs), self._ptr(xe),
+                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return xe.t()
+
+    def backward(self, lam_end):
+        le = lam_end.t().contiguous()
+        ls = torch.empty_like(le)
+        g = torch.empty((self.nt, self.nc), dtype=torch.float64, device=self.device)
+        self._check(self.lib.qoc_shard_backward_device(self.cache.handle, self._ptr(le), self._ptr(g), self._ptr(ls),
+                                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return g.t(), ls.t()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one long pulse, time-segment sharded
+# ----------------------------------------------------------------------------------------------------------------------
+def _builtin_cost_torch(cost, x):
+    """J and dJ_dx of the library's built-in costs on a torch tensor (boundary algebra; identical on every rank)."""
+    T = torch.as_tensor(np.ascontiguousarray(cost.T), device=x.device)
+    om = torch.sum(torch.conj(T) * x)
+    if cost.kind == COST_INFIDELITY:  # src/penalty_fcns.jl:15-24
+        n2 = float(cost.n) ** 2
+        return float(1 - (om.real ** 2 + om.imag ** 2) / n2), (-2 * om / n2) * T
+    if cost.kind == COST_ABS_TRACE:   # test/test_gradient_computation.jl:24-25
+        a = torch.abs(om)
+        return float(1 - a), -(om / a) * T
+    raise ValueError("unknown built-in cost")
+
+
+class TimeShardedEvaluator:
+    """Fidelity + gradient of ONE pulse whose Nt slices are split over the ranks of `group`."""
+
+    def __init__(self, engine, x0, cost, nt_total, group=None):
+        self.engine, self.cost, self.nt_total, self.group = engine, cost, nt_total, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = getattr(engine, "device", torch.device("cpu"))
+        self.x0 = torch.as_tensor(np.asarray(x0, dtype=np.complex128).reshape(np.asarray(x0).shape[0], -1)).to(self.device)
+        self.lo, self.hi = time_partition(nt_total, self.world, self.rank)
+
+    def _all_gather(self, t):
+        if self.world == 1:
+            return [t]
+        t = t.contiguous()
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return out
+
+    def evaluate(self, u_full):
+        """u_full: (nc, Nt) on every rank (only the local columns are used).  -> (J, dJdu (nc, Nt) numpy)."""
+        u_full = np.asarray(u_full, dtype=np.float64)
+        u_loc = u_full[:, self.lo:self.hi]
+        # phase 1 + exchange of the boundary propagators
+        S = self._all_gather(self.engine.phase1(u_loc))
+        # boundary algebra (redundant on every rank; P small products of d x d by d x m)
+        x = self.x0
+        x_start = None
+        for p in range(self.world):
+            if p == self.rank:
+                x_start = x
+            x = S[p] @ x
+        x_N = x
+        if isinstance(self.cost, _BuiltinCost):
+            J, lam = _builtin_cost_torch(self.cost, x_N)
+        else:  # arbitrary host closures (J, dJ_dx) like the reference's
+            Jf, dJf = self.cost
+            xh = x_N.cpu().numpy()
+            J = float(Jf(xh))
+            lam = torch.as_tensor(np.asarray(dJf(xh), dtype=np.complex128)).to(self.device)
+        lam_end = None
+        for p in range(self.world - 1, -1, -1):
+            if p == self.rank:
+                lam_end = lam
+            lam = S[p].conj().t() @ lam
+        # phase 2: local sweeps
+        self.engine.forward(x_start)
+        g_loc, _ = self.engine.backward(lam_end)
+        # gradient segments: ranks may own different numbers of slices -> pad to the longest
+        nmax = max(time_partition(self.nt_total, self.world, r)[1] - time_partition(self.nt_total, self.world, r)[0]
+                   for r in range(self.world))
+        nc = u_full.shape[0]
+        pad = torch.zeros((nc, nmax), dtype=torch.float64, device=self.device)
+        pad[:, : self.hi - self.lo] = g_loc
+        parts = self._all_gather(pad)
+        g = np.zeros((nc, self.nt_total))
+        for r in range(self.world):
+            lo, hi = time_partition(self.nt_total, self.world, r)
+            g[:, lo:hi] = parts[r][:, : hi - lo].cpu().numpy()
+        return J, g
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# independent pulses, batch sharded (no data-path collective)
+# ----------------------------------------------------------------------------------------------------------------------
+def evaluate_batch_sharded(eval_local, u_batch, group=None, gather=True):
+    """u_batch: (B, nc, Nt) identical on every rank.  eval_local(u_block) -> (J (b,), dJdu (b, nc, Nt)) evaluates this
+    rank's block.  With gather=True the per-rank results are all-gathered so every rank returns the full (J, dJdu)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = u_batch.shape[0]
+    lo, hi = block_partition(B, world, rank)
+    J_loc, g_loc = eval_local(u_batch[lo:hi]) if hi > lo else (np.zeros(0), np.zeros((0,) + u_batch.shape[1:]))
+    if not gather or world == 1:
+        return np.asarray(J_loc), np.asarray(g_loc), (lo, hi)
+    nmax = max(block_partition(B, world, r)[1] - block_partition(B, world, r)[0] for r in range(world))
+    padJ = torch.zeros(nmax, dtype=torch.float64)
+    padg = torch.zeros((nmax,) + tuple(u_batch.shape[1:]), dtype=torch.float64)
+    padJ[: hi - lo] = torch.as_tensor(np.asarray(J_loc, dtype=np.float64))
+    padg[: hi - lo] = torch.as_tensor(np.asarray(g_loc, dtype=np.float64))
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        padJ, padg = padJ.to(dev), padg.to(dev)
+    outJ = [torch.empty_like(padJ) for _ in range(world)]
+    outg = [torch.empty_like(padg) for _ in range(world)]
+    dist.all_gather(outJ, padJ, group=group)
+    dist.all_gather(outg, padg, group=group)
+    J = np.zeros(B)
+    g = np.zeros(u_batch.shape)
+    for r in range(world):
+        l, h = block_partition(B, world, r)
+        J[l:h] = outJ[r][: h - l].cpu().numpy()
+        g[l:h] = outg[r][: h - l].cpu().numpy()
+    return J, g, (lo, hi)

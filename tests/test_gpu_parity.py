@@ -300,3 +300,43 @@ def test_state_penalty_golden_and_variants(golden_dir):
                       dUkdp_order=0, penalty=q.setup_state_penalty(*pen2))
     assert_parity(J, g, Jo, go)
     assert np.abs(cache.lam - co["lam"]).max() < 1e-11
+
+
+# ---- time-segment sharding through the C ABI phase API (one GPU, virtual ranks; real ranks: bench.py --shard time) -----
+def test_time_sharding_virtual_ranks_on_one_gpu():
+    """P contiguous time segments, one all-gather of the rank propagators, redundant boundary algebra.
+    Here the P ranks are emulated sequentially on one GPU (a single exchange step, no kernel waits on another)."""
+    import torch
+    from qoc_b200 import sharding
+    cfg = o.config_bus(Nt=1003, tgate=35.105)        # 1003 slices: uneven segments
+    P = 4
+    Jo, go, co = o.evaluate(cfg, order=0)
+    engines, S = [], []
+    for r in range(P):
+        lo, hi = sharding.time_partition(1003, P, r)
+        e = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, cfg["x0"].shape[1], 0, order=0)
+        S.append(e.phase1(cfg["u"][:, lo:hi]).clone())
+        engines.append(e)
+    dev = engines[0].device
+    x = torch.as_tensor(cfg["x0"]).to(dev)
+    starts = []
+    for r in range(P):
+        starts.append(x)
+        x = S[r] @ x
+    assert np.abs(x.cpu().numpy() - co["x"][-1]).max() < 1e-11
+    J, lam = sharding._builtin_cost_torch(q.setup_infidelity(cfg["T"], cfg["n"])[1], x)
+    assert abs(J - Jo) <= TOL_J
+    g = np.zeros_like(go)
+    for r in range(P - 1, -1, -1):
+        lo, hi = sharding.time_partition(1003, P, r)
+        xe = engines[r].forward(starts[r])
+        gl, lam_next = engines[r].backward(lam)
+        g[:, lo:hi] = gl.cpu().numpy()
+        assert np.abs(lam_next.cpu().numpy() - co["lam"][lo]).max() < 1e-11
+        lam = S[r].conj().t() @ lam
+    assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+    # and the evaluator class itself with world_size 1
+    ev = sharding.TimeShardedEvaluator(sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], 1003, 1, 0, order=0), cfg["x0"],
+                                       q.setup_infidelity(cfg["T"], cfg["n"])[1], 1003)
+    J1, g1 = ev.evaluate(cfg["u"])
+    assert_parity(J1, g1, Jo, go)
