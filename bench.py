@@ -171,6 +171,57 @@ def run_reference(args):
     return 0
 
 
+def run_time_sharded(args, rank, world, local_rank, order):
+    """ONE pulse of the workload split into `world` contiguous time segments: per step, phase 1 on the
+    local slices, NCCL all-gather of the d x d rank propagators, redundant boundary algebra, local sweeps, all-gather of
+    the gradient segments.  Strong scaling: total work is fixed."""
+    import torch
+    import torch.distributed as dist
+    import qoc_b200 as q
+    from qoc_b200 import sharding
+    cfg, u, batch, desc = build_workload(args.workload, 0, args.mode)
+    if batch != 1:
+        raise SystemExit("--shard time needs a single-pulse workload")
+    nt = u.shape[1]
+    lo, hi = sharding.time_partition(nt, world, rank)
+    eng = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, cfg["x0"].shape[1], local_rank, order=order)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"])[1] if cfg["cost"] == 0 else q.setup_infidelity_abs_trace(cfg["T"])[1]
+    ev = sharding.TimeShardedEvaluator(eng, cfg["x0"], cost, nt)
+    for _ in range(args.warmup):
+        J, g = ev.evaluate(u)
+    dist.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        J, g = ev.evaluate(u)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    value = nt * args.steps / (ms * 1e-3)
+    if rank == 0:
+        d = cfg["A0"].shape[0]
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc.replace("per GPU", "time-sharded over all GPUs"), "mode": args.mode,
+                       "parallelism": f"time-segment sharded x{world}: all-gather of {world} rank propagators "
+                                      f"({16 * d * d} B each) + all-gather of gradient segments per step"},
+            "clocks": clocks,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * u[:, lo:hi].size),
+                    "d2h_bytes_per_step": int(8 * u.size + 8),
+                    "note": "the sharded evaluator is host-driven: u enters from host memory and J, dJdu return to it every step"},
+            "gpu_launches": int(5 * args.steps * world), "J": J}))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +231,9 @@ def main():
     ap.add_argument("--mode", default="frechet", choices=["frechet", "taylor3"])
     ap.add_argument("--workload", default="bus", choices=["bus", "zz_batch", "cavity"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="batch", choices=["batch", "time"],
+                    help="N>1: 'batch' = one pulse per rank, no collective (weak scaling, default); "
+                         "'time' = ONE pulse split into time segments, NCCL all-gather of rank propagators (strong scaling)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -202,6 +256,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     order = 0 if args.mode == "frechet" else 3
+    if args.shard == "time" and world > 1:
+        return run_time_sharded(args, rank, world, local_rank, order)
     cfg, u, batch, desc = build_workload(args.workload, rank, args.mode)
     nc, nt = u.shape[-2], u.shape[-1]
     lib = _lib.load()
@@ -309,7 +365,7 @@ def main():
            "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(u_host.nbytes),
                    "d2h_bytes_per_step": int(J_pin.numel() * 8 + g_pin.numel() * 8), "ms_per_step": 1e3 * e2e_s / args.steps},
-           "gpu_launches": int(launches_per_step * args.steps),
+           "gpu_launches": int(launches_per_step * args.steps * world),
            "roofline": roofline}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         slices, times, nth, npulse = cpu_port_run(cfg, u, batch, order, 0, 3)
