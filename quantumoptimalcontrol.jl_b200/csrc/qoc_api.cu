@@ -34,6 +34,7 @@ struct qoc_handle {
   double *dS = nullptr;
   long long* dbg = nullptr;  // developer timeline buffer (qoc_debug_k1_timeline)
   int dbg_slices = 0;
+  int dbg_flags = 0;
   int* dstatus = nullptr;
   int *dpen_rows = nullptr, *dpen_cols = nullptr;
   double *dcs = nullptr, *dJpen = nullptr;
@@ -93,9 +94,9 @@ static auto with_cfg(int cfg, F f) {
   }
 }
 
-static size_t k1_smem_bytes(int d, int nc, int S) {
+static size_t k1_smem_bytes(int d, int nc, int S, int pad_rows) {
   const size_t slot = (size_t)2 * d * S * 8;
-  return (size_t)k1_num_slots(nc) * slot + (size_t)8 * S * 8 + sizeof(SvcScratch) + 64;
+  return (size_t)k1_num_slots(nc) * slot + (size_t)pad_rows * S * 8 + sizeof(SvcScratch) + 16;
 }
 static size_t k2_smem_bytes(int d, int m, int S) {
   const size_t slot = (size_t)2 * d * S * 8;
@@ -218,7 +219,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     h->S = C::S;
     h->slot_d = 2 * p.d * C::S;
     h->k1_threads = C::NTHREADS;
-    h->k1_smem = k1_smem_bytes(p.d, p.nc, C::S);
+    h->k1_smem = k1_smem_bytes(p.d, p.nc, C::S, k1_pad_rows<C>(p.d));
     h->k2_smem = k2_smem_bytes(p.d, p.m, C::S);
     if (h->k1_smem > (size_t)dp.sharedMemPerBlockOptin) {
       g_create_error = "K1 working set (16+2*nc matrices) exceeds shared memory for this d / nc";
@@ -343,7 +344,7 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   k.A0p = h->dA0p; k.Ap = h->dAp; k.u = d_u; k.U = h->dU; k.L = h->dL; k.Q = h->dQ;
   k.flops = h->dflops; k.status = h->dstatus;
   k.theta13 = (p.order == QOC_ORDER_FRECHET) ? 4.74 : 5.4;
-  k.dbg = h->dbg; k.dbg_slices = h->dbg_slices;
+  k.dbg = h->dbg; k.dbg_slices = h->dbg_slices; k.dbg_flags = h->dbg_flags;
   QOC_CUDA(h, cudaMemsetAsync(h->dflops, 0, 8, st));
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
@@ -681,13 +682,17 @@ extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_e
 extern "C" int qoc_debug_k1_timeline(qoc_handle* h, long long* out, int nslices, int want_jac) {
   if (!h || !out || nslices <= 0 || !h->have_u) return QOC_ERR_INVALID;
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
-  QOC_CUDA(h, cudaMalloc(&h->dbg, sizeof(long long) * 16 * nslices));
-  QOC_CUDA(h, cudaMemset(h->dbg, 0, sizeof(long long) * 16 * nslices));
+  QOC_CUDA(h, cudaMalloc(&h->dbg, sizeof(long long) * (16 * nslices + 4096)));
+  QOC_CUDA(h, cudaMemset(h->dbg, 0, sizeof(long long) * (16 * nslices + 4096)));
   h->dbg_slices = nslices;
+  h->dbg_flags = 0;
+  if (want_jac >= 8) { h->dbg_flags |= 4; want_jac -= 8; }  // timing experiment: skip the U_k / dU_k stores
+  if (want_jac >= 4) { h->dbg_flags |= 2; want_jac -= 4; }  // also record one stamp per compute-warp barrier
+  if (want_jac >= 2) { h->dbg_flags |= 1; want_jac -= 2; }  // timing experiment: skip the inverse (results invalid)
   int rc = launch_k1(h, h->du, want_jac != 0, h->stream);
   cudaStreamSynchronize(h->stream);
-  if (rc == QOC_OK) cudaMemcpy(out, h->dbg, sizeof(long long) * 16 * nslices, cudaMemcpyDeviceToHost);
+  if (rc == QOC_OK) cudaMemcpy(out, h->dbg, sizeof(long long) * (16 * nslices + ((h->dbg_flags & 2) ? 4096 : 0)), cudaMemcpyDeviceToHost);
   cudaFree(h->dbg);
-  h->dbg = nullptr; h->dbg_slices = 0;
+  h->dbg = nullptr; h->dbg_slices = 0; h->dbg_flags = 0;
   return rc;
 }

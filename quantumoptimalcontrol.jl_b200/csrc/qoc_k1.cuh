@@ -39,6 +39,7 @@ struct K1Params {
   double theta13;          // scaling threshold: 5.4 (Higham-2005 / reference) or 4.74 (Frechet, Al-Mohy-Higham)
   long long* dbg;          // optional timeline of CTA 0: [slice][16] clock64 stamps (NULL in production)
   int dbg_slices;
+  int dbg_flags;           // bit 0: skip the service inverse (timing experiment, results invalid)
 };
 #define QOC_STAMP(idx)                                                                     \
   do {                                                                                     \
@@ -57,6 +58,11 @@ enum : int { sA = 0, sA2, sA4, sA6, sWZ, sW, sU0, sU1, sN0, sN1, sM2, sM4, sM6, 
 // then nc slots E_j (control operators, resident for the whole kernel) and, for every control after the first, two
 // slots that carry (Lu - Lv, Lu + Lv) of that control from part1 to the tail
 __host__ __device__ constexpr int k1_num_slots(int nc) { return K1_FIXED_SLOTS + nc + 2 * (nc - 1); }
+// rows of zero padding needed behind the last slot: tile loads touch rows < 8*NT and k-steps rows < 4*KS
+template <class C>
+__host__ __device__ constexpr int k1_pad_rows(int d) {
+  return ((8 * C::NT > 4 * C::KS ? 8 * C::NT : 4 * C::KS) - d + 1) & ~1;  // even: keeps 16-byte alignment (S is even anyway)
+}
 
 // named barriers: 1 = compute warps, 7 = service warps, 2/3 = "N ready" (even/odd slice), 4/5 = "N^-1 ready"
 enum : int { BAR_C = 1, BAR_NREADY = 2, BAR_NINV = 4 };
@@ -65,6 +71,17 @@ __device__ __forceinline__ void bar_arrive(int id, int n) {
   __threadfence_block();
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
+
+// Asynchronous shared -> global bulk copy (TMA, SASS UBLKCP): one thread issues it, the copy engine streams the slot out
+// while the warps go on.  The source slot may be overwritten once bulk_wait_read() has returned.
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // the sequence of (segment, slice) work items of one CTA; both roles walk it identically
 struct WorkIter {
@@ -97,10 +114,15 @@ struct K1Ctx {
   int slot_d;
   int d, n2;                 // n2 = double2 per slot
   int tid, lane, warp, mi, nj0;
+  long long* stamp = nullptr;  // developer timeline: one clock64 per compute-warp barrier (CTA 0, warp 0 only)
+  int stamp_left = 0;
+  __device__ __forceinline__ void mark() {
+    if (stamp_left > 0) { if (lane == 0) *stamp = clock64(); stamp++; stamp_left--; }
+  }
 
   __device__ __forceinline__ Mat E(int j) const { Mat m; m.re = E0.re + (size_t)j * slot_d; m.im = E0.im + (size_t)j * slot_d; return m; }
   __device__ __forceinline__ Mat extra(int i) const { Mat m; m.re = X0.re + (size_t)i * slot_d; m.im = X0.im + (size_t)i * slot_d; return m; }
-  __device__ __forceinline__ void cbar() const { bar_sync(BAR_C, C::NTHREADS); }
+  __device__ __forceinline__ void cbar() { bar_sync(BAR_C, C::NTHREADS); mark(); }
 
   // dst = epilogue(sum of products); one compute-warp barrier at the end
   template <class F>
@@ -212,7 +234,7 @@ struct SvcScratch {
   int pidx[2];
   int ok;             // cleared to 0 by a service warp that meets a zero pivot
   int pad_;
-  float colsum[12][32];  // per-warp partial column sums of the generator build (compute warps)
+  float colsum[22][32];  // partial column sums of the generator build, one row per row group (compute warps)
 };
 
 __device__ __forceinline__ void bar_svc() { asm volatile("bar.sync %0, %1;" ::"r"(7), "r"(NSW * 32) : "memory"); }
@@ -313,28 +335,34 @@ __device__ __noinline__ bool service_inverse(Mat N, int d, SvcScratch* sc, int s
 // ---------------------------------------------------------------------------------------------------------------------
 
 // X = A0 + sum_j u_j E_j -> sA scaled by 2^-s (and unscaled -> sX for the Taylor mode); returns s (uniform).
-// A0 is constant over the whole launch: each thread keeps its elements in registers (a0r/a0i, one double2 of the real
-// and of the imaginary plane per iteration), the control operators are shared-memory resident, so assembling a
-// generator touches no global memory except the nc control amplitudes.
+// A0 is constant over the whole launch: each thread keeps its elements in registers, the control operators are
+// shared-memory resident, so assembling a generator touches no global memory except the nc control amplitudes
+// (passed in, prefetched by the caller).  Thread t owns column pair cp = t % (S/2) of the rows r0, r0 + G
+// (r0 = t / (S/2), G = row groups), so the partial column sums of the 1-norm need no atomics.
+template <class C>
+struct GenMap {
+  static constexpr int S2 = C::S / 2;              // double2 per row
+  static constexpr int G = (C::NTHREADS / S2 < 22) ? C::NTHREADS / S2 : 22;  // row groups (scratch holds 22)
+  static constexpr int RPT = (C::DMAX + G - 1) / G;  // rows per thread (1 or 2)
+};
+
 template <class C>
 __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, const double2 (&a0r)[2], const double2 (&a0i)[2],
-                                               size_t slice, bool need_x, SvcScratch* sc) {
+                                               const double (&uj)[8], bool need_x, SvcScratch* sc) {
+  typedef GenMap<C> GM;
+  static_assert(GM::RPT <= 2 && GM::G <= 22, "generator mapping");
   constexpr int S = C::S;
-  const int d = c.d, nc = p.nc, h2 = c.n2 / 2;  // h2 = double2 per plane
-  double uj[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) uj[j] = (j < nc) ? __ldg(p.u + slice * nc + j) : 0.0;
-  // 1-norm in single precision (it only picks the number of squarings): every warp accumulates partial column sums
-  // of |x_ij| in its own row of the scratch (<= 3 lanes of a warp share a column), then all warps combine them
-  float* mycs = sc->colsum[c.warp];
-  mycs[c.lane] = 0.f;
-  __syncwarp();
+  const int d = c.d, nc = p.nc;
+  const int cp = c.tid % GM::S2, r0 = c.tid / GM::S2;
+  const bool act = r0 < GM::G;
   double2 xr[2], xi[2];
+  float cs0 = 0.f, cs1 = 0.f;
 #pragma unroll
-  for (int t = 0; t < 2; t++) {
-    const int e = c.tid + t * C::NTHREADS;
+  for (int t = 0; t < GM::RPT; t++) {
+    const int r = r0 + t * GM::G;
     xr[t] = a0r[t]; xi[t] = a0i[t];
-    if (e < h2) {
+    if (act && r < d) {
+      const int e = r * GM::S2 + cp;
 #pragma unroll
       for (int j = 0; j < 8; j++)
         if (j < nc) {
@@ -343,29 +371,33 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
           xr[t].x = fma(uj[j], wr.x, xr[t].x); xr[t].y = fma(uj[j], wr.y, xr[t].y);
           xi[t].x = fma(uj[j], wi.x, xi[t].x); xi[t].y = fma(uj[j], wi.y, xi[t].y);
         }
-      const int col = (2 * e) % S;
+      // 1-norm in single precision (it only picks the number of squarings)
       const float ax = (float)xr[t].x, bx = (float)xi[t].x, ay = (float)xr[t].y, by = (float)xi[t].y;
-      if (col < d) atomicAdd(&mycs[col], sqrtf(ax * ax + bx * bx));
-      if (col + 1 < d) atomicAdd(&mycs[col + 1], sqrtf(ay * ay + by * by));
+      const float m0 = ax * ax + bx * bx, m1 = ay * ay + by * by;
+      cs0 += m0 * __frsqrt_rn(fmaxf(m0, 1e-37f));
+      cs1 += m1 * __frsqrt_rn(fmaxf(m1, 1e-37f));
     }
   }
+  if (act) *reinterpret_cast<float2*>(&sc->colsum[r0][2 * cp]) = make_float2(cs0, cs1);
   c.cbar();
   int sq = 0;
   {
-    constexpr int NP = C::NTHREADS / 32;
     float ps = 0.f;
-#pragma unroll
-    for (int q = 0; q < NP; q++) ps += sc->colsum[q][c.lane];
+    if (c.lane < d) {
+#pragma unroll 4
+      for (int g = 0; g < GM::G; g++) ps += sc->colsum[g][c.lane];
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ps = fmaxf(ps, __shfl_xor_sync(0xffffffffu, ps, off));
     float t = (float)p.theta13;
     while (ps > t && sq < 60) { t *= 2.f; sq++; }
   }
-  const double scl = ldexp(1.0, -sq);
+  const double scl = __hiloint2double((1023 - sq) << 20, 0);  // 2^-sq exactly
 #pragma unroll
-  for (int t = 0; t < 2; t++) {
-    const int e = c.tid + t * C::NTHREADS;
-    if (e < h2) {
+  for (int t = 0; t < GM::RPT; t++) {
+    const int r = r0 + t * GM::G;
+    if (act && r < d) {
+      const int e = r * GM::S2 + cp;
       if (need_x) {
         reinterpret_cast<double2*>(c.s[sX].re)[e] = xr[t];
         reinterpret_cast<double2*>(c.s[sX].im)[e] = xi[t];
@@ -502,15 +534,16 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
   for (int i = 0; i < K1_FIXED_SLOTS; i++) { c.s[i].re = base + (size_t)i * slot_d; c.s[i].im = c.s[i].re + d * S; }
   c.E0.re = base + (size_t)K1_FIXED_SLOTS * slot_d; c.E0.im = c.E0.re + d * S;
   c.X0.re = base + (size_t)(K1_FIXED_SLOTS + nc) * slot_d; c.X0.im = c.X0.re + d * S;
-  // tail: 8 rows of zero padding (fragment loads of the last tile row run past the last slot), then small buffers
+  // tail: rows of zero padding (fragment loads of the last tile row / k-step run past the last slot), then small buffers
+  const int pad_rows = k1_pad_rows<C>(d);
   double* tail = base + (size_t)nslots * slot_d;
-  SvcScratch* sc = reinterpret_cast<SvcScratch*>(tail + 8 * S);
+  SvcScratch* sc = reinterpret_cast<SvcScratch*>(tail + pad_rows * S);
   const bool is_service = (c.warp >= C::NW);
   const bool taylor = (p.order != 0);
 
   // zero everything once (pad columns must be exactly zero, all pad reads finite), then load the control operators
   {
-    const int total2 = (nslots * slot_d + 8 * S) / 2;
+    const int total2 = (nslots * slot_d + pad_rows * S) / 2;
     double2* z = reinterpret_cast<double2*>(base);
     for (int e = threadIdx.x; e < total2; e += NALL) z[e] = make_double2(0.0, 0.0);
     if (threadIdx.x == 0) sc->ok = 1;
@@ -534,7 +567,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
       QOC_STAMP(8);
       bar_sync(BAR_NREADY + par, NALL);         // compute warps have formed N = V - U of this slice
       QOC_STAMP(9);
-      all_ok &= service_inverse<C>(c.s[sN0 + par], d, sc, sw, lane);
+      if (!(p.dbg_flags & 1)) all_ok &= service_inverse<C>(c.s[sN0 + par], d, sc, sw, lane);
       QOC_STAMP(10);
       bar_arrive(BAR_NINV + par, NALL);         // N^-1 is in place
       dbg_i++;
@@ -549,23 +582,32 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
   double my_flops = 0.0;
   const double M = 8.0 * d * d * (double)d;
   int dbg_i = (c.warp == 0) ? 0 : (1 << 30);
+  if (p.dbg && (p.dbg_flags & 2) && blockIdx.x == 0 && c.warp == 0) { c.stamp = p.dbg + 16 * p.dbg_slices; c.stamp_left = 4096; }
   // A0 stays in registers for the whole launch
   double2 a0r[2], a0i[2];
 #pragma unroll
   for (int t = 0; t < 2; t++) {
-    const int e = c.tid + t * C::NTHREADS;
-    const bool v = e < c.n2 / 2;
+    typedef GenMap<C> GM;
+    const int r = c.tid / GM::S2 + t * GM::G, e = r * GM::S2 + c.tid % GM::S2;
+    const bool v = (t < GM::RPT) && (c.tid / GM::S2 < GM::G) && (r < d);
     a0r[t] = v ? reinterpret_cast<const double2*>(p.A0p)[e] : make_double2(0.0, 0.0);
     a0i[t] = v ? reinterpret_cast<const double2*>(p.A0p + d * S)[e] : make_double2(0.0, 0.0);
   }
+  double uj[8];  // control amplitudes of the slice whose generator is built next (prefetched one phase ahead)
+  auto load_u = [&](const WorkIter& w) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) uj[j] = (j < nc && w.valid()) ? __ldg(p.u + ((size_t)w.b * p.nt + w.k) * nc + j) : 0.0;
+  };
   // (D, S) = (Lu - Lv, Lu + Lv) homes per control: control 0 uses (sM2, sLv); control j >= 1 the extra slots.
   // They are tracked by pointer because the squaring phase ping-pongs results through scratch slots.
   Mat Dh[8], Sh[8];
   for (int j = 1; j < nc && j < 8; j++) { Dh[j] = c.extra(2 * (j - 1)); Sh[j] = c.extra(2 * (j - 1) + 1); }
   int par = 0;
   int sq = 0;
+  const unsigned slot_bytes = (unsigned)slot_d * 8u;
   if (it.valid()) {
-    sq = build_generator<C>(p, c, a0r, a0i, (size_t)it.b * p.nt + it.k, need_x, sc);
+    load_u(it);
+    sq = build_generator<C>(p, c, a0r, a0i, uj, need_x, sc);
     pade13_build_N<C>(c, c.s[sU0], c.s[sN0]);
     bar_arrive(BAR_NREADY + 0, NALL);
   }
@@ -575,17 +617,27 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
     const bool last_of_seg = (it.k + 1 >= it.k1);
     const int seg = it.seg;
     const size_t slice = (size_t)it.b * p.nt + it.k;
-    const double scl = ldexp(1.0, -sq);
+    const double scl = __hiloint2double((1023 - sq) << 20, 0);  // 2^-sq
     const int sq_cur = sq;
     QOC_STAMP(0);
+    WorkIter nx = it;
+    nx.next();
+    load_u(nx);  // the amplitudes of the next slice arrive while part1 runs
+    // the previous slice's U_k / dU_k bulk stores read slots that part1 is about to reuse: they were issued a whole
+    // product phase ago, so this wait is normally free
+    if (c.tid == 0) bulk_wait_read();
+    c.cbar();
 
     // ---- part1(k): everything that does not need N^-1(k) ----
     if (p.want_jac) {
       if (taylor) {
         for (int j = 0; j < nc; j++) {
-          taylor_jacobian<C>(c, c.E(j), c.s[sT], p.order);
-          slot_copy(p.L + (slice * nc + j) * slot_d, c.s[sT].re, c.n2, c.tid, C::NTHREADS);
+          if (c.tid == 0) bulk_wait_read();   // the previous bulk store out of sT has been read
           c.cbar();
+          taylor_jacobian<C>(c, c.E(j), c.s[sT], p.order);
+          fence_async_smem();
+          c.cbar();
+          if (c.tid == 0) { bulk_store(p.L + (slice * nc + j) * slot_d, c.s[sT].re, slot_bytes); bulk_commit(); }
         }
       } else {
         // control 0 last: its (D, S) stay in (sM2, sLv), which the other controls' part1 uses as workspace (sM2)
@@ -596,10 +648,8 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
     QOC_STAMP(1);
 
     // ---- software pipeline: generator and Pade denominator of the NEXT slice while N^-1(k) is being formed ----
-    WorkIter nx = it;
-    nx.next();
     if (nx.valid()) {
-      sq = build_generator<C>(p, c, a0r, a0i, (size_t)nx.b * p.nt + nx.k, need_x, sc);
+      sq = build_generator<C>(p, c, a0r, a0i, uj, need_x, sc);
       pade13_build_N<C>(c, c.s[sU0 + (par ^ 1)], c.s[sN0 + (par ^ 1)]);
       bar_arrive(BAR_NREADY + (par ^ 1), NALL);
     }
@@ -630,7 +680,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
         c.mm1(tmp2, R, R, NoEpi());
         Mat x = tmp2; tmp2 = R; R = x;
       }
-      for (int j = 0; j < nc; j++) slot_copy(p.L + (slice * nc + j) * slot_d, Lc[j].re, c.n2, c.tid, C::NTHREADS);
+      // (stored below together with R, asynchronously)
       // every slot touched here is dead once stored: hand the (permuted) physical slots back to their roles
       c.s[sM2] = Lc[0];
       for (int j = 1; j < nc; j++) Dh[j] = Lc[j];
@@ -642,7 +692,18 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
       }
     }
     c.s[sT] = R; c.s[sLw] = tmp2;
-    slot_copy(p.U + slice * slot_d, R.re, c.n2, c.tid, C::NTHREADS);
+    // U_k and dU_k/du_j leave through the copy engine (TMA bulk store); all generic-proxy writes of the slots were
+    // ordered by the barrier that ended the last product, the proxy fence makes them visible to the async proxy
+    fence_async_smem();
+    c.cbar();
+    if (c.tid == 0 && !(p.dbg_flags & 4)) {
+      bulk_store(p.U + slice * slot_d, R.re, slot_bytes);
+      if (p.want_jac && !taylor) {
+        bulk_store(p.L + (slice * nc + 0) * slot_d, c.s[sM2].re, slot_bytes);
+        for (int j = 1; j < nc; j++) bulk_store(p.L + (slice * nc + j) * slot_d, Dh[j].re, slot_bytes);
+      }
+      bulk_commit();
+    }
     QOC_STAMP(4);
 
     // ---- level-1 scan: Q <- U_k Q ----
@@ -668,7 +729,10 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
     par ^= 1;
     it = nx;
   }
-  if (c.tid == 0 && my_flops != 0.0) atomicAdd(p.flops, my_flops);
+  if (c.tid == 0) {
+    bulk_wait_all();
+    if (my_flops != 0.0) atomicAdd(p.flops, my_flops);
+  }
 }
 
 }  // namespace qoc

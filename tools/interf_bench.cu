@@ -6,7 +6,7 @@
 using namespace qoc;
 typedef Cfg<4, 28, 7> C;
 
-template <int MODE>
+template <int MODE, int CM>
 __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) bench(int d, int reps, long long* out, double* sink, volatile int* stop) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* base = reinterpret_cast<double*>(smem_raw);
@@ -60,7 +60,12 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) bench(int d, int re
     return;
   }
   long long t0 = clock64();
-  for (int it = 0; it < reps; it++) c.mm1(c.s[4 + (it & 1)], c.s[0], c.s[1], NoEpi());
+  for (int it = 0; it < reps; it++) {
+    if (CM == 0) c.mm1(c.s[4 + (it & 1)], c.s[0], c.s[1], NoEpi());
+    if (CM == 1) c.mm1(c.s[4 + (it & 1)], c.s[0], c.s[1], c.epi(1.0, 0.5, c.s[2], 0.25, c.s[3], 0.125, c.s[0], 1.0));
+    if (CM == 2) { c.lc(c.s[4], 0.5, c.s[0], 0.25, c.s[1], 0.125, c.s[2], 0.0); c.cbar(); }
+    if (CM == 3) c.mm2(c.s[4 + (it & 1)], c.s[0], c.s[1], c.s[2], c.s[3], NoEpi());
+  }
   long long t1 = clock64();
   if (threadIdx.x == 0) { out[blockIdx.x] = t1 - t0; done = 1; }
   sink[threadIdx.x] += c.s[4].re[threadIdx.x % (d * C::S)];
@@ -72,14 +77,15 @@ int main() {
   cudaMalloc(&out, 8 * 296); cudaMalloc(&sink, 8 * 1024); cudaMalloc(&stop, 4);
   size_t smem = (size_t)(9 * 2 * d * C::S + 8 * C::S) * 8 + sizeof(SvcScratch) + 64;
   const char* names[] = {"service idle", "service: GJ inverse", "service: independent DFMA bursts (8-way ILP)", "service: bar + LDS only", "service: dependent DFMA chain", "service: SHFL + FADD chain"};
-#define RUN(M)                                                                                                     \
+#define RUN2(M, CMM)                                                                                                     \
   {                                                                                                                \
-    cudaFuncSetAttribute(bench<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
-    bench<M><<<148, C::NTHREADS + NSW * 32, smem>>>(d, reps, out, sink, stop);                                     \
+    cudaFuncSetAttribute(bench<M, CMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+    bench<M, CMM><<<148, C::NTHREADS + NSW * 32, smem>>>(d, reps, out, sink, stop);                                     \
     cudaError_t e = cudaDeviceSynchronize();                                                                       \
     long long h[296]; cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost);                                        \
-    printf("{\"mode\": \"%s\", \"cycles_per_mm1_phase\": %.1f, \"cycles_per_service_iter\": %lld, \"err\": \"%s\"}\n", names[M], (double)h[0] / reps, h[148], cudaGetErrorString(e)); \
+    printf("{\"compute\": \"%s\", \"mode\": \"%s\", \"cycles_per_phase\": %.1f, \"cycles_per_service_iter\": %lld, \"err\": \"%s\"}\n", cn[CMM], names[M], (double)h[0] / reps, h[148], cudaGetErrorString(e)); \
   }
-  RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5)
+  const char* cn[] = {"mm1", "mm1+LinEpi", "lincomb", "mm2"};
+  RUN2(0, 0) RUN2(1, 0) RUN2(0, 1) RUN2(1, 1) RUN2(0, 2) RUN2(1, 2) RUN2(0, 3) RUN2(1, 3)
   return 0;
 }
