@@ -39,6 +39,11 @@ __device__ __forceinline__ void mv_acc(double (&cr)[2], double (&ci)[2], Mat A, 
   int astep;
   if (ADJ) { are = A.re + q * S + mi * 8 + g; aim = A.im + q * S + mi * 8 + g; astep = 4 * S; }
   else     { are = A.re + (mi * 8 + g) * S + q; aim = A.im + (mi * 8 + g) * S + q; astep = 4; }
+  // The sweeps are latency-bound (one small product per step of a serial recurrence), so the four real products of
+  // the complex tile go to separate accumulators, split once more by k-step parity: 8 independent DMMA chains of
+  // length <= 4 instead of 2 chains of length 14.
+  double a1[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  double a3[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, a4[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
   for (int ks = 0; ks < C::KS; ks++) {
     double ar = are[ks * astep], ai = aim[ks * astep];
@@ -46,11 +51,16 @@ __device__ __forceinline__ void mv_acc(double (&cr)[2], double (&ci)[2], Mat A, 
     const int k = ks * 4 + q;
     double br = 0.0, bi = 0.0;
     if (k < d && g < m) { br = xr[k * m + g]; bi = xi[k * m + g]; }
-    dmma(cr[0], cr[1], ar, br);
-    dmma(ci[0], ci[1], ar, bi);
-    dmma(cr[0], cr[1], -ai, bi);
-    dmma(ci[0], ci[1], ai, br);
+    const int h = ks & 1;
+    dmma(a1[h][0], a1[h][1], ar, br);
+    dmma(a3[h][0], a3[h][1], ar, bi);
+    dmma(a2[h][0], a2[h][1], -ai, bi);
+    dmma(a4[h][0], a4[h][1], ai, br);
   }
+  cr[0] += (a1[0][0] + a1[1][0]) + (a2[0][0] + a2[1][0]);
+  cr[1] += (a1[0][1] + a1[1][1]) + (a2[0][1] + a2[1][1]);
+  ci[0] += (a3[0][0] + a3[1][0]) + (a4[0][0] + a4[1][0]);
+  ci[1] += (a3[0][1] + a3[1][1]) + (a4[0][1] + a4[1][1]);
 }
 
 // write the tile result into a compact planar state buffer
@@ -143,7 +153,7 @@ __device__ __forceinline__ double penalty_partial(const double* xr, const double
   return s;
 }
 
-constexpr int K2_NST = 3;
+constexpr int K2_NST = 6;
 
 // K2: one CTA per pulse, NT warps.
 template <class C>
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(C::NT * 32, 1) k2_kernel(K23Params p) {
   if (p.lam_start) state_to_global(p.lam_start + (size_t)b * 2 * dm, XR(cur), XI(cur), d, m, tid, NTH);
 }
 
-constexpr int K3_NST = 3;
+constexpr int K3_NST = 4;
 
 // K3: one CTA per segment; warps [0,NT) run the recurrences, warps [NT*(1+j), NT*(2+j)) contract control j.
 template <class C>
