@@ -10,6 +10,7 @@
 #include "../../include/qoc_b200.h"
 #include "qoc_k1.cuh"
 #include "qoc_k23.cuh"
+#include "qoc_gpath.cuh"
 
 using namespace qoc;
 
@@ -32,6 +33,13 @@ struct qoc_handle {
   double *dx0 = nullptr, *dT = nullptr, *dxs = nullptr, *dle = nullptr, *dX = nullptr, *dLAM = nullptr;
   double *dxf = nullptr, *dlam0 = nullptr, *dJ = nullptr, *dg = nullptr, *dflops = nullptr, *dlamf = nullptr;
   double *dS = nullptr;
+  // general path (d > 28): matrices in HBM/L2, batched launches over chunks of slices (csrc/qoc_gpath.cuh)
+  bool gpath = false;
+  int gchunk = 0, gnw = 0;
+  double* gW = nullptr;       // workspace: gnw slots x gchunk slices
+  double* dumax = nullptr;    // max_k |u_jk| per control
+  double normA0 = 0.0, normA[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long row_mask64 = 0ull;
   long long* dbg = nullptr;  // developer timeline buffer (qoc_debug_k1_timeline)
   int dbg_slices = 0;
   int dbg_flags = 0;
@@ -156,7 +164,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
   cudaSetDevice(h->prob.device);
   double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
-                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen};
+                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->dstatus) cudaFree(h->dstatus);
@@ -183,8 +191,10 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   if ((p.n_pen_rows > 0) != (p.n_pen_cols > 0) || (p.n_pen_rows > 0 && (!p.pen_rows || !p.pen_cols))) {
     g_create_error = "penalty index lists inconsistent"; return QOC_ERR_INVALID;
   }
-  const int cfg = pick_cfg(p.d);
-  if (cfg < 0) { g_create_error = "d > 28 not supported yet by the shared-memory-resident kernels"; return QOC_ERR_UNSUPPORTED; }
+  int cfg = pick_cfg(p.d);
+  const char* force_g = getenv("QOC_FORCE_GPATH");
+  bool use_gpath = (cfg < 0) || (force_g && force_g[0] == '1');
+  if (p.d > 512) { g_create_error = "d > 512 not supported"; return QOC_ERR_UNSUPPORTED; }
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || p.device < 0 || p.device >= ndev) {
@@ -197,12 +207,21 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     g_create_error = "device is not compute capability 10.x (kernels are built for sm_100a only)";
     return QOC_ERR_NO_DEVICE;
   }
+  if (!use_gpath) {
+    // the shared-memory-resident kernels need 17 + 3 nc - 2 matrices on chip; otherwise take the general path
+    const size_t need = with_cfg(cfg, [&](auto c) -> size_t { typedef decltype(c) C; return k1_smem_bytes(p.d, p.nc, C::S, k1_pad_rows<C>(p.d)); });
+    if (need > (size_t)dp.sharedMemPerBlockOptin) use_gpath = true;
+  }
+  if (use_gpath) cfg = 5;
   qoc_handle* h = new qoc_handle();
   h->prob = p;
   if (h->prob.n <= 0) h->prob.n = p.m;
+  h->gpath = use_gpath;
   for (int i = 0; i < p.n_pen_rows; i++) {
     if (p.pen_rows[i] < 0 || p.pen_rows[i] >= p.d) { g_create_error = "penalty row index out of range"; delete h; return QOC_ERR_INVALID; }
-    h->row_mask |= 1u << p.pen_rows[i];
+    if (use_gpath && p.pen_rows[i] >= 64) { g_create_error = "penalty rows >= 64 not supported on the general path yet"; delete h; return QOC_ERR_UNSUPPORTED; }
+    if (p.pen_rows[i] < 32) h->row_mask |= 1u << p.pen_rows[i];
+    h->row_mask64 |= 1ull << p.pen_rows[i];
   }
   for (int i = 0; i < p.n_pen_cols; i++) {
     if (p.pen_cols[i] < 0 || p.pen_cols[i] >= p.m) { g_create_error = "penalty column index out of range"; delete h; return QOC_ERR_INVALID; }
@@ -214,7 +233,23 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   h->nsm = dp.multiProcessorCount;
   h->stream = nullptr;
   for (int i = 0; i < 4; i++) h->ev[i] = nullptr;
-  int rc = with_cfg(cfg, [&](auto c) -> int {
+  int rc = QOC_OK;
+  if (use_gpath) {
+    int S = (p.d + 3) / 4 * 4;
+    if (S % 8 != 4) S += 4;
+    h->S = S;
+    h->slot_d = 2 * p.d * S;
+    h->spp = 1; h->nseg = p.batch; h->seg_cap = p.nt; h->k1_grid = 0; h->k3_threads = 256;
+    h->k1_smem = h->k2_smem = h->k3_smem = 0;
+    h->gnw = 24 + p.nc;
+    const size_t slotBg = (size_t)h->slot_d * 8;
+    size_t chunk = (size_t)(1536ull << 20) / ((size_t)h->gnw * slotBg);   // ~1.5 GB of workspace
+    if (chunk < 1) chunk = 1;
+    if (chunk > 2048) chunk = 2048;
+    if (chunk > (size_t)p.batch * p.nt) chunk = (size_t)p.batch * p.nt;
+    h->gchunk = (int)chunk;
+  } else
+  rc = with_cfg(cfg, [&](auto c) -> int {
     typedef decltype(c) C;
     h->S = C::S;
     h->slot_d = 2 * p.d * C::S;
@@ -258,6 +293,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
 
   auto fail = [&](int code) { g_create_error = h->err; qoc_destroy(h); return code; };
 #define CR(call) do { int r__ = [&]() -> int { QOC_CUDA(h, call); return QOC_OK; }(); if (r__ != QOC_OK) return fail(r__); } while (0)
+  CR(cudaSetDevice(p.device));
   CR(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 4; i++) CR(cudaEventCreate(&h->ev[i]));
   const size_t slotB = (size_t)h->slot_d * 8;
@@ -282,6 +318,18 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   CR(cudaMalloc(&h->dg, nsl * p.nc * 8));
   CR(cudaMalloc(&h->dflops, 8));
   CR(cudaMalloc(&h->dS, slotB));
+  if (h->gpath) {
+    CR(cudaSetDevice(p.device));
+    CR(cudaMalloc(&h->gW, (size_t)h->gnw * h->gchunk * slotB));
+    CR(cudaMalloc(&h->dumax, 8 * 8));
+    auto norm1 = [&](const double* M) {
+      double mx = 0;
+      for (int c = 0; c < p.d; c++) { double sm_ = 0; for (int r = 0; r < p.d; r++) sm_ += hypot(M[2 * (r + (size_t)p.d * c)], M[2 * (r + (size_t)p.d * c) + 1]); if (sm_ > mx) mx = sm_; }
+      return mx;
+    };
+    h->normA0 = norm1(A0);
+    for (int j = 0; j < p.nc; j++) h->normA[j] = norm1(A + (size_t)j * 2 * p.d * p.d);
+  }
   CR(cudaMalloc(&h->dcs, (size_t)h->nseg * dmB));
   CR(cudaMalloc(&h->dJpen, (size_t)p.batch * 8));
   CR(cudaMalloc(&h->dstatus, 4));
@@ -336,7 +384,182 @@ static K23Params base_k23(qoc_handle* h) {
   return q;
 }
 
+
+// ---- general path (d > 28): host-orchestrated batched launches -------------------------------------------------------
+namespace {
+struct GRun {
+  qoc_handle* h;
+  cudaStream_t st;
+  int nb;           // slices in this chunk
+  int tiles;
+  GOp W(int slot) const { return GOp{h->gW + (size_t)slot * h->gchunk * h->slot_d, (long long)h->slot_d}; }
+  double* Wp(int slot) const { return h->gW + (size_t)slot * h->gchunk * h->slot_d; }
+  // C = alpha * sum_p A_p B_p + sum_q beta_q D_q + gamma I
+  void gemm(double* C, long long cstride, int npairs, const GOp* A, const GOp* B, double alpha, int nadd, const GOp* D,
+            const double* beta, double gamma) const {
+    GGemm g;
+    memset(&g, 0, sizeof g);
+    g.d = h->prob.d; g.S = h->S; g.nb = nb; g.npairs = npairs; g.nadd = nadd; g.alpha = alpha; g.gamma = gamma;
+    for (int i = 0; i < npairs; i++) { g.A[i] = A[i]; g.B[i] = B[i]; }
+    for (int i = 0; i < nadd; i++) { g.D[i] = D[i]; g.beta[i] = beta[i]; }
+    g.C = C; g.cstride = cstride;
+    g_gemm_kernel<<<dim3(tiles, tiles, nb), 256, 0, st>>>(g);
+    h->launches++;
+  }
+  void mm1(int c, GOp a, GOp b, double alpha = 1.0, int nadd = 0, const GOp* D = nullptr, const double* beta = nullptr, double gamma = 0.0) const {
+    gemm(Wp(c), h->slot_d, 1, &a, &b, alpha, nadd, D, beta, gamma);
+  }
+  void mm2(int c, GOp a0, GOp b0, GOp a1, GOp b1, double alpha = 1.0, int nadd = 0, const GOp* D = nullptr, const double* beta = nullptr, double gamma = 0.0) const {
+    GOp A[2] = {a0, a1}, B[2] = {b0, b1};
+    gemm(Wp(c), h->slot_d, 2, A, B, alpha, nadd, D, beta, gamma);
+  }
+  void lin(int c, int nadd, const GOp* D, const double* beta, double gamma = 0.0) const { gemm(Wp(c), h->slot_d, 0, nullptr, nullptr, 0.0, nadd, D, beta, gamma); }
+};
+}  // namespace
+
+static const double kB13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
+                                10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
+
+static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_t st) {
+  const qoc_problem& p = h->prob;
+  const int nc = p.nc, d = p.d;
+  const size_t nsl = (size_t)p.batch * p.nt;
+  const bool taylor = p.order != 0;
+  // number of squarings from the bound ||X_k||_1 <= ||A0||_1 + sum_j max_k|u_jk| ||A_j||_1 (uniform over the launch)
+  QOC_CUDA(h, cudaMemsetAsync(h->dumax, 0, 64, st));
+  g_umax_kernel<<<64, 256, 0, st>>>(d_u, nc, (long long)nsl, h->dumax);
+  h->launches++;
+  double umax[8];
+  QOC_CUDA(h, cudaMemcpyAsync(umax, h->dumax, 64, cudaMemcpyDeviceToHost, st));
+  QOC_CUDA(h, cudaStreamSynchronize(st));
+  double bound = h->normA0;
+  for (int j = 0; j < nc; j++) bound += umax[j] * h->normA[j];
+  const double theta = taylor ? 5.4 : 4.74;
+  int sq = 0;
+  if (bound > theta) sq = (int)ceil(log2(bound / theta));
+  if (sq < 0) sq = 0;
+  const double sc = ldexp(1.0, -sq);
+  const double* b = kB13;
+  enum { A = 0, X, A2, A4, A6, W1, Z1, Wm, V, U, R, M2, M4, M6, T1, T2, Lw, Lv, Dd, Ss, RH, TMP, TMPR, L0 };
+  GRun g{h, st, 0, (d + 31) / 32};
+  const GOp A0op{h->dA0p, 0};
+  for (size_t c0 = 0; c0 < nsl; c0 += h->gchunk) {
+    const int nb = (int)((nsl - c0 < (size_t)h->gchunk) ? nsl - c0 : h->gchunk);
+    g.nb = nb;
+    g_build_kernel<<<nb, 256, 0, st>>>(d, h->S, nc, h->dA0p, h->dAp, d_u + c0 * nc, sc, g.Wp(A),
+                                       (taylor && want_jac && p.order >= 2) ? g.Wp(X) : nullptr, h->slot_d);
+    h->launches++;
+    g.mm1(A2, g.W(A), g.W(A));
+    g.mm1(A4, g.W(A2), g.W(A2));
+    g.mm1(A6, g.W(A2), g.W(A4));
+    { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[13], b[11], b[9]}; g.lin(W1, 3, D, be); }
+    { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[12], b[10], b[8]}; g.lin(Z1, 3, D, be); }
+    { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[7], b[5], b[3]}; g.mm1(Wm, g.W(A6), g.W(W1), 1.0, 3, D, be, b[1]); }
+    { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[6], b[4], b[2]}; g.mm1(V, g.W(A6), g.W(Z1), 1.0, 3, D, be, b[0]); }
+    g.mm1(U, g.W(A), g.W(Wm));
+    { GOp D[2] = {g.W(V), g.W(U)}; double be[2] = {1.0, -1.0}; g.lin(V, 2, D, be); }   // N = V - U (in place: elementwise)
+    g_inverse_kernel<<<nb, 256, (size_t)d * 36, st>>>(d, h->S, g.Wp(V), h->slot_d, h->dstatus);
+    h->launches++;
+    // R = I + 2 N^-1 U
+    double* Rout = (sq == 0) ? h->dU + c0 * h->slot_d : g.Wp(R);
+    { GOp a1 = g.W(V), b1 = g.W(U); g.gemm(Rout, h->slot_d, 1, &a1, &b1, 2.0, 0, nullptr, nullptr, 1.0); }
+    GOp Rop{Rout, (long long)h->slot_d};
+    if (want_jac) {
+      for (int j = 0; j < nc; j++) {
+        const GOp E{h->dAp + (size_t)j * h->slot_d, 0};
+        double* Lout = h->dL + (c0 * nc + j) * h->slot_d;
+        const long long lstride = (long long)nc * h->slot_d;
+        if (taylor) {
+          // expm_jacobian!  src/gradient_computations.jl:177-213 (dt = 1), X = unscaled generator
+          if (p.order == 1) { double be[1] = {1.0}; g.gemm(Lout, lstride, 0, nullptr, nullptr, 0.0, 1, &E, be, 0.0); continue; }
+          g.mm1(M2, E, g.W(X));   // AjX
+          g.mm1(M4, g.W(X), E);   // XAj
+          if (p.order == 2) {
+            GOp D[3] = {E, g.W(M2), g.W(M4)}; double be[3] = {1.0, 0.5, 0.5};
+            g.gemm(Lout, lstride, 0, nullptr, nullptr, 0.0, 3, D, be, 0.0);
+            continue;
+          }
+          GOp A3[3] = {g.W(M2), g.W(M4), g.W(X)}, B3[3] = {g.W(X), g.W(X), g.W(M4)};
+          GOp D[3] = {E, g.W(M2), g.W(M4)}; double be[3] = {1.0, 0.5, 0.5};
+          if (p.order == 3) { g.gemm(Lout, lstride, 3, A3, B3, 1.0 / 6.0, 3, D, be, 0.0); continue; }
+          g.gemm(g.Wp(Lw), h->slot_d, 3, A3, B3, 1.0 / 6.0, 3, D, be, 0.0);
+          g.mm1(M6, g.W(X), g.W(X));  // X2
+          GOp A4_[4] = {g.W(M2), g.W(M4), g.W(M6), g.W(M6)}, B4_[4] = {g.W(M6), g.W(M6), g.W(M2), g.W(M4)};
+          GOp D4[1] = {g.W(Lw)}; double b4[1] = {1.0};
+          g.gemm(Lout, lstride, 4, A4_, B4_, 1.0 / 24.0, 1, D4, b4, 0.0);
+          continue;
+        }
+        // exact Frechet derivative, structured block-triangular evaluation (Al-Mohy & Higham 2009, Alg. 6.4)
+        g.mm2(M2, g.W(A), E, E, g.W(A));
+        g.mm2(M4, g.W(A2), g.W(M2), g.W(M2), g.W(A2));
+        g.mm2(M6, g.W(A4), g.W(M2), g.W(M4), g.W(A2));
+        { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[13], b[11], b[9]}; g.lin(T1, 3, D, be); }
+        { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[12], b[10], b[8]}; g.lin(T2, 3, D, be); }
+        { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[7], b[5], b[3]}; g.mm2(Lw, g.W(A6), g.W(T1), g.W(M6), g.W(W1), 1.0, 3, D, be); }
+        { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[6], b[4], b[2]}; g.mm2(Lv, g.W(A6), g.W(T2), g.W(M6), g.W(Z1), 1.0, 3, D, be); }
+        { GOp D[1] = {g.W(Lv)}; double be[1] = {-1.0}; g.mm2(Dd, g.W(A), g.W(Lw), E, g.W(Wm), 1.0, 1, D, be); }        // D = Lu - Lv
+        { GOp D[2] = {g.W(Dd), g.W(Lv)}; double be[2] = {1.0, 2.0}; g.lin(Ss, 2, D, be); }                          // S = Lu + Lv
+        { GOp D[1] = {g.W(Ss)}; double be[1] = {1.0}; g.mm1(RH, g.W(Dd), Rop, 1.0, 1, D, be); }                       // rhs = S + D R
+        double* Lj = (sq == 0) ? Lout : g.Wp(L0 + j);
+        { GOp a1 = g.W(V), b1 = g.W(RH); g.gemm(Lj, (sq == 0) ? lstride : (long long)h->slot_d, 1, &a1, &b1, sc, 0, nullptr, nullptr, 0.0); }
+      }
+    }
+    // squaring phase: L <- R L + L R ; R <- R R
+    for (int t = 0; t < sq; t++) {
+      const bool last = (t == sq - 1);
+      if (want_jac && !taylor) {
+        for (int j = 0; j < nc; j++) {
+          GOp Lj = g.W(L0 + j);
+          GOp Aa[2] = {Rop, Lj}, Bb[2] = {Lj, Rop};
+          if (last) g.gemm(h->dL + (c0 * nc + j) * h->slot_d, (long long)nc * h->slot_d, 2, Aa, Bb, 1.0, 0, nullptr, nullptr, 0.0);
+          else {
+            g.gemm(g.Wp(TMP), h->slot_d, 2, Aa, Bb, 1.0, 0, nullptr, nullptr, 0.0);
+            GOp D[1] = {g.W(TMP)}; double be[1] = {1.0}; g.lin(L0 + j, 1, D, be);
+          }
+        }
+      }
+      double* Rn = last ? h->dU + c0 * h->slot_d : g.Wp(TMPR);
+      g.gemm(Rn, h->slot_d, 1, &Rop, &Rop, 1.0, 0, nullptr, nullptr, 0.0);
+      if (!last) { GOp D[1] = {g.W(TMPR)}; double be[1] = {1.0}; g.lin(R, 1, D, be); }
+    }
+    QOC_CUDA(h, cudaGetLastError());
+  }
+  // F_alg bookkeeping, q = 13
+  {
+    const double M = 8.0 * d * d * (double)d;
+    double G = 0.0;
+    if (want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0) : (2.0 * 6 + 2.0 * sq + 2.0);
+    const double f = M * ((6.0 + sq + 4.0 / 3.0) + nc * G) * (double)nsl;
+    QOC_CUDA(h, cudaMemcpyAsync(h->dflops, &f, 8, cudaMemcpyHostToDevice, st));
+  }
+  h->have_jac = want_jac;
+  return QOC_OK;
+}
+
+static int gpath_sweep(qoc_handle* h, int phase, bool want_grad, const double* d_lam_final, const double* d_x_start,
+                       double* d_J, double* d_dJdu, cudaStream_t st) {
+  const qoc_problem& p = h->prob;
+  GSweep g;
+  memset(&g, 0, sizeof g);
+  g.d = p.d; g.S = h->S; g.m = p.m; g.nc = p.nc; g.nt = p.nt; g.cost = p.cost; g.n = p.n;
+  g.phase = phase; g.want_grad = want_grad ? 1 : 0; g.store_costates = p.store_costates;
+  g.U = h->dU; g.L = h->dL; g.slot = h->slot_d; g.x0 = h->dx0; g.x_start_ext = d_x_start; g.T = h->dT;
+  g.lam_final = d_lam_final; g.X = h->dX; g.LAM = h->dLAM; g.x_final = h->dxf; g.lam_start = h->dlam0;
+  g.J = d_J ? d_J : h->dJ; g.dJdu = d_dJdu ? d_dJdu : h->dg;
+  g.row_mask_lo = (p.mu != 0.0) ? h->row_mask64 : 0ull; g.col_mask = h->col_mask; g.mu = p.mu;
+  const size_t sweep_smem = (size_t)6 * p.d * p.m * 8;
+  if (sweep_smem > 40 * 1024)
+    QOC_CUDA(h, cudaFuncSetAttribute(g_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
+  g_sweep_kernel<<<p.batch, 256, sweep_smem, st>>>(g);
+  h->launches++;
+  QOC_CUDA(h, cudaGetLastError());
+  h->states_valid = (phase != 2);
+  if (want_grad && p.store_costates) h->costates_valid = true;
+  return QOC_OK;
+}
+
 static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_t st) {
+  if (h->gpath) return gpath_k1(h, d_u, want_jac, st);
   const qoc_problem& p = h->prob;
   K1Params k;
   k.d = p.d; k.nc = p.nc; k.nt = p.nt; k.batch = p.batch; k.order = p.order;
@@ -406,6 +629,10 @@ static int run_sweeps(qoc_handle* h, bool want_grad, const double* d_lam_final, 
                       bool store_states, cudaStream_t st) {
   int rc;
   const bool builtin = h->prob.cost != QOC_COST_NONE;
+  if (h->gpath) {
+    if (d_lam_final) return gpath_sweep(h, 2, true, d_lam_final, nullptr, d_J, d_dJdu, st);
+    return gpath_sweep(h, want_grad ? 0 : 1, want_grad, nullptr, nullptr, d_J, d_dJdu, st);
+  }
   if (!has_penalty(h)) {
     if (d_lam_final) rc = launch_k2(h, 2, false, d_lam_final, nullptr, nullptr, st);
     else rc = launch_k2(h, builtin ? 0 : 1, !want_grad, nullptr, nullptr, d_J, st);
@@ -450,7 +677,7 @@ extern "C" int qoc_eval_device(qoc_handle* h, const double* d_u, double* d_J, do
   if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[0], st));
   if ((rc = launch_k1(h, d_u, true, st)) != QOC_OK) return rc;
   if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[1], st));
-  if (!has_penalty(h)) {
+  if (!has_penalty(h) && !h->gpath) {
     if ((rc = launch_k2(h, 0, false, nullptr, nullptr, d_J, st)) != QOC_OK) return rc;
     if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[2], st));
     if ((rc = launch_k3(h, true, h->prob.store_costates != 0, d_dJdu, st)) != QOC_OK) return rc;
@@ -560,7 +787,8 @@ extern "C" int qoc_get_states(qoc_handle* h, double* x_out) {
   const qoc_problem& p = h->prob;
   QOC_CUDA(h, cudaSetDevice(p.device));
   if (!h->states_valid) {
-    int rc = launch_k3(h, false, true, nullptr, h->stream);
+    int rc = h->gpath ? gpath_sweep(h, 1, false, nullptr, nullptr, nullptr, nullptr, h->stream)
+                      : launch_k3(h, false, true, nullptr, h->stream);
     if (rc != QOC_OK) return rc;
   }
   QOC_CUDA(h, cudaMemcpyAsync(x_out, h->dX, (size_t)p.batch * (p.nt + 1) * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -635,6 +863,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) kq_reduce_kernel(const double*
 extern "C" int qoc_shard_phase1_device(qoc_handle* h, const double* d_u, double* d_S_out, void* stream) {
   if (!h || !d_u || !d_S_out) return QOC_ERR_INVALID;
   if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
+  if (h->gpath) { h->err = "time sharding is not available on the general (d > 28) path yet"; return QOC_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
   h->launches = 0;

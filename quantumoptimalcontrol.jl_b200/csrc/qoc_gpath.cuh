@@ -1,0 +1,401 @@
+// qoc_gpath.cuh -- general path for Hilbert-space dimensions whose working set does not fit shared memory (d > 28).
+//
+// Same arithmetic as K1/K2/K3 (Pade [13/13] expm, structured block-triangular Frechet derivative or the reference's
+// truncated Taylor Jacobian, adjoint gradient), but every matrix lives in HBM/L2 as a planar slot and the program is
+// a sequence of BATCHED launches over a chunk of slices:
+//   g_build_kernel    X_k = (A0 + sum_j u_jk A_j) 2^-s                         src/gradient_computations.jl:18-22
+//   g_gemm_kernel     C = alpha (A1 B1 [+ A2 B2 ...]) + sum_q beta_q D_q + gamma I   on 32x32 DMMA tiles (3M products),
+//                     operands staged global -> shared per 32-wide k chunk; an operand with stride 0 is broadcast
+//   g_inverse_kernel  in-place Gauss-Jordan inverse with partial pivoting, one CTA per slice
+//   g_sweep_kernel    serial forward sweep, cost / terminal costate, backward sweep with the gradient contraction
+//                     (:27-29, :46-58, :65-74), one CTA per pulse
+// This first version favours coverage over speed (no cross-launch fusion, serial sweeps); see DESIGN.md.
+#pragma once
+#include "qoc_tiles.cuh"
+
+namespace qoc {
+
+struct GOp {
+  const double* p;
+  long long stride;  // doubles between consecutive slices (0: same matrix for every slice)
+};
+
+struct GGemm {
+  int d, S, nb, npairs, nadd;
+  GOp A[4], B[4], D[3];
+  double alpha, beta[3], gamma;
+  double* C;
+  long long cstride;
+};
+
+typedef Cfg<4, 36, 8> GTile;  // 32 x 32 output tile, 32-wide k chunks, shared tiles with row stride 36
+
+__global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
+  constexpr int TS = GTile::S;
+  __shared__ __align__(16) double sm[4][32 * TS];  // A.re, A.im, B.re, B.im
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mi = warp / 2, nj0 = (warp % 2) * 2;
+  const int s = blockIdx.z, tm = blockIdx.y, tn = blockIdx.x;
+  const int d = g.d, S = g.S, plane = d * S;
+  Acc<2> acc;
+  acc.zero();
+  const int nkc = (d + 31) / 32;
+  for (int p = 0; p < g.npairs; p++) {
+    const double* Ag = g.A[p].p + (long long)s * g.A[p].stride;
+    const double* Bg = g.B[p].p + (long long)s * g.B[p].stride;
+    for (int kc = 0; kc < nkc; kc++) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int e = tid + i * 256, r = e >> 4, c = (e & 15) * 2;
+        {
+          const int gr = tm * 32 + r, gc = kc * 32 + c;
+          double2 vr = make_double2(0.0, 0.0), vi = vr;
+          if (gr < d && gc < d) {
+            vr = *reinterpret_cast<const double2*>(Ag + (size_t)gr * S + gc);
+            vi = *reinterpret_cast<const double2*>(Ag + plane + (size_t)gr * S + gc);
+          }
+          *reinterpret_cast<double2*>(&sm[0][r * TS + c]) = vr;
+          *reinterpret_cast<double2*>(&sm[1][r * TS + c]) = vi;
+        }
+        {
+          const int gr = kc * 32 + r, gc = tn * 32 + c;
+          double2 vr = make_double2(0.0, 0.0), vi = vr;
+          if (gr < d && gc < d) {
+            vr = *reinterpret_cast<const double2*>(Bg + (size_t)gr * S + gc);
+            vi = *reinterpret_cast<const double2*>(Bg + plane + (size_t)gr * S + gc);
+          }
+          *reinterpret_cast<double2*>(&sm[2][r * TS + c]) = vr;
+          *reinterpret_cast<double2*>(&sm[3][r * TS + c]) = vi;
+        }
+      }
+      __syncthreads();
+      Mat At, Bt;
+      At.re = sm[0]; At.im = sm[1]; Bt.re = sm[2]; Bt.im = sm[3];
+      mm_acc<GTile, false>(acc, At, Bt, mi, nj0, lane);
+    }
+  }
+  acc.finish();
+  const int row = tm * 32 + mi * 8 + (lane >> 2);
+  double* Cg = g.C + (long long)s * g.cstride;
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    const int col = tn * 32 + (nj0 + n) * 8 + 2 * (lane & 3);
+    if (row < d && col < d) {
+      double r0 = g.alpha * acc.re[n][0], r1 = g.alpha * acc.re[n][1];
+      double i0 = g.alpha * acc.im[n][0], i1 = g.alpha * acc.im[n][1];
+      const size_t o = (size_t)row * S + col;
+      for (int q = 0; q < g.nadd; q++) {
+        const double* Dg = g.D[q].p + (long long)s * g.D[q].stride;
+        const double2 a = *reinterpret_cast<const double2*>(Dg + o), b = *reinterpret_cast<const double2*>(Dg + plane + o);
+        r0 = fma(g.beta[q], a.x, r0); r1 = fma(g.beta[q], a.y, r1);
+        i0 = fma(g.beta[q], b.x, i0); i1 = fma(g.beta[q], b.y, i1);
+      }
+      if (row == col) r0 += g.gamma;
+      if (row == col + 1) r1 += g.gamma;
+      if (col + 1 >= d) { r1 = 0.0; i1 = 0.0; }
+      *reinterpret_cast<double2*>(Cg + o) = make_double2(r0, r1);
+      *reinterpret_cast<double2*>(Cg + plane + o) = make_double2(i0, i1);
+    }
+  }
+}
+
+// X[s] = (A0 + sum_j u[s][j] A_j) * scale ;  optionally the unscaled generator too (Taylor mode)
+__global__ void g_build_kernel(int d, int S, int nc, const double* A0p, const double* Ap, const double* u /* [s][nc] */,
+                               double scale, double* X, double* Xun, long long xstride) {
+  const int s = blockIdx.x;
+  const int n2 = d * S;  // double2 per slot
+  double uj[8];
+  for (int j = 0; j < nc && j < 8; j++) uj[j] = u[(size_t)s * nc + j];
+  double2* out = reinterpret_cast<double2*>(X + (long long)s * xstride);
+  double2* out2 = Xun ? reinterpret_cast<double2*>(Xun + (long long)s * xstride) : nullptr;
+  for (int e = threadIdx.x; e < n2; e += blockDim.x) {
+    double2 v = reinterpret_cast<const double2*>(A0p)[e];
+    for (int j = 0; j < nc; j++) {
+      const double2 w = reinterpret_cast<const double2*>(Ap + (size_t)j * 2 * n2)[e];
+      v.x = fma(uj[j], w.x, v.x);
+      v.y = fma(uj[j], w.y, v.y);
+    }
+    if (out2) out2[e] = v;
+    out[e] = make_double2(v.x * scale, v.y * scale);
+  }
+}
+
+// max_k |u[j][k]| per control (device-resident u): out[j]
+__global__ void g_umax_kernel(const double* u, int nc, long long n, double* out) {
+  __shared__ double red[8][32];
+  double m[8];
+  for (int j = 0; j < 8; j++) m[j] = 0.0;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    for (int j = 0; j < nc && j < 8; j++) m[j] = fmax(m[j], fabs(u[k * nc + j]));
+  for (int j = 0; j < nc && j < 8; j++) {
+    double v = m[j];
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < nc && threadIdx.x < 8) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) v = fmax(v, red[threadIdx.x][w]);
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(out + threadIdx.x), (unsigned long long)__double_as_longlong(v));
+  }
+}
+
+// In-place Gauss-Jordan inverse with partial (row) pivoting, one CTA per slice, matrix in global memory (L2).
+__global__ void __launch_bounds__(256) g_inverse_kernel(int d, int S, double* N, long long stride, int* status) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  double2* rowbuf = reinterpret_cast<double2*>(gsm);   // d
+  double2* colbuf = rowbuf + d;                        // d
+  int* piv = reinterpret_cast<int*>(colbuf + d);       // d
+  __shared__ double red_v[8];
+  __shared__ int red_i[8];
+  __shared__ int sh_p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* re = N + (long long)blockIdx.x * stride;
+  double* im = re + (size_t)d * S;
+  bool ok = true;
+  for (int k = 0; k < d; k++) {
+    // pivot search over rows i >= k
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < d; i += 256) {
+      const double x = re[(size_t)i * S + k], y = im[(size_t)i * S + k];
+      const double m = x * x + y * y;
+      if (m > best) { best = m; bi = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = red_v[0];
+      int p = red_i[0];
+      for (int w = 1; w < 8; w++)
+        if (red_v[w] > b || (red_v[w] == b && red_i[w] < p)) { b = red_v[w]; p = red_i[w]; }
+      sh_p = (b > 0.0) ? p : -1 - p;
+      piv[k] = p;
+    }
+    __syncthreads();
+    int p = sh_p;
+    if (p < 0) { ok = false; p = -1 - p; }
+    // stage the pivot row (old row p), the displaced row goes to row p; multipliers = column k after the swap
+    for (int c = tid; c < d; c += 256) {
+      const double2 rp = make_double2(re[(size_t)p * S + c], im[(size_t)p * S + c]);
+      if (p != k) {
+        re[(size_t)p * S + c] = re[(size_t)k * S + c];
+        im[(size_t)p * S + c] = im[(size_t)k * S + c];
+      }
+      rowbuf[c] = rp;
+    }
+    __syncthreads();
+    for (int i = tid; i < d; i += 256) colbuf[i] = make_double2(re[(size_t)i * S + k], im[(size_t)i * S + k]);  // row k entry unused
+    __syncthreads();
+    const double2 pv = rowbuf[k];
+    const double den = 1.0 / (pv.x * pv.x + pv.y * pv.y);
+    const double pir = pv.x * den, pii = -pv.y * den;
+    for (int e = tid; e < d * d; e += 256) {
+      const int i = e / d, c = e - i * d;
+      double vr, vi;
+      if (i == k) {
+        if (c == k) { vr = pir; vi = pii; }
+        else { const double2 r = rowbuf[c]; vr = r.x * pir - r.y * pii; vi = r.x * pii + r.y * pir; }
+      } else {
+        const double2 f = colbuf[i];
+        const double gr = f.x * pir - f.y * pii, gi = f.x * pii + f.y * pir;  // f / pivot
+        if (c == k) { vr = -gr; vi = -gi; }
+        else {
+          const double2 r = rowbuf[c];
+          vr = re[(size_t)i * S + c] - (gr * r.x - gi * r.y);
+          vi = im[(size_t)i * S + c] - (gr * r.y + gi * r.x);
+        }
+      }
+      re[(size_t)i * S + c] = vr;
+      im[(size_t)i * S + c] = vi;
+    }
+    __syncthreads();
+  }
+  // undo the row interchanges as column interchanges in reverse order
+  for (int k = d - 1; k >= 0; k--) {
+    const int p = piv[k];
+    if (p != k) {
+      for (int i = tid; i < d; i += 256) {
+        const size_t a = (size_t)i * S + k, b = (size_t)i * S + p;
+        const double tr = re[a], ti = im[a];
+        re[a] = re[b]; im[a] = im[b];
+        re[b] = tr; im[b] = ti;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && !ok) atomicExch(status, 8);
+}
+
+struct GSweep {
+  int d, S, m, nc, nt, cost, n;
+  int phase;          // 0: forward + cost + backward; 1: forward (+ J) only; 2: backward only (lam_final given)
+  int want_grad, store_costates;
+  const double* U;    // [b*nt + k] planar slots
+  const double* L;    // [(b*nt + k)*nc + j]
+  long long slot;     // doubles per slot
+  const double* x0;   // c128 col-major d x m (shared)  or per-pulse when x_start_ext
+  const double* x_start_ext;
+  const double* T;
+  const double* lam_final;
+  double* X;          // [(b*(nt+1) + k)] d x m c128
+  double* LAM;
+  double* x_final;
+  double* lam_start;
+  double* J;
+  double* dJdu;
+  unsigned long long row_mask_lo;  // penalty rows < 64 (larger d: rows list not supported on this path yet)
+  unsigned col_mask;
+  double mu;
+};
+
+// y (d x m, shared, [r*m + c] re/im) = op(U) x ;  8 warps: warp w takes rows/cols w, w+8, ...; lanes split the sum index
+template <bool ADJ>
+__device__ __forceinline__ void g_matvec(const double* Ure, const double* Uim, int d, int S, int m, const double* xr,
+                                         const double* xi, double* yr, double* yi, int warp, int lane) {
+  for (int r = warp; r < d; r += 8) {
+    double ar[8], ai[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) { ar[c] = 0.0; ai[c] = 0.0; }
+    for (int k = lane; k < d; k += 32) {
+      double qr, qi;
+      if (ADJ) { qr = Ure[(size_t)k * S + r]; qi = -Uim[(size_t)k * S + r]; }
+      else     { qr = Ure[(size_t)r * S + k]; qi = Uim[(size_t)r * S + k]; }
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        if (c < m) {
+          const double vr = xr[k * m + c], vi = xi[k * m + c];
+          ar[c] = fma(qr, vr, fma(-qi, vi, ar[c]));
+          ai[c] = fma(qr, vi, fma(qi, vr, ai[c]));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      if (c < m) {
+        double a = ar[c], b = ai[c];
+        for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+        if (lane == 0) { yr[r * m + c] = a; yi[r * m + c] = b; }
+      }
+  }
+}
+
+// One CTA (256 threads) per pulse: the serial loops of the reference, with the matrices streamed from HBM/L2.
+__global__ void __launch_bounds__(256) g_sweep_kernel(GSweep g) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int d = g.d, m = g.m, dm = d * m, nt = g.nt;
+  double* buf = reinterpret_cast<double*>(gsm);   // 3 state buffers x (re, im): x / lambda ping-pong + y
+  double* b0 = buf; double* b1 = buf + 2 * dm; double* b2 = buf + 4 * dm;
+  __shared__ double red[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const size_t plane = (size_t)d * g.S;
+  const bool pen = g.col_mask != 0u && g.row_mask_lo != 0ull;
+  auto load = [&](double* dst, const double* src) {
+    for (int e = tid; e < dm; e += 256) { const int c = e / d, r = e - c * d; dst[r * m + c] = src[2 * e]; dst[dm + r * m + c] = src[2 * e + 1]; }
+  };
+  auto store = [&](double* dst, const double* src) {
+    for (int e = tid; e < dm; e += 256) { const int c = e / d, r = e - c * d; dst[2 * e] = src[r * m + c]; dst[2 * e + 1] = src[dm + r * m + c]; }
+  };
+  auto penalised = [&](int r, int c) { return pen && r < 64 && ((g.row_mask_lo >> r) & 1ull) && ((g.col_mask >> c) & 1u); };
+  double Jpen = 0.0;
+  double* cur = b0; double* nxt = b1;
+  if (g.phase != 2) {
+    load(cur, g.x_start_ext ? g.x_start_ext + (size_t)b * 2 * dm : g.x0);
+    __syncthreads();
+    for (int k = 0; k < nt; k++) {
+      store(g.X + ((size_t)b * (nt + 1) + k) * 2 * dm, cur);
+      if (pen) for (int e = tid; e < dm; e += 256) { const int r = e / m, c = e - r * m; if (penalised(r, c)) Jpen += cur[e] * cur[e] + cur[dm + e] * cur[dm + e]; }
+      const double* Uk = g.U + ((size_t)b * nt + k) * g.slot;
+      g_matvec<false>(Uk, Uk + plane, d, g.S, m, cur, cur + dm, nxt, nxt + dm, warp, lane);
+      __syncthreads();
+      double* t = cur; cur = nxt; nxt = t;
+    }
+    store(g.X + ((size_t)b * (nt + 1) + nt) * 2 * dm, cur);
+    if (g.x_final) store(g.x_final + (size_t)b * 2 * dm, cur);
+    if (pen) for (int e = tid; e < dm; e += 256) { const int r = e / m, c = e - r * m; if (penalised(r, c)) Jpen += cur[e] * cur[e] + cur[dm + e] * cur[dm + e]; }
+  } else {
+    load(cur, g.X + ((size_t)b * (nt + 1) + nt) * 2 * dm);
+  }
+  __syncthreads();
+  // ---- terminal cost / costate: x_N in cur, lambda_N -> nxt ----
+  const bool builtin = (g.phase != 2) && g.cost != 2;
+  if (tid < 4) red[tid] = 0.0;
+  __syncthreads();
+  double J = 0.0, cr_ = 0.0, ci_ = 0.0;
+  if (builtin) {
+    double orr = 0.0, oii = 0.0;
+    for (int e = tid; e < dm; e += 256) {
+      const int c = e / d, r = e - c * d;
+      const double tr = g.T[2 * e], ti = g.T[2 * e + 1];
+      const double xr = cur[r * m + c], xi = cur[dm + r * m + c];
+      orr += tr * xr + ti * xi;
+      oii += tr * xi - ti * xr;
+    }
+    for (int off = 16; off > 0; off >>= 1) { orr += __shfl_xor_sync(0xffffffffu, orr, off); oii += __shfl_xor_sync(0xffffffffu, oii, off); }
+    if (lane == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
+  }
+  if (pen && g.phase != 2) {
+    double ps = Jpen;
+    for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+    if (lane == 0) atomicAdd(&red[2], ps);
+  }
+  __syncthreads();
+  if (builtin) {
+    const double Or = red[0], Oi = red[1], nn = (double)g.n * (double)g.n;
+    if (g.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
+    else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
+  }
+  if (pen && g.phase != 2) J += g.mu * red[2];
+  if (tid == 0 && g.J && (builtin || (pen && g.phase != 2))) g.J[b] = J;
+  if (g.phase == 1 || !g.want_grad) return;
+  for (int e = tid; e < dm; e += 256) {
+    const int c = e / d, r = e - c * d;
+    double lr = 0.0, li = 0.0;
+    if (g.lam_final) { lr = g.lam_final[(size_t)b * 2 * dm + 2 * e]; li = g.lam_final[(size_t)b * 2 * dm + 2 * e + 1]; }
+    else if (builtin) { const double tr = g.T[2 * e], ti = g.T[2 * e + 1]; lr = cr_ * tr - ci_ * ti; li = cr_ * ti + ci_ * tr; }
+    if (penalised(r, c)) { lr = fma(2.0 * g.mu, cur[r * m + c], lr); li = fma(2.0 * g.mu, cur[dm + r * m + c], li); }
+    nxt[r * m + c] = lr; nxt[dm + r * m + c] = li;
+  }
+  __syncthreads();
+  // ---- backward sweep with the gradient contraction: lam in `lam`, x_k reloaded from the stored states ----
+  double* lam = nxt; double* lam2 = cur; double* xk = b2;
+  // (cur / nxt roles are free now; b2 holds x_k, y goes to lam2 temporarily before the costate update)
+  if (g.store_costates && g.LAM) store(g.LAM + ((size_t)b * (nt + 1) + nt) * 2 * dm, lam);
+  for (int k = nt - 1; k >= 0; k--) {
+    load(xk, g.X + ((size_t)b * (nt + 1) + k) * 2 * dm);
+    __syncthreads();
+    for (int j = 0; j < g.nc; j++) {
+      const double* Lk = g.L + (((size_t)b * nt + k) * g.nc + j) * g.slot;
+      g_matvec<false>(Lk, Lk + plane, d, g.S, m, xk, xk + dm, lam2, lam2 + dm, warp, lane);   // y = dU x_k
+      __syncthreads();
+      double s = 0.0;
+      for (int e = tid; e < dm; e += 256) s += lam[e] * lam2[e] + lam[dm + e] * lam2[dm + e];  // Re(conj(lam) .* y)
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (tid < 4) red[tid] = 0.0;
+      __syncthreads();
+      if (lane == 0) atomicAdd(&red[0], s);
+      __syncthreads();
+      if (tid == 0) g.dJdu[((size_t)b * nt + k) * g.nc + j] = red[0];
+      __syncthreads();
+    }
+    const double* Uk = g.U + ((size_t)b * nt + k) * g.slot;
+    g_matvec<true>(Uk, Uk + plane, d, g.S, m, lam, lam + dm, lam2, lam2 + dm, warp, lane);       // lam_k = U_k' lam_{k+1}
+    __syncthreads();
+    if (pen) {
+      for (int e = tid; e < dm; e += 256) { const int r = e / m, c = e - r * m; if (penalised(r, c)) { lam2[e] = fma(2.0 * g.mu, xk[e], lam2[e]); lam2[dm + e] = fma(2.0 * g.mu, xk[dm + e], lam2[dm + e]); } }
+      __syncthreads();
+    }
+    double* t = lam; lam = lam2; lam2 = t;
+    if (g.store_costates && g.LAM) store(g.LAM + ((size_t)b * (nt + 1) + k) * 2 * dm, lam);
+  }
+  if (g.lam_start) store(g.lam_start + (size_t)b * 2 * dm, lam);
+}
+
+}  // namespace qoc

@@ -95,7 +95,7 @@ def test_known_answers_full_size(golden_dir):
 @pytest.mark.parametrize("d,nt,nc,m,order", [
     (3, 17, 1, 1, 0), (4, 9, 2, 4, 3), (8, 33, 2, 8, 0), (9, 100, 2, 4, 4), (12, 40, 3, 2, 0), (13, 21, 1, 3, 2),
     (16, 50, 2, 4, 0), (17, 30, 2, 1, 3), (20, 25, 1, 5, 0), (21, 19, 2, 2, 1), (24, 60, 2, 2, 0), (25, 14, 1, 4, 0), (23, 14, 2, 4, 0),
-    (27, 80, 1, 1, 0), (28, 31, 1, 7, 3), (24, 31, 2, 7, 3), (27, 1, 1, 1, 0), (9, 2, 2, 4, 0),
+    (27, 80, 1, 1, 0), (28, 31, 1, 7, 3), (24, 31, 2, 7, 3), (27, 1, 1, 1, 0), (9, 2, 2, 4, 0), (25, 14, 2, 4, 0),
 ])
 def test_random_shapes_vs_oracle(d, nt, nc, m, order):
     """Ragged sizes across every shape class, incl. d not a multiple of 4/8, Nt = 1, m up to 8."""
@@ -109,12 +109,83 @@ def test_random_shapes_vs_oracle(d, nt, nc, m, order):
 
 
 def test_unsupported_sizes_fail_loudly():
-    """Sizes outside what the shared-memory-resident kernels cover must raise, never fall back."""
-    for d, nc in ((28, 2), (25, 2), (33, 1), (64, 2)):
-        cfg = o.config_synthetic(d, 4, nc=nc, m=2, seed=1)
-        with pytest.raises(q.QOCError) as ei:
-            gpu_eval(cfg, 0)
+    """Sizes no kernel covers must raise, never fall back to anything on the CPU."""
+    for d, nc, m in ((600, 1, 1), (16, 9, 2), (16, 1, 9)):
+        cfg = o.config_synthetic(d, 2, nc=nc, m=m, seed=1) if d < 100 else None
+        if cfg is None:
+            with pytest.raises(q.QOCError) as ei:
+                c = q.setup_grape_cache(np.zeros((d, d), complex), np.zeros((d, m), complex), (nc, 2))
+                c._ensure(np.zeros((d, d), complex), [np.zeros((d, d), complex)] * nc, np.zeros((d, m), complex))
+        else:
+            with pytest.raises(q.QOCError) as ei:
+                gpu_eval(cfg, 0)
         assert ei.value.status == _lib.ERR_UNSUPPORTED
+
+
+# ---- general path (d > 28, or a working set that does not fit shared memory): csrc/qoc_gpath.cuh --------------------
+@pytest.mark.parametrize("d,nt,nc,m,order", [
+    (28, 9, 2, 3, 0),      # d <= 28 but 17 + 3 nc - 2 matrices do not fit on chip -> general path
+    (29, 11, 1, 2, 0), (32, 20, 2, 4, 0), (33, 7, 2, 1, 3), (40, 16, 2, 2, 4), (50, 6, 3, 8, 0), (64, 12, 2, 4, 0),
+    (80, 8, 2, 2, 0), (100, 4, 1, 1, 2), (128, 5, 1, 2, 0), (130, 3, 2, 2, 1), (256, 2, 1, 4, 0),
+])
+def test_general_path_vs_oracle(d, nt, nc, m, order):
+    cfg = o.config_synthetic(d, nt, nc=nc, m=m, seed=2000 + d + nt)
+    Jo, go, co = o.evaluate(cfg, order=order)
+    J, g, cache = gpu_eval(cfg, order)
+    assert_parity(J, g, Jo, go)
+    assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-12
+    assert np.abs(cache.x - co["x"]).max() < 1e-12
+    assert np.abs(cache.lam - co["lam"]).max() < 1e-12
+
+
+def test_general_path_cavity_truncations():
+    """BASELINE.json configs[2]: cavity-qubit with cavity truncation 20 and 40 levels (d = 40, 80), CSV pulse."""
+    for N_cav, nt in ((20, 120), (40, 40)):
+        cfg = o.config_cavity(N_cav, Nt=nt)
+        for order in (3, 0):
+            Jo, go, _ = o.evaluate(cfg, order=order)
+            J, g, _ = gpu_eval(cfg, order)
+            assert_parity(J, g, Jo, go)
+
+
+def test_general_path_forced_on_small_sizes(monkeypatch):
+    """The same configs the shared-memory path serves, pushed through the general path (QOC_FORCE_GPATH=1):
+    penalty, host-closure costate, Taylor orders, several squarings, batches."""
+    monkeypatch.setenv("QOC_FORCE_GPATH", "1")
+    cfg = o.config_zz()
+    for order in (0, 3, 4):
+        Jo, go, co = o.evaluate(cfg, order=order)
+        J, g, cache = gpu_eval(cfg, order)
+        assert_parity(J, g, Jo, go)
+        assert cache.launch_count() > 3   # really the multi-launch path
+    pen = ([6, 7, 8], [0, 1, 2, 3], 0.22)
+    Jo, go, co = o.evaluate(cfg, order=4, penalty=pen)
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 100), dUkdp_order=4)
+    J, g = q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], q.setup_infidelity(cfg["T"], cfg["n"])[1],
+                      dUkdp_order=4, penalty=q.setup_state_penalty(*pen))
+    assert_parity(J, g, Jo, go)
+    assert np.abs(cache.lam - co["lam"]).max() < 1e-12
+    # host closure (lambda_final) path
+    c2 = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 100))
+    q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], c2)
+    Jf, dJf = o.setup_infidelity(cfg["T"], cfg["n"])
+    g2 = q.grape_sensitivity(cfg["A0"], cfg["A"], dJf, cfg["u"], cfg["x0"], c2, dUkdp_order=3)
+    _, go3, _ = o.evaluate(cfg, order=3)
+    assert np.abs(g2 - go3).max() <= TOL_G * np.abs(go3).max()
+    # several squarings
+    s = o.config_synthetic(12, 24, nc=2, m=3, seed=5)
+    s["A0"] = s["A0"] * 11
+    s["A"] = [a * 11 for a in s["A"]]
+    for order in (0, 3):
+        Jo, go, co = o.evaluate(s, order=order)
+        J, g, cache = gpu_eval(s, order)
+        assert abs(J - Jo) <= TOL_J and np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+    # batch
+    cb = o.config_zz_batch(5)
+    Jb, gb, _ = gpu_eval(cb, 3, u=cb["u_batch"], batch=5)
+    for b in (0, 4):
+        Jo, go, _ = o.evaluate(cb, order=3, u=cb["u_batch"][b])
+        assert_parity(Jb[b], gb[b], Jo, go)
 
 
 @pytest.mark.parametrize("scale", [1e-3, 0.3, 3.0, 11.0, 40.0])
