@@ -77,6 +77,16 @@ def build_workload(name, rank, mode):
         cfg = configs.config_cavity(12, Nt=550)
         desc = "C3 cavity_qubit N_cavity=12 d=24 m=2 nc=2 Nt=550, single pulse per GPU"
         batch, u = 1, cfg["u"]
+    elif name.startswith("cavity") and name[6:].isdigit():
+        ncav = int(name[6:])
+        cfg = configs.config_cavity(ncav, Nt=550)
+        desc = f"C3 cavity_qubit N_cavity={ncav} d={2 * ncav} m=2 nc=2 Nt=550, single pulse per GPU"
+        batch, u = 1, cfg["u"]
+    elif name.startswith("synth"):
+        d, nt = (int(x) for x in name[5:].split("x"))
+        cfg = configs.config_synthetic(d, nt)
+        desc = f"C5 synthetic GUE d={d} m=4 nc=2 Nt={nt}, single pulse per GPU"
+        batch, u = 1, cfg["u"]
     else:
         raise SystemExit(f"unknown workload {name}")
     return cfg, u, batch, desc
@@ -229,7 +239,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="frechet", choices=["frechet", "taylor3"])
-    ap.add_argument("--workload", default="bus", choices=["bus", "zz_batch", "cavity"])
+    ap.add_argument("--workload", default="bus",
+                    help="bus (default, BASELINE configs[1]) | zz_batch | cavity | cavity<N_cavity> | synth<d>x<Nt>")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default="batch", choices=["batch", "time"],
                     help="N>1: 'batch' = one pulse per rank, no collective (weak scaling, default); "
