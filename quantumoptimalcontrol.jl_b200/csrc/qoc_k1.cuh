@@ -58,6 +58,9 @@ enum : int { sA = 0, sA2, sA4, sA6, sWZ, sW, sU0, sU1, sN0, sN1, sM2, sM4, sM6, 
 // then nc slots E_j (control operators, resident for the whole kernel) and, for every control after the first, two
 // slots that carry (Lu - Lv, Lu + Lv) of that control from part1 to the tail
 __host__ __device__ constexpr int k1_num_slots(int nc) { return K1_FIXED_SLOTS + nc + 2 * (nc - 1); }
+// roles of the (D, S) pair of control j: control 0 uses (sM2, sLv); control j >= 1 the extra roles behind the fixed ones
+__host__ __device__ constexpr int k1_role_D(int j) { return j == 0 ? (int)sM2 : K1_FIXED_SLOTS + 2 * (j - 1); }
+__host__ __device__ constexpr int k1_role_S(int j) { return j == 0 ? (int)sLv : K1_FIXED_SLOTS + 2 * (j - 1) + 1; }
 // rows of zero padding needed behind the last slot: tile loads touch rows < 8*NT and k-steps rows < 4*KS
 template <class C>
 __host__ __device__ constexpr int k1_pad_rows(int d) {
@@ -107,9 +110,15 @@ struct WorkIter {
   }
 };
 
+// Slot roles are permuted at run time (ping-pong results, the scan's Q swap).  The role -> physical slot table lives in
+// REGISTERS, one entry per lane (lane r holds the slot of role r), and is read with a warp shuffle: a dynamically
+// indexed array would be demoted to local memory, whose lines get evicted to HBM by the U_k / dU_k store stream and
+// then cost a DRAM round trip at the start of every phase (measured: 13.5 M local loads per launch, 9% L1 hits).
 template <class C>
 struct K1Ctx {
-  Mat s[K1_FIXED_SLOTS];
+  double* base;              // slot 0
+  int plane;                 // d * S : offset of the imaginary plane
+  int role_slot;             // this lane's entry of the role table
   Mat E0, X0;                // first E slot / first extra (D,S) slot; slot j is at + j*slot_d
   int slot_d;
   int d, n2;                 // n2 = double2 per slot
@@ -120,6 +129,14 @@ struct K1Ctx {
     if (stamp_left > 0) { if (lane == 0) *stamp = clock64(); stamp++; stamp_left--; }
   }
 
+  __device__ __forceinline__ Mat S(int role) const {
+    const int si = __shfl_sync(0xffffffffu, role_slot, role);
+    Mat m; m.re = base + (size_t)si * slot_d; m.im = m.re + plane; return m;
+  }
+  // slots that are never permuted (U0/U1, N0/N1): no table lookup, usable from divergent code and the service warps
+  __device__ __forceinline__ Mat fixed(int slot) const {
+    Mat m; m.re = base + (size_t)slot * slot_d; m.im = m.re + plane; return m;
+  }
   __device__ __forceinline__ Mat E(int j) const { Mat m; m.re = E0.re + (size_t)j * slot_d; m.im = E0.im + (size_t)j * slot_d; return m; }
   __device__ __forceinline__ Mat extra(int i) const { Mat m; m.re = X0.re + (size_t)i * slot_d; m.im = X0.im + (size_t)i * slot_d; return m; }
   __device__ __forceinline__ void cbar() { bar_sync(BAR_C, C::NTHREADS); mark(); }
@@ -168,7 +185,11 @@ struct K1Ctx {
     e.alpha = alpha; e.c1 = c1; e.c2 = c2; e.c3 = c3; e.cI = cI; e.m1 = m1; e.m2 = m2; e.m3 = m3;
     return e;
   }
-  __device__ __forceinline__ void swap(int a, int b) { Mat t = s[a]; s[a] = s[b]; s[b] = t; }
+  __device__ __forceinline__ void swap(int a, int b) {
+    const int sa = __shfl_sync(0xffffffffu, role_slot, a), sb = __shfl_sync(0xffffffffu, role_slot, b);
+    if (lane == a) role_slot = sb;
+    if (lane == b) role_slot = sa;
+  }
 };
 
 // epilogue that writes the product result AND a second matrix at the same position:
@@ -393,17 +414,18 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
     while (ps > t && sq < 60) { t *= 2.f; sq++; }
   }
   const double scl = __hiloint2double((1023 - sq) << 20, 0);  // 2^-sq exactly
+  const Mat mX = c.S(sX), mA = c.S(sA);
 #pragma unroll
   for (int t = 0; t < GM::RPT; t++) {
     const int r = r0 + t * GM::G;
     if (act && r < d) {
       const int e = r * GM::S2 + cp;
       if (need_x) {
-        reinterpret_cast<double2*>(c.s[sX].re)[e] = xr[t];
-        reinterpret_cast<double2*>(c.s[sX].im)[e] = xi[t];
+        reinterpret_cast<double2*>(mX.re)[e] = xr[t];
+        reinterpret_cast<double2*>(mX.im)[e] = xi[t];
       }
-      reinterpret_cast<double2*>(c.s[sA].re)[e] = make_double2(xr[t].x * scl, xr[t].y * scl);
-      reinterpret_cast<double2*>(c.s[sA].im)[e] = make_double2(xi[t].x * scl, xi[t].y * scl);
+      reinterpret_cast<double2*>(mA.re)[e] = make_double2(xr[t].x * scl, xr[t].y * scl);
+      reinterpret_cast<double2*>(mA.im)[e] = make_double2(xi[t].x * scl, xi[t].y * scl);
     }
   }
   c.cbar();
@@ -414,7 +436,7 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
 template <class C>
 __device__ __forceinline__ void pade13_build_N(K1Ctx<C>& c, Mat U, Mat N) {
   const double* b = c_b13;
-  Mat A = c.s[sA], A2 = c.s[sA2], A4 = c.s[sA4], A6 = c.s[sA6], WZ = c.s[sWZ], W = c.s[sW];
+  Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), A6 = c.S(sA6), WZ = c.S(sWZ), W = c.S(sW);
   c.mm1(A2, A, A, NoEpi());
   c.mm1(A4, A2, A2, NoEpi());
   {  // A6 = A2 A4, and W1 = b13 A6 + b11 A4 + b9 A2 written by the same epilogue
@@ -453,8 +475,8 @@ __device__ __forceinline__ void pade13_build_N(K1Ctx<C>& c, Mat U, Mat N) {
 template <class C>
 __device__ __forceinline__ void frechet13_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat Sst) {
   const double* b = c_b13;
-  Mat A = c.s[sA], A2 = c.s[sA2], A4 = c.s[sA4], A6 = c.s[sA6], WZ = c.s[sWZ], W = c.s[sW], M2 = c.s[sM2],
-      M4 = c.s[sM4], M6 = c.s[sM6], T = c.s[sT], Lw = c.s[sLw], Lv = Sst;
+  Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), A6 = c.S(sA6), WZ = c.S(sWZ), W = c.S(sW), M2 = c.S(sM2),
+      M4 = c.S(sM4), M6 = c.S(sM6), T = c.S(sT), Lw = c.S(sLw), Lv = Sst;
   c.mm2(M2, A, E, E, A, NoEpi());
   c.mm2(M4, A2, M2, M2, A2, NoEpi());
   {  // M6 = A4 M2 + M4 A2 ; T = Lw1 = b13 M6 + b11 M4 + b9 M2 from the same epilogue
@@ -479,7 +501,7 @@ __device__ __forceinline__ void frechet13_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat
 // X (unscaled generator) in s[sX]; result -> out.  Uses sM2, sM4, sM6, sLw as scratch.
 template <class C>
 __device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, Mat Aj, Mat out, int order) {
-  Mat X = c.s[sX], AjX = c.s[sM2], XAj = c.s[sM4], X2 = c.s[sM6];
+  Mat X = c.S(sX), AjX = c.S(sM2), XAj = c.S(sM4), X2 = c.S(sM6);
   if (order <= 1) {
     slot_copy(out.re, Aj.re, c.n2, c.tid, C::NTHREADS);
     c.cbar();
@@ -508,8 +530,8 @@ __device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, Mat Aj, Mat out, in
     c.mm3(out, AjX, X, XAj, X, X, XAj, c.epi(1.0 / 6.0, 1.0, Aj, 0.5, AjX, 0.5, XAj, 0.0));
     return;
   }
-  c.mm3(c.s[sLw], AjX, X, XAj, X, X, XAj, c.epi(1.0 / 6.0, 1.0, Aj, 0.5, AjX, 0.5, XAj, 0.0));
-  c.mm4(out, AjX, X2, XAj, X2, X2, AjX, X2, XAj, c.epi(1.0 / 24.0, 1.0, c.s[sLw], 0.0, Aj, 0.0, Aj, 0.0));
+  c.mm3(c.S(sLw), AjX, X, XAj, X, X, XAj, c.epi(1.0 / 6.0, 1.0, Aj, 0.5, AjX, 0.5, XAj, 0.0));
+  c.mm4(out, AjX, X2, XAj, X2, X2, AjX, X2, XAj, c.epi(1.0 / 24.0, 1.0, c.S(sLw), 0.0, Aj, 0.0, Aj, 0.0));
 }
 
 template <class C>
@@ -531,7 +553,10 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
   c.warp = threadIdx.x >> 5;
   c.mi = c.warp / (C::NT / C::BN);
   c.nj0 = (c.warp % (C::NT / C::BN)) * C::BN;
-  for (int i = 0; i < K1_FIXED_SLOTS; i++) { c.s[i].re = base + (size_t)i * slot_d; c.s[i].im = c.s[i].re + d * S; }
+  c.base = base;
+  c.plane = d * S;
+  // physical layout: [fixed roles][E_0 .. E_{nc-1}][extra (D, S) pairs]; extra role r sits nc slots behind its index
+  c.role_slot = (c.lane < K1_FIXED_SLOTS) ? c.lane : c.lane + nc;
   c.E0.re = base + (size_t)K1_FIXED_SLOTS * slot_d; c.E0.im = c.E0.re + d * S;
   c.X0.re = base + (size_t)(K1_FIXED_SLOTS + nc) * slot_d; c.X0.im = c.X0.re + d * S;
   // tail: rows of zero padding (fragment loads of the last tile row / k-step run past the last slot), then small buffers
@@ -567,7 +592,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
       QOC_STAMP(8);
       bar_sync(BAR_NREADY + par, NALL);         // compute warps have formed N = V - U of this slice
       QOC_STAMP(9);
-      if (!(p.dbg_flags & 1)) all_ok &= service_inverse<C>(c.s[sN0 + par], d, sc, sw, lane);
+      if (!(p.dbg_flags & 1)) all_ok &= service_inverse<C>(c.fixed(sN0 + par), d, sc, sw, lane);
       QOC_STAMP(10);
       bar_arrive(BAR_NINV + par, NALL);         // N^-1 is in place
       dbg_i++;
@@ -598,17 +623,14 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
 #pragma unroll
     for (int j = 0; j < 8; j++) uj[j] = (j < nc && w.valid()) ? __ldg(p.u + ((size_t)w.b * p.nt + w.k) * nc + j) : 0.0;
   };
-  // (D, S) = (Lu - Lv, Lu + Lv) homes per control: control 0 uses (sM2, sLv); control j >= 1 the extra slots.
-  // They are tracked by pointer because the squaring phase ping-pongs results through scratch slots.
-  Mat Dh[8], Sh[8];
-  for (int j = 1; j < nc && j < 8; j++) { Dh[j] = c.extra(2 * (j - 1)); Sh[j] = c.extra(2 * (j - 1) + 1); }
+  // (D, S) = (Lu - Lv, Lu + Lv) homes per control: roles k1_role_D(j), k1_role_S(j)
   int par = 0;
   int sq = 0;
   const unsigned slot_bytes = (unsigned)slot_d * 8u;
   if (it.valid()) {
     load_u(it);
     sq = build_generator<C>(p, c, a0r, a0i, uj, need_x, sc);
-    pade13_build_N<C>(c, c.s[sU0], c.s[sN0]);
+    pade13_build_N<C>(c, c.fixed(sU0), c.fixed(sN0));
     bar_arrive(BAR_NREADY + 0, NALL);
   }
 
@@ -634,15 +656,16 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
         for (int j = 0; j < nc; j++) {
           if (c.tid == 0) bulk_wait_read();   // the previous bulk store out of sT has been read
           c.cbar();
-          taylor_jacobian<C>(c, c.E(j), c.s[sT], p.order);
+          taylor_jacobian<C>(c, c.E(j), c.S(sT), p.order);
           fence_async_smem();
           c.cbar();
-          if (c.tid == 0) { bulk_store(p.L + (slice * nc + j) * slot_d, c.s[sT].re, slot_bytes); bulk_commit(); }
+          const Mat Tj = c.S(sT);
+          if (c.tid == 0) { bulk_store(p.L + (slice * nc + j) * slot_d, Tj.re, slot_bytes); bulk_commit(); }
         }
       } else {
         // control 0 last: its (D, S) stay in (sM2, sLv), which the other controls' part1 uses as workspace (sM2)
         for (int j = nc - 1; j >= 0; j--)
-          frechet13_part1<C>(c, c.E(j), j == 0 ? c.s[sM2] : Dh[j], j == 0 ? c.s[sLv] : Sh[j]);
+          frechet13_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)));
       }
     }
     QOC_STAMP(1);
@@ -650,7 +673,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
     // ---- software pipeline: generator and Pade denominator of the NEXT slice while N^-1(k) is being formed ----
     if (nx.valid()) {
       sq = build_generator<C>(p, c, a0r, a0i, uj, need_x, sc);
-      pade13_build_N<C>(c, c.s[sU0 + (par ^ 1)], c.s[sN0 + (par ^ 1)]);
+      pade13_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
       bar_arrive(BAR_NREADY + (par ^ 1), NALL);
     }
     QOC_STAMP(2);
@@ -658,64 +681,64 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
     // ---- tail(k) ----
     bar_sync(BAR_NINV + par, NALL);
     QOC_STAMP(3);
-    Mat Ninv = c.s[sN0 + par], U = c.s[sU0 + par];
-    // R = N^-1 (V + U) = N^-1 (N + 2U) = I + 2 N^-1 U
-    Mat R = c.s[sT], tmp1 = c.s[sM6], tmp2 = c.s[sLw];
-    c.mm1(R, Ninv, U, c.epi(2.0, 0.0, U, 0.0, U, 0.0, U, 1.0));
+    const Mat Ninv = c.fixed(sN0 + par), U = c.fixed(sU0 + par);
+    // R = N^-1 (V + U) = N^-1 (N + 2U) = I + 2 N^-1 U   (R lives in role sT; results ping-pong by swapping roles)
+    c.mm1(c.S(sT), Ninv, U, c.epi(2.0, 0.0, U, 0.0, U, 0.0, U, 1.0));
     if (p.want_jac && !taylor) {
-      Mat Lc[8];
-      for (int j = 0; j < nc; j++) {
-        Mat Dj = j == 0 ? c.s[sM2] : Dh[j], Sj = j == 0 ? c.s[sLv] : Sh[j];
-        // rhs = (Lu + Lv) + (Lu - Lv) R -> sM4 ;  L = 2^-s N^-1 rhs -> in place of D_j
-        c.mm1(c.s[sM4], Dj, R, c.epi(1.0, 1.0, Sj, 0.0, Sj, 0.0, Sj, 0.0));
-        c.mm1(Dj, Ninv, c.s[sM4], c.epi(scl, 0.0, Ninv, 0.0, Ninv, 0.0, Ninv, 0.0));
-        Lc[j] = Dj;
-      }
-      // squaring phase: L <- R L + L R ; R <- R R   (results ping-pong through tmp1 / tmp2)
-      for (int t = 0; t < sq_cur; t++) {
+      {
+        const Mat R = c.S(sT), rhs = c.S(sM4);
         for (int j = 0; j < nc; j++) {
-          c.mm2(tmp1, R, Lc[j], Lc[j], R, NoEpi());
-          Mat x = tmp1; tmp1 = Lc[j]; Lc[j] = x;
+          const Mat Dj = c.S(k1_role_D(j)), Sj = c.S(k1_role_S(j));
+          // rhs = (Lu + Lv) + (Lu - Lv) R -> sM4 ;  L = 2^-s N^-1 rhs -> in place of D_j
+          c.mm1(rhs, Dj, R, c.epi(1.0, 1.0, Sj, 0.0, Sj, 0.0, Sj, 0.0));
+          c.mm1(Dj, Ninv, rhs, c.epi(scl, 0.0, Ninv, 0.0, Ninv, 0.0, Ninv, 0.0));
         }
-        c.mm1(tmp2, R, R, NoEpi());
-        Mat x = tmp2; tmp2 = R; R = x;
       }
-      // (stored below together with R, asynchronously)
-      // every slot touched here is dead once stored: hand the (permuted) physical slots back to their roles
-      c.s[sM2] = Lc[0];
-      for (int j = 1; j < nc; j++) Dh[j] = Lc[j];
-      c.s[sM6] = tmp1;
+      // squaring phase: L <- R L + L R ; R <- R R   (results land in scratch roles sM6 / sLw, then the roles swap)
+      for (int t = 0; t < sq_cur; t++) {
+        const Mat R = c.S(sT);
+        for (int j = 0; j < nc; j++) {
+          const Mat Lj = c.S(k1_role_D(j));
+          c.mm2(c.S(sM6), R, Lj, Lj, R, NoEpi());
+          c.swap(sM6, k1_role_D(j));
+        }
+        c.mm1(c.S(sLw), R, R, NoEpi());
+        c.swap(sT, sLw);
+      }
     } else {
       for (int t = 0; t < sq_cur; t++) {
-        c.mm1(tmp2, R, R, NoEpi());
-        Mat x = tmp2; tmp2 = R; R = x;
+        const Mat R = c.S(sT);
+        c.mm1(c.S(sLw), R, R, NoEpi());
+        c.swap(sT, sLw);
       }
     }
-    c.s[sT] = R; c.s[sLw] = tmp2;
+    const Mat R = c.S(sT);
     // U_k and dU_k/du_j leave through the copy engine (TMA bulk store); all generic-proxy writes of the slots were
     // ordered by the barrier that ended the last product, the proxy fence makes them visible to the async proxy
     fence_async_smem();
     c.cbar();
-    if (c.tid == 0 && !(p.dbg_flags & 4)) {
-      bulk_store(p.U + slice * slot_d, R.re, slot_bytes);
-      if (p.want_jac && !taylor) {
-        bulk_store(p.L + (slice * nc + 0) * slot_d, c.s[sM2].re, slot_bytes);
-        for (int j = 1; j < nc; j++) bulk_store(p.L + (slice * nc + j) * slot_d, Dh[j].re, slot_bytes);
-      }
-      bulk_commit();
+    {
+      const bool stL = p.want_jac && !taylor;
+      if (c.tid == 0 && !(p.dbg_flags & 4)) bulk_store(p.U + slice * slot_d, R.re, slot_bytes);
+      if (stL)
+        for (int j = 0; j < nc; j++) {
+          const Mat Lj = c.S(k1_role_D(j));
+          if (c.tid == 0 && !(p.dbg_flags & 4)) bulk_store(p.L + (slice * nc + j) * slot_d, Lj.re, slot_bytes);
+        }
+      if (c.tid == 0) bulk_commit();
     }
     QOC_STAMP(4);
 
     // ---- level-1 scan: Q <- U_k Q ----
     if (first_of_seg) {
-      slot_copy(c.s[sQ].re, R.re, c.n2, c.tid, C::NTHREADS);
+      slot_copy(c.S(sQ).re, R.re, c.n2, c.tid, C::NTHREADS);
       c.cbar();
     } else {
-      c.mm1(c.s[sM4], R, c.s[sQ], NoEpi());
+      c.mm1(c.S(sM4), R, c.S(sQ), NoEpi());
       c.swap(sM4, sQ);
     }
     if (last_of_seg) {
-      slot_copy(p.Q + (size_t)seg * slot_d, c.s[sQ].re, c.n2, c.tid, C::NTHREADS);
+      slot_copy(p.Q + (size_t)seg * slot_d, c.S(sQ).re, c.n2, c.tid, C::NTHREADS);
       c.cbar();
     }
     if (c.tid == 0) {
