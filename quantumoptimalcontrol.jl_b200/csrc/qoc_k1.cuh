@@ -67,13 +67,22 @@ __host__ __device__ constexpr int k1_pad_rows(int d) {
   return ((8 * C::NT > 4 * C::KS ? 8 * C::NT : 4 * C::KS) - d + 1) & ~1;  // even: keeps 16-byte alignment (S is even anyway)
 }
 
-// named barriers: 1 = compute warps, 7 = service warps, 2/3 = "N ready" (even/odd slice), 4/5 = "N^-1 ready"
-enum : int { BAR_C = 1, BAR_NREADY = 2, BAR_NINV = 4 };
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int n) {
+// named barriers: 1 = compute warps, 6 = service warps, 2/3 = "N ready" (even/odd slice), 4/5 = "N^-1 ready".
+// The ids are IMMEDIATES in the SASS (a register id makes ptxas reserve all 16 hardware barriers for the CTA, which caps
+// the number of co-resident CTAs of the small shape classes).
+enum : int { BAR_C = 1, BAR_NREADY = 2, BAR_NINV = 4, BAR_SVC = 6 };
+template <int ID>
+__device__ __forceinline__ void bar_sync_i(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_arrive_i(int n) {
   __threadfence_block();
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(n) : "memory");
 }
+// parity-selected pairs (par is CTA-uniform)
+template <int ID0>
+__device__ __forceinline__ void bar_sync_p(int par, int n) { if (par) bar_sync_i<ID0 + 1>(n); else bar_sync_i<ID0>(n); }
+template <int ID0>
+__device__ __forceinline__ void bar_arrive_p(int par, int n) { if (par) bar_arrive_i<ID0 + 1>(n); else bar_arrive_i<ID0>(n); }
 
 // Asynchronous shared -> global bulk copy (TMA, SASS UBLKCP): one thread issues it, the copy engine streams the slot out
 // while the warps go on.  The source slot may be overwritten once bulk_wait_read() has returned.
@@ -139,7 +148,7 @@ struct K1Ctx {
   }
   __device__ __forceinline__ Mat E(int j) const { Mat m; m.re = E0.re + (size_t)j * slot_d; m.im = E0.im + (size_t)j * slot_d; return m; }
   __device__ __forceinline__ Mat extra(int i) const { Mat m; m.re = X0.re + (size_t)i * slot_d; m.im = X0.im + (size_t)i * slot_d; return m; }
-  __device__ __forceinline__ void cbar() { bar_sync(BAR_C, C::NTHREADS); mark(); }
+  __device__ __forceinline__ void cbar() { bar_sync_i<BAR_C>(C::NTHREADS); mark(); }
 
   // dst = epilogue(sum of products); one compute-warp barrier at the end
   template <class F>
@@ -258,7 +267,7 @@ struct SvcScratch {
   float colsum[22][32];  // partial column sums of the generator build, one row per row group (compute warps)
 };
 
-__device__ __forceinline__ void bar_svc() { asm volatile("bar.sync %0, %1;" ::"r"(7), "r"(NSW * 32) : "memory"); }
+__device__ __forceinline__ void bar_svc() { bar_sync_i<BAR_SVC>(NSW * 32); }
 
 template <class C>
 __device__ __noinline__ bool service_inverse(Mat N, int d, SvcScratch* sc, int sw, int lane) {
@@ -535,7 +544,7 @@ __device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, Mat Aj, Mat out, in
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params p) {
+__global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int S = C::S;
   constexpr int NALL = C::NTHREADS + NSW * 32;
@@ -590,11 +599,11 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
     int dbg_i = (sw == 0) ? 0 : (1 << 30);
     while (it.valid()) {
       QOC_STAMP(8);
-      bar_sync(BAR_NREADY + par, NALL);         // compute warps have formed N = V - U of this slice
+      bar_sync_p<BAR_NREADY>(par, NALL);         // compute warps have formed N = V - U of this slice
       QOC_STAMP(9);
       if (!(p.dbg_flags & 1)) all_ok &= service_inverse<C>(c.fixed(sN0 + par), d, sc, sw, lane);
       QOC_STAMP(10);
-      bar_arrive(BAR_NINV + par, NALL);         // N^-1 is in place
+      bar_arrive_p<BAR_NINV>(par, NALL);         // N^-1 is in place
       dbg_i++;
       par ^= 1;
       it.next();
@@ -631,7 +640,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
     load_u(it);
     sq = build_generator<C>(p, c, a0r, a0i, uj, need_x, sc);
     pade13_build_N<C>(c, c.fixed(sU0), c.fixed(sN0));
-    bar_arrive(BAR_NREADY + 0, NALL);
+    bar_arrive_i<BAR_NREADY>(NALL);
   }
 
   while (it.valid()) {
@@ -674,12 +683,12 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, 1) k1_kernel(K1Params 
     if (nx.valid()) {
       sq = build_generator<C>(p, c, a0r, a0i, uj, need_x, sc);
       pade13_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
-      bar_arrive(BAR_NREADY + (par ^ 1), NALL);
+      bar_arrive_p<BAR_NREADY>(par ^ 1, NALL);
     }
     QOC_STAMP(2);
 
     // ---- tail(k) ----
-    bar_sync(BAR_NINV + par, NALL);
+    bar_sync_p<BAR_NINV>(par, NALL);
     QOC_STAMP(3);
     const Mat Ninv = c.fixed(sN0 + par), U = c.fixed(sU0 + par);
     // R = N^-1 (V + U) = N^-1 (N + 2U) = I + 2 N^-1 U   (R lives in role sT; results ping-pong by swapping roles)

@@ -35,6 +35,7 @@ struct Cfg {
   static constexpr int NW = NBLK;                      // warps per CTA in K1
   static constexpr int NTHREADS = NW * 32;
   static constexpr int DMAX = (8 * NT_ < 4 * KS_) ? 8 * NT_ : 4 * KS_;  // largest d this class serves
+  static constexpr int MINB = (NT_ <= 2) ? 3 : 1;     // K1 CTAs per SM the register budget is sized for
 };
 
 // Complex products are formed with THREE real tile products (the "3M" scheme, as in BLAS zgemm3m):

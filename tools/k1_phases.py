@@ -5,9 +5,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import qoc_b200 as q
 from qoc_b200 import configs, _lib
-cfg = configs.config_bus(Nt=10000)
-cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=0, store_costates=False)
-q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], q.setup_infidelity(cfg["T"], cfg["n"])[1], dUkdp_order=0)
+name = sys.argv[2] if len(sys.argv) > 2 else "bus"
+if name == "zz_batch":
+    cfg = configs.config_zz_batch(4096); u = cfg["u_batch"]; batch = 4096
+elif name == "cavity":
+    cfg = configs.config_cavity(12, Nt=550); u = cfg["u"]; batch = 1
+else:
+    cfg = configs.config_bus(Nt=10000); u = cfg["u"]; batch = 1
+cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], u.shape[-2:], batch=batch, dUkdp_order=0, store_costates=False)
+cost = q.setup_infidelity(cfg["T"], cfg["n"]) if cfg["cost"] == 0 else q.setup_infidelity_abs_trace(cfg["T"])
+q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], cost[1], dUkdp_order=0)
 lib = _lib.load()
 n = 8
 out = np.zeros(16 * n + 4096, dtype=np.int64)

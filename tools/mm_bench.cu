@@ -13,26 +13,26 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) bench(int d, int reps, long lo
   K1Ctx<C> c;
   c.d = d; c.slot_d = slot_d; c.n2 = slot_d / 2; c.tid = threadIdx.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5;
   c.mi = c.warp / (C::NT / C::BN); c.nj0 = (c.warp % (C::NT / C::BN)) * C::BN;
-  for (int i = 0; i < 8; i++) { c.s[i].re = base + (size_t)i * slot_d; c.s[i].im = c.s[i].re + d * C::S; }
+  c.base = base; c.plane = d * C::S; c.role_slot = c.lane;
   for (int e = threadIdx.x; e < 9 * slot_d; e += C::NTHREADS) base[e] = 0.0;
   __syncthreads();
   for (int e = threadIdx.x; e < d * d; e += C::NTHREADS) {
     int r = e / d, cc = e % d;
-    for (int i = 0; i < 4; i++) { c.s[i].re[r * C::S + cc] = 1e-3 * ((e + i) % 7) ; c.s[i].im[r * C::S + cc] = 1e-3 * ((e + 2 * i) % 5); }
+    for (int i = 0; i < 4; i++) { c.fixed(i).re[r * C::S + cc] = 1e-3 * ((e + i) % 7) ; c.fixed(i).im[r * C::S + cc] = 1e-3 * ((e + 2 * i) % 5); }
   }
   __syncthreads();
   long long t0 = clock64();
   for (int it = 0; it < reps; it++) {
-    if (MODE == 0) c.mm1(c.s[4 + (it & 1)], c.s[0], c.s[1], NoEpi());
-    if (MODE == 1) c.mm2(c.s[4 + (it & 1)], c.s[0], c.s[1], c.s[2], c.s[3], NoEpi());
-    if (MODE == 2) c.mm1(c.s[4 + (it & 1)], c.s[0], c.s[1], c.epi(1.0, 0.5, c.s[2], 0.25, c.s[3], 0.125, c.s[0], 1.0));
-    if (MODE == 3) { Acc<C::BN> acc; acc.zero(); mm_acc<C, false>(acc, c.s[0], c.s[1], c.mi, c.nj0, c.lane); sink[threadIdx.x] += acc.re[0][0] + acc.im[1][1]; }
-    if (MODE == 4) { c.lc(c.s[4], 0.5, c.s[0], 0.25, c.s[1], 0.125, c.s[2], 0.0); c.cbar(); }
+    if (MODE == 0) c.mm1(c.fixed(4 + (it & 1)), c.fixed(0), c.fixed(1), NoEpi());
+    if (MODE == 1) c.mm2(c.fixed(4 + (it & 1)), c.fixed(0), c.fixed(1), c.fixed(2), c.fixed(3), NoEpi());
+    if (MODE == 2) c.mm1(c.fixed(4 + (it & 1)), c.fixed(0), c.fixed(1), c.epi(1.0, 0.5, c.fixed(2), 0.25, c.fixed(3), 0.125, c.fixed(0), 1.0));
+    if (MODE == 3) { Acc<C::BN> acc; acc.zero(); mm_acc<C, false>(acc, c.fixed(0), c.fixed(1), c.mi, c.nj0, c.lane); sink[threadIdx.x] += acc.re[0][0] + acc.im[1][1]; }
+    if (MODE == 4) { c.lc(c.fixed(4), 0.5, c.fixed(0), 0.25, c.fixed(1), 0.125, c.fixed(2), 0.0); c.cbar(); }
     if (MODE == 5) { c.cbar(); }
   }
   long long t1 = clock64();
   if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
-  sink[threadIdx.x] += c.s[4].re[threadIdx.x % (d * C::S)];
+  sink[threadIdx.x] += c.fixed(4).re[threadIdx.x % (d * C::S)];
 }
 
 int main() {
