@@ -10,6 +10,7 @@
 #include "../../include/qoc_b200.h"
 #include "qoc_k1.cuh"
 #include "qoc_k23.cuh"
+#include "qoc_sweep.cuh"
 #include "qoc_gpath.cuh"
 
 using namespace qoc;
@@ -33,6 +34,14 @@ struct qoc_handle {
   double *dx0 = nullptr, *dT = nullptr, *dxs = nullptr, *dle = nullptr, *dX = nullptr, *dLAM = nullptr;
   double *dxf = nullptr, *dlam0 = nullptr, *dJ = nullptr, *dg = nullptr, *dflops = nullptr, *dlamf = nullptr;
   double *dS = nullptr;
+  // second-generation sweeps (csrc/qoc_sweep.cuh): two-level boundary scan K2G + K3N; used when there is no running penalty
+  bool new_k2 = false, new_k3 = false;
+  int G = 1;                  // groups per pulse in K2G
+  double* dPg = nullptr;      // [batch * G] group propagators
+  unsigned* dsync = nullptr;  // [batch] arrival counters of the per-pulse barrier (monotone, never reset)
+  unsigned sync_epoch = 0;
+  size_t k2g_smem = 0, k3n_smem = 0;
+  int k3n_threads = 0, k3n_ngrp = 1, k3n_grid = 0;
   // general path (d > 28): matrices in HBM/L2, batched launches over chunks of slices (csrc/qoc_gpath.cuh)
   bool gpath = false;
   int gchunk = 0, gnw = 0;
@@ -117,6 +126,19 @@ static size_t k3_smem_bytes(int d, int m, int nc, int S, int NT, int seg_cap, bo
          (size_t)2 * nc * NT * 8 + 64;
 }
 
+template <class C>
+static size_t k2g_smem_bytes(int d, int m) {
+  const size_t slot = (size_t)2 * d * C::S * 8;
+  return (size_t)(SW_NST + 2) * slot + (size_t)k1_pad_rows<C>(d) * C::S * 8 + (size_t)4 * state_rows<C>() * 2 * m * 8 + 4 * 8 +
+         2 * SW_NST * 8 + 64;
+}
+template <class C>
+static size_t k3n_smem_bytes(int d, int m, int nc, int seg_cap) {
+  const size_t slot = (size_t)2 * d * C::S * 8;
+  return (size_t)SW_NST * slot + (size_t)k1_pad_rows<C>(d) * C::S * 8 + (size_t)(2 * seg_cap + 1) * state_rows<C>() * 2 * m * 8 +
+         2 * SW_NST * 8 + 64;
+}
+
 static void to_planar(const double* M, int d, int S, double* out) {  // c128 col-major -> planar slot
   memset(out, 0, sizeof(double) * 2 * d * S);
   for (int c = 0; c < d; c++)
@@ -164,10 +186,11 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
   cudaSetDevice(h->prob.device);
   double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
-                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax};
+                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->dstatus) cudaFree(h->dstatus);
+  if (h->dsync) cudaFree(h->dsync);
   if (h->dpen_rows) cudaFree(h->dpen_rows);
   if (h->dpen_cols) cudaFree(h->dpen_cols);
   for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
@@ -287,6 +310,35 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     h->spp = (int)spp;
     h->nseg = (int)(spp * p.batch);
     h->k1_grid = (int)(h->nseg < target ? h->nseg : target);
+    // second-generation sweeps (no running penalty)
+    const char* old_sw = getenv("QOC_OLD_SWEEPS");
+    const bool pen = h->row_mask != 0u && h->col_mask != 0u && p.mu != 0.0;
+    if (!pen && !(old_sw && old_sw[0] == '1')) {
+      h->k3n_threads = (C::NT + 1 + K3N_CW) * 32;
+      h->k3n_smem = k3n_smem_bytes<C>(p.d, p.m, p.nc, h->seg_cap);
+      if (h->k3n_smem <= (size_t)dp.sharedMemPerBlockOptin) {
+        QOC_CUDA(h, cudaFuncSetAttribute(k3n_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k3n_smem));
+        int occ3 = 1;
+        QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k3n_kernel<C>, h->k3n_threads, h->k3n_smem));
+        if (occ3 < 1) occ3 = 1;
+        h->k3n_grid = h->nseg < h->nsm * occ3 ? h->nseg : h->nsm * occ3;
+        h->new_k3 = true;
+      }
+      // K2G: G groups per pulse, chosen to balance the spp/G tile products against the 2 G + 2 spp/G mat-vec steps;
+      // every CTA of the launch must be resident at once (per-pulse barrier)
+      h->k2g_smem = k2g_smem_bytes<C>(p.d, p.m);
+      if (spp >= 8 && h->k2g_smem <= (size_t)dp.sharedMemPerBlockOptin) {
+        QOC_CUDA(h, cudaFuncSetAttribute(k2g_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k2g_smem));
+        int occ2 = 0;
+        QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2g_kernel<C>, C::NTHREADS + 32, h->k2g_smem));
+        const long long cap = (long long)h->nsm * occ2;
+        long long gs = llround(sqrt(0.29 * (double)spp));
+        if (gs < 1) gs = 1;
+        long long G = (spp + gs - 1) / gs;
+        if (G * p.batch > cap) G = cap / p.batch;
+        if (G >= 2) { h->G = (int)G; h->new_k2 = true; }
+      }
+    }
     return QOC_OK;
   });
   if (rc != QOC_OK) { if (g_create_error.empty()) g_create_error = h->err; delete h; return rc; }
@@ -329,6 +381,11 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     };
     h->normA0 = norm1(A0);
     for (int j = 0; j < p.nc; j++) h->normA[j] = norm1(A + (size_t)j * 2 * p.d * p.d);
+  }
+  if (h->new_k2) {
+    CR(cudaMalloc(&h->dPg, (size_t)p.batch * h->G * slotB));
+    CR(cudaMalloc(&h->dsync, (size_t)p.batch * 4));
+    CR(cudaMemset(h->dsync, 0, (size_t)p.batch * 4));
   }
   CR(cudaMalloc(&h->dcs, (size_t)h->nseg * dmB));
   CR(cudaMalloc(&h->dJpen, (size_t)p.batch * 8));
@@ -590,6 +647,17 @@ static int launch_k2(qoc_handle* h, int phase, bool no_backward, const double* d
   q.x_start_ext = d_x_start;
   q.store_states = 1;
   if (d_J) q.J = d_J;
+  if (h->new_k2 && phase != 3) {
+    K2GParams P;
+    P.q = q; P.G = h->G; P.Pg = h->dPg; P.sync = h->dsync;
+    h->sync_epoch += 1;
+    P.sync_target = (unsigned)h->G * h->sync_epoch;
+    with_cfg(h->cfg, [&](auto c) {
+      typedef decltype(c) C;
+      k2g_kernel<C><<<h->prob.batch * h->G, C::NTHREADS + 32, h->k2g_smem, st>>>(P);
+      return 0;
+    });
+  } else
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
     k2_kernel<C><<<h->prob.batch, C::NT * 32, h->k2_smem, st>>>(q);
@@ -602,11 +670,19 @@ static int launch_k2(qoc_handle* h, int phase, bool no_backward, const double* d
 
 static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d_dJdu, cudaStream_t st, int mode = 0) {
   K23Params q = base_k23(h);
+  q.dbg = h->dbg; q.dbg_steps = h->dbg_slices;
   q.k3_mode = mode;
   q.want_grad = want_grad ? 1 : 0;
   q.store_states = store_states ? 1 : 0;
   if (d_dJdu) q.dJdu = d_dJdu;
   const int grid = h->nseg < h->nsm * 2 ? h->nseg : h->nsm * 2;
+  if (h->new_k3 && mode == 0)
+    with_cfg(h->cfg, [&](auto c) {
+      typedef decltype(c) C;
+      k3n_kernel<C><<<h->k3n_grid, h->k3n_threads, h->k3n_smem, st>>>(q, h->seg_cap);
+      return 0;
+    });
+  else
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
     k3_kernel<C><<<grid, h->k3_threads, h->k3_smem, st>>>(q, h->seg_cap);
@@ -923,5 +999,20 @@ extern "C" int qoc_debug_k1_timeline(qoc_handle* h, long long* out, int nslices,
   if (rc == QOC_OK) cudaMemcpy(out, h->dbg, sizeof(long long) * (16 * nslices + ((h->dbg_flags & 2) ? 4096 : 0)), cudaMemcpyDeviceToHost);
   cudaFree(h->dbg);
   h->dbg = nullptr; h->dbg_slices = 0; h->dbg_flags = 0;
+  return rc;
+}
+
+// Developer aid: K3N once on the cached evaluation with clock64 stamps of CTA 0's recurrence warp 0 (4 per step).
+extern "C" int qoc_debug_k3_timeline(qoc_handle* h, long long* out, int nsteps) {
+  if (!h || !out || nsteps <= 0 || !h->have_u) return QOC_ERR_INVALID;
+  QOC_CUDA(h, cudaSetDevice(h->prob.device));
+  QOC_CUDA(h, cudaMalloc(&h->dbg, sizeof(long long) * 4 * nsteps));
+  QOC_CUDA(h, cudaMemset(h->dbg, 0, sizeof(long long) * 4 * nsteps));
+  h->dbg_slices = nsteps;
+  int rc = launch_k3(h, true, false, nullptr, h->stream);
+  cudaStreamSynchronize(h->stream);
+  if (rc == QOC_OK) cudaMemcpy(out, h->dbg, sizeof(long long) * 4 * nsteps, cudaMemcpyDeviceToHost);
+  cudaFree(h->dbg);
+  h->dbg = nullptr; h->dbg_slices = 0;
   return rc;
 }

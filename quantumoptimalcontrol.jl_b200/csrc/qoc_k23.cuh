@@ -120,6 +120,8 @@ struct K23Params {
   double* cs;                  // [nseg] d x m c128: affine term of the segment-level costate recurrence
   double* Jpen;                // [batch] sum_k L(x_k), accumulated by K3 (atomicAdd)
   int k3_mode;                 // 0: forward (+ backward + contraction if want_grad); 1: forward + penalty pre-pass
+  long long* dbg;              // developer timeline (NULL in production): clock64 stamps of CTA 0, 4 per recurrence step
+  int dbg_steps;
 };
 
 // mv_store variant that adds the penalty gradient 2 mu x[r][c] (src/penalty_fcns.jl:5-9) to the stored costate
