@@ -47,6 +47,9 @@ struct qoc_handle {
   int gchunk = 0, gnw = 0;
   double* gW = nullptr;       // workspace: gnw slots x gchunk slices
   double* dumax = nullptr;    // max_k |u_jk| per control
+  double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
+  int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
+  bool gs2 = false;           // second-generation general-path sweeps (no running penalty)
   double normA0 = 0.0, normA[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long row_mask64 = 0ull;
   long long* dbg = nullptr;  // developer timeline buffer (qoc_debug_k1_timeline)
@@ -186,7 +189,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
   cudaSetDevice(h->prob.device);
   double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
-                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg};
+                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg, h->dQ2};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->dstatus) cudaFree(h->dstatus);
@@ -263,6 +266,18 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     h->S = S;
     h->slot_d = 2 * p.d * S;
     h->spp = 1; h->nseg = p.batch; h->seg_cap = p.nt; h->k1_grid = 0; h->k3_threads = 256;
+    {
+      const char* old_sw = getenv("QOC_OLD_SWEEPS");
+      const bool pen = h->row_mask64 != 0ull && h->col_mask != 0u && p.mu != 0.0;
+      if (!pen && !(old_sw && old_sw[0] == '1') && p.nt >= 4) {
+        // two-level sweeps: L slices per segment ~ sqrt(nt) balances the boundary walk (2 spp steps) against the
+        // per-segment sweeps (2 L steps)
+        int L = (int)ceil(sqrt((double)p.nt));
+        if (L < 2) L = 2;
+        const int spp = (p.nt + L - 1) / L;
+        if ((long long)spp * p.batch <= 65535) { h->gs2 = true; h->gL = L; h->spp = spp; h->nseg = spp * p.batch; h->seg_cap = L; }
+      }
+    }
     h->k1_smem = h->k2_smem = h->k3_smem = 0;
     h->gnw = 24 + p.nc;
     const size_t slotBg = (size_t)h->slot_d * 8;
@@ -362,7 +377,8 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   CR(cudaMalloc(&h->dxs, (size_t)h->nseg * dmB));
   CR(cudaMalloc(&h->dle, (size_t)h->nseg * dmB));
   CR(cudaMalloc(&h->dX, (size_t)p.batch * (p.nt + 1) * dmB));
-  if (p.store_costates) CR(cudaMalloc(&h->dLAM, (size_t)p.batch * (p.nt + 1) * dmB));
+  if (p.store_costates || h->gs2) CR(cudaMalloc(&h->dLAM, (size_t)p.batch * (p.nt + 1) * dmB));
+  if (h->gs2) CR(cudaMalloc(&h->dQ2, (size_t)h->nseg * slotB));
   CR(cudaMalloc(&h->dxf, (size_t)p.batch * dmB));
   CR(cudaMalloc(&h->dlam0, (size_t)p.batch * dmB));
   CR(cudaMalloc(&h->dlamf, (size_t)p.batch * dmB));
@@ -473,6 +489,73 @@ struct GRun {
   void lin(int c, int nadd, const GOp* D, const double* beta, double gamma = 0.0) const { gemm(Wp(c), h->slot_d, 0, nullptr, nullptr, 0.0, nadd, D, beta, gamma); }
 };
 }  // namespace
+
+// Segment propagators of the general path: Q_seg = U_{k1-1} ... U_{k0}, one batched product launch per slice position of a
+// segment (all full-length segments of all pulses in one launch, the shorter last segments of the pulses in a second one).
+static int gpath_build_Q(qoc_handle* h, cudaStream_t st) {
+  const qoc_problem& p = h->prob;
+  const int L = h->gL, spp = h->spp, d = p.d;
+  const long long slot = h->slot_d;
+  const int len_last = p.nt - (spp - 1) * L;          // 1..L
+  const int tiles = (d + 31) / 32;
+  struct Grp { int inner, count, len; long long first; };   // segments si in [first, first + inner) of every pulse
+  Grp grp[2] = {{spp - 1, (spp - 1) * p.batch, L, 0}, {1, p.batch, len_last, spp - 1}};
+  if (len_last == L) { grp[0] = Grp{spp, spp * p.batch, L, 0}; grp[1].count = 0; }
+  for (int gi = 0; gi < 2; gi++) {
+    const Grp& G = grp[gi];
+    if (G.count <= 0) continue;
+    double* cur = h->dQ; double* oth = h->dQ2;
+    auto launch = [&](int npairs, const GOp* A, const GOp* B, int nadd, const GOp* D, double* C) {
+      GGemm g;
+      memset(&g, 0, sizeof g);
+      g.d = d; g.S = h->S; g.nb = G.count; g.npairs = npairs; g.nadd = nadd; g.alpha = 1.0; g.gamma = 0.0;
+      for (int i = 0; i < npairs; i++) { g.A[i] = A[i]; g.B[i] = B[i]; }
+      for (int i = 0; i < nadd; i++) { g.D[i] = D[i]; g.beta[i] = 1.0; }
+      g.C = C + G.first * slot; g.cstride = slot; g.cinner = G.inner; g.cstride2 = (long long)spp * slot;
+      g_gemm_kernel<<<dim3(tiles, tiles, G.count), 256, 0, st>>>(g);
+      h->launches++;
+    };
+    auto Uop = [&](int t) { return GOp{h->dU + (G.first * L + t) * slot, (long long)L * slot, G.inner, (long long)p.nt * slot}; };
+    auto Qop = [&](const double* buf) { return GOp{buf + G.first * slot, slot, G.inner, (long long)spp * slot}; };
+    { GOp D0 = Uop(0); launch(0, nullptr, nullptr, 1, &D0, cur); }                 // Q = U_{k0}
+    for (int t = 1; t < G.len; t++) {
+      GOp A = Uop(t), B = Qop(cur);
+      launch(1, &A, &B, 0, nullptr, oth);                                           // Q <- U_{k0+t} Q
+      double* x = cur; cur = oth; oth = x;
+    }
+    if (cur != h->dQ) { GOp D0 = Qop(cur); launch(0, nullptr, nullptr, 1, &D0, h->dQ); }
+  }
+  QOC_CUDA(h, cudaGetLastError());
+  return QOC_OK;
+}
+
+static int gpath_sweep2(qoc_handle* h, int mode, bool skip_bwd, bool want_grad, const double* d_lam_final, const double* d_x_start,
+                        double* d_J, double* d_dJdu, cudaStream_t st) {
+  const qoc_problem& p = h->prob;
+  GS g;
+  memset(&g, 0, sizeof g);
+  g.d = p.d; g.S = h->S; g.m = p.m; g.nc = p.nc; g.nt = p.nt; g.cost = p.cost; g.n = p.n;
+  g.spp = h->spp; g.L = h->gL; g.mode = mode; g.skip_bwd = skip_bwd ? 1 : 0; g.slot = h->slot_d;
+  g.U = h->dU; g.L_ = h->dL; g.Q = h->dQ; g.x0 = h->dx0; g.x_start_ext = d_x_start; g.T = h->dT; g.lam_final = d_lam_final;
+  g.xs_start = h->dxs; g.lam_end = h->dle; g.X = h->dX; g.LAM = h->dLAM; g.x_final = h->dxf; g.lam_start = h->dlam0;
+  g.J = d_J ? d_J : h->dJ; g.dJdu = d_dJdu ? d_dJdu : h->dg;
+  const size_t st_smem = (size_t)2 * ((p.d + 7) / 8 * 8) * 2 * p.m * 8;
+  gs_scan_kernel<<<p.batch, GS_NW * 32, st_smem, st>>>(g);
+  h->launches++;
+  const int grid = h->nseg < h->nsm * 4 ? h->nseg : h->nsm * 4;
+  gs_seg_kernel<<<grid, GS_NW * 32, st_smem, st>>>(g, h->nseg);
+  h->launches++;
+  if (want_grad && (mode == 2 || (mode == 0 && !skip_bwd))) {
+    const size_t c_smem = (size_t)(h->S + p.d) * 2 * p.m * 8;
+    if (c_smem > 40 * 1024) QOC_CUDA(h, cudaFuncSetAttribute(gs_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
+    gs_contract_kernel<<<dim3((unsigned)((size_t)p.batch * p.nt), p.nc), 256, c_smem, st>>>(g);
+    h->launches++;
+    if (p.store_costates) h->costates_valid = true;
+  }
+  QOC_CUDA(h, cudaGetLastError());
+  if (mode != 2) h->states_valid = true;
+  return QOC_OK;
+}
 
 static const double kB13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
                                 10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
@@ -590,6 +673,7 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
     QOC_CUDA(h, cudaMemcpyAsync(h->dflops, &f, 8, cudaMemcpyHostToDevice, st));
   }
   h->have_jac = want_jac;
+  if (h->gs2) return gpath_build_Q(h, st);
   return QOC_OK;
 }
 
@@ -705,6 +789,11 @@ static int run_sweeps(qoc_handle* h, bool want_grad, const double* d_lam_final, 
                       bool store_states, cudaStream_t st) {
   int rc;
   const bool builtin = h->prob.cost != QOC_COST_NONE;
+  if (h->gpath && h->gs2) {
+    if (d_lam_final) return gpath_sweep2(h, 2, false, true, d_lam_final, nullptr, d_J, d_dJdu, st);
+    if (want_grad) return gpath_sweep2(h, 0, false, true, nullptr, nullptr, d_J, d_dJdu, st);
+    return gpath_sweep2(h, builtin ? 0 : 1, true, false, nullptr, nullptr, d_J, d_dJdu, st);
+  }
   if (h->gpath) {
     if (d_lam_final) return gpath_sweep(h, 2, true, d_lam_final, nullptr, d_J, d_dJdu, st);
     return gpath_sweep(h, want_grad ? 0 : 1, want_grad, nullptr, nullptr, d_J, d_dJdu, st);
@@ -863,7 +952,8 @@ extern "C" int qoc_get_states(qoc_handle* h, double* x_out) {
   const qoc_problem& p = h->prob;
   QOC_CUDA(h, cudaSetDevice(p.device));
   if (!h->states_valid) {
-    int rc = h->gpath ? gpath_sweep(h, 1, false, nullptr, nullptr, nullptr, nullptr, h->stream)
+    int rc = (h->gpath && h->gs2) ? gpath_sweep2(h, 1, true, false, nullptr, nullptr, nullptr, nullptr, h->stream)
+             : h->gpath ? gpath_sweep(h, 1, false, nullptr, nullptr, nullptr, nullptr, h->stream)
                       : launch_k3(h, false, true, nullptr, h->stream);
     if (rc != QOC_OK) return rc;
   }

@@ -17,7 +17,12 @@ namespace qoc {
 
 struct GOp {
   const double* p;
-  long long stride;  // doubles between consecutive slices (0: same matrix for every slice)
+  long long stride;   // doubles between consecutive slices (0: same matrix for every slice)
+  int inner;          // 0: flat;  > 0: slice s sits at (s / inner) * stride2 + (s % inner) * stride
+  long long stride2;
+  __host__ __device__ __forceinline__ long long off(int s) const {
+    return inner > 0 ? (long long)(s / inner) * stride2 + (long long)(s % inner) * stride : (long long)s * stride;
+  }
 };
 
 struct GGemm {
@@ -26,6 +31,8 @@ struct GGemm {
   double alpha, beta[3], gamma;
   double* C;
   long long cstride;
+  int cinner;
+  long long cstride2;
 };
 
 typedef Cfg<4, 36, 8> GTile;  // 32 x 32 output tile, 32-wide k chunks, shared tiles with row stride 36
@@ -41,8 +48,8 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
   acc.zero();
   const int nkc = (d + 31) / 32;
   for (int p = 0; p < g.npairs; p++) {
-    const double* Ag = g.A[p].p + (long long)s * g.A[p].stride;
-    const double* Bg = g.B[p].p + (long long)s * g.B[p].stride;
+    const double* Ag = g.A[p].p + g.A[p].off(s);
+    const double* Bg = g.B[p].p + g.B[p].off(s);
     for (int kc = 0; kc < nkc; kc++) {
       __syncthreads();
 #pragma unroll
@@ -77,7 +84,8 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
   }
   acc.finish();
   const int row = tm * 32 + mi * 8 + (lane >> 2);
-  double* Cg = g.C + (long long)s * g.cstride;
+  double* Cg = g.C + (g.cinner > 0 ? (long long)(s / g.cinner) * g.cstride2 + (long long)(s % g.cinner) * g.cstride
+                                   : (long long)s * g.cstride);
 #pragma unroll
   for (int n = 0; n < 2; n++) {
     const int col = tn * 32 + (nj0 + n) * 8 + 2 * (lane & 3);
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
       double i0 = g.alpha * acc.im[n][0], i1 = g.alpha * acc.im[n][1];
       const size_t o = (size_t)row * S + col;
       for (int q = 0; q < g.nadd; q++) {
-        const double* Dg = g.D[q].p + (long long)s * g.D[q].stride;
+        const double* Dg = g.D[q].p + g.D[q].off(s);
         const double2 a = *reinterpret_cast<const double2*>(Dg + o), b = *reinterpret_cast<const double2*>(Dg + plane + o);
         r0 = fma(g.beta[q], a.x, r0); r1 = fma(g.beta[q], a.y, r1);
         i0 = fma(g.beta[q], b.x, i0); i1 = fma(g.beta[q], b.y, i1);
@@ -396,6 +404,283 @@ __global__ void __launch_bounds__(256) g_sweep_kernel(GSweep g) {
     if (g.store_costates && g.LAM) store(g.LAM + ((size_t)b * (nt + 1) + k) * 2 * dm, lam);
   }
   if (g.lam_start) store(g.lam_start + (size_t)b * 2 * dm, lam);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// General-path sweeps, second generation (no running penalty): the same two-level structure as K1/K2G/K3N.
+//   host: segment propagators Q_seg = U_{k1-1} ... U_{k0} by batched g_gemm launches (one level per slice of a segment)
+//   gs_scan_kernel      one CTA per pulse: boundary states / costates of every segment, terminal cost
+//   gs_seg_kernel       one CTA per segment: x_k (forward) and lambda_k (backward) of its slices, to HBM
+//   gs_contract_kernel  one CTA per (slice, control): Re tr(lambda' dU x) = <dU, lambda x'>_F, a streaming pass over dU
+// Mat-vec: DMMA.8x8x4 with the operand fragments read straight from HBM/L2 (each warp request covers whole 32-byte
+// sectors), the d x m state interleaved in shared memory as in qoc_sweep.cuh (two real DMMAs per complex k-step).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int GS_NW = 8;  // warps per CTA in the scan / segment kernels
+
+// y = op(U) x; U planar in global memory (row stride S), xs / ys interleaved [row][2 m] in shared memory with rows up to
+// rows_pad zeroed.  Warp w takes the 8-row output tiles w, w + GS_NW, ...
+template <bool ADJ, int NCT>
+__device__ __forceinline__ void gs_mv(const double* Ure, const double* Uim, int d, int S, int m, const double* xs, double* ys,
+                                      int warp, int lane) {
+  const int g = lane >> 2, q = lane & 3, W = 2 * m;
+  const int ntile = (d + 7) / 8, nks = (d + 3) / 4;
+  constexpr int KB = 8;   // k-steps per batch of loads in flight
+  for (int mi = warp; mi < ntile; mi += GS_NW) {
+    double p1[2][NCT][2], p2[2][NCT][2];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int ct = 0; ct < NCT; ct++) { p1[h][ct][0] = p1[h][ct][1] = 0.0; p2[h][ct][0] = p2[h][ct][1] = 0.0; }
+    const int orow = mi * 8 + g;                       // output row (non-adj) / operand column (adj) of this thread
+    const int oc = orow < d ? orow : d - 1;            // clamped: results of rows >= d are discarded
+    for (int k0 = 0; k0 < nks; k0 += KB) {
+      double ar[KB], ai[KB];
+#pragma unroll
+      for (int kk = 0; kk < KB; kk++) {
+        int kr = (k0 + kk) * 4 + q;                    // reduction index
+        kr = kr < d ? kr : d - 1;                      // clamped: multiplied by the zero rows of x
+        const size_t off = ADJ ? (size_t)kr * S + oc : (size_t)oc * S + kr;
+        const bool v = (k0 + kk) < nks;
+        ar[kk] = v ? __ldg(Ure + off) : 0.0;
+        ai[kk] = v ? __ldg(Uim + off) : 0.0;
+      }
+#pragma unroll
+      for (int kk = 0; kk < KB; kk++) {
+        const int ks = k0 + kk;
+        const int h = kk & 1;
+        const int kr = ks * 4 + q;
+#pragma unroll
+        for (int ct = 0; ct < NCT; ct++) {
+          const double bv = (ks < nks && kr < d && ct * 8 + g < W) ? xs[kr * W + ct * 8 + g] : 0.0;
+          dmma(p1[h][ct][0], p1[h][ct][1], ar[kk], bv);
+          dmma(p2[h][ct][0], p2[h][ct][1], ai[kk], bv);
+        }
+      }
+    }
+#pragma unroll
+    for (int ct = 0; ct < NCT; ct++) {
+      const int c = ct * 4 + q;
+      const double u = p1[0][ct][0] + p1[1][ct][0], v = p1[0][ct][1] + p1[1][ct][1];
+      const double e = p2[0][ct][0] + p2[1][ct][0], f = p2[0][ct][1] + p2[1][ct][1];
+      const double yr = ADJ ? u + f : u - f;
+      const double yi = ADJ ? v - e : v + e;
+      if (orow < d && c < m) *reinterpret_cast<double2*>(ys + orow * W + 2 * c) = make_double2(yr, yi);
+    }
+  }
+}
+template <bool ADJ>
+__device__ __forceinline__ void gs_mv_any(const double* U, int d, int S, int m, const double* xs, double* ys, int warp, int lane) {
+  const double* Uim = U + (size_t)d * S;
+  if (m <= 4) gs_mv<ADJ, 1>(U, Uim, d, S, m, xs, ys, warp, lane);
+  else gs_mv<ADJ, 2>(U, Uim, d, S, m, xs, ys, warp, lane);
+}
+
+// interleaved (shared) <-> c128 column-major (global)
+__device__ __forceinline__ void gs_to_global(double* g, const double* xs, int d, int m, int tid, int nth) {
+  for (int c = 0; c < m; c++)
+    for (int r = tid; r < d; r += nth)
+      reinterpret_cast<double2*>(g)[r + (size_t)d * c] = *reinterpret_cast<const double2*>(xs + r * 2 * m + 2 * c);
+}
+__device__ __forceinline__ void gs_from_global(double* xs, const double* g, int d, int m, int tid, int nth) {
+  for (int c = 0; c < m; c++)
+    for (int r = tid; r < d; r += nth)
+      *reinterpret_cast<double2*>(xs + r * 2 * m + 2 * c) = reinterpret_cast<const double2*>(g)[r + (size_t)d * c];
+}
+
+struct GS {
+  int d, S, m, nc, nt, cost, n;
+  int spp, L;          // segments per pulse, slices per segment (the last segment may be shorter)
+  int mode;            // 0: forward + cost + backward, 1: forward (+ cost unless skip_cost) only, 2: backward only
+  int skip_bwd;        // mode 0 without the backward part (propagate with a built-in cost)
+  long long slot;
+  const double* U;     // [b*nt + k]
+  const double* L_;    // [(b*nt + k)*nc + j]
+  const double* Q;     // [b*spp + s]
+  const double* x0;
+  const double* x_start_ext;
+  const double* T;
+  const double* lam_final;
+  double* xs_start;    // [b*spp + s] d x m c128
+  double* lam_end;
+  double* X;           // [b*(nt+1) + k]
+  double* LAM;
+  double* x_final;
+  double* lam_start;
+  double* J;
+  double* dJdu;
+};
+
+// one CTA per pulse: boundary walk over the segment propagators
+__global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int d = g.d, m = g.m, W = 2 * m, dm = d * m;
+  const int rows_pad = (d + 7) / 8 * 8;
+  double* b0 = reinterpret_cast<double*>(gsm);
+  double* b1 = b0 + rows_pad * W;
+  __shared__ double red[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nth = blockDim.x;
+  const int b = blockIdx.x;
+  for (int e = tid; e < 2 * rows_pad * W; e += nth) b0[e] = 0.0;
+  __syncthreads();
+  double* cur = b0; double* nxt = b1;
+  const bool do_fwd = g.mode != 2, do_bwd = g.mode == 2 || (g.mode == 0 && !g.skip_bwd);
+  if (do_fwd) {
+    gs_from_global(cur, g.x_start_ext ? g.x_start_ext + (size_t)b * 2 * dm : g.x0, d, m, tid, nth);
+    __syncthreads();
+    for (int s = 0; s < g.spp; s++) {
+      gs_to_global(g.xs_start + ((size_t)b * g.spp + s) * 2 * dm, cur, d, m, tid, nth);
+      gs_mv_any<false>(g.Q + ((size_t)b * g.spp + s) * g.slot, d, g.S, m, cur, nxt, warp, lane);
+      __syncthreads();
+      double* t = cur; cur = nxt; nxt = t;
+    }
+    if (g.x_final) gs_to_global(g.x_final + (size_t)b * 2 * dm, cur, d, m, tid, nth);
+    gs_to_global(g.X + ((size_t)b * (g.nt + 1) + g.nt) * 2 * dm, cur, d, m, tid, nth);
+  }
+  if (g.mode == 1) return;
+  const bool builtin = do_fwd && g.cost != 2;
+  if (tid < 4) red[tid] = 0.0;
+  __syncthreads();
+  double cr_ = 0.0, ci_ = 0.0;
+  if (builtin) {
+    double orr = 0.0, oii = 0.0;
+    for (int c = 0; c < m; c++)
+      for (int r = tid; r < d; r += nth) {
+        const double2 t = reinterpret_cast<const double2*>(g.T)[r + (size_t)d * c];
+        const double2 x = *reinterpret_cast<const double2*>(cur + r * W + 2 * c);
+        orr += t.x * x.x + t.y * x.y;
+        oii += t.x * x.y - t.y * x.x;
+      }
+    for (int off = 16; off > 0; off >>= 1) { orr += __shfl_xor_sync(0xffffffffu, orr, off); oii += __shfl_xor_sync(0xffffffffu, oii, off); }
+    if (lane == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
+    __syncthreads();
+    const double Or = red[0], Oi = red[1], nn = (double)g.n * (double)g.n;
+    double J;
+    if (g.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
+    else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
+    if (tid == 0 && g.J) g.J[b] = J;
+  }
+  if (!do_bwd) return;
+  for (int c = 0; c < m; c++)
+    for (int r = tid; r < d; r += nth) {
+      double2 l = make_double2(0.0, 0.0);
+      if (g.lam_final) l = reinterpret_cast<const double2*>(g.lam_final + (size_t)b * 2 * dm)[r + (size_t)d * c];
+      else if (builtin) {
+        const double2 t = reinterpret_cast<const double2*>(g.T)[r + (size_t)d * c];
+        l = make_double2(cr_ * t.x - ci_ * t.y, cr_ * t.y + ci_ * t.x);
+      }
+      *reinterpret_cast<double2*>(nxt + r * W + 2 * c) = l;
+    }
+  { double* t = cur; cur = nxt; nxt = t; }
+  __syncthreads();
+  for (int s = g.spp - 1; s >= 0; s--) {
+    gs_to_global(g.lam_end + ((size_t)b * g.spp + s) * 2 * dm, cur, d, m, tid, nth);
+    gs_mv_any<true>(g.Q + ((size_t)b * g.spp + s) * g.slot, d, g.S, m, cur, nxt, warp, lane);
+    __syncthreads();
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  if (g.lam_start) gs_to_global(g.lam_start + (size_t)b * 2 * dm, cur, d, m, tid, nth);
+}
+
+// one CTA per segment: states and costates of its slices
+__global__ void __launch_bounds__(GS_NW * 32) gs_seg_kernel(GS g, int nseg_total) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int d = g.d, m = g.m, W = 2 * m, dm = d * m;
+  const int rows_pad = (d + 7) / 8 * 8;
+  double* b0 = reinterpret_cast<double*>(gsm);
+  double* b1 = b0 + rows_pad * W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nth = blockDim.x;
+  for (int e = tid; e < 2 * rows_pad * W; e += nth) b0[e] = 0.0;
+  __syncthreads();
+  const bool do_fwd = g.mode != 2, do_bwd = g.mode == 2 || (g.mode == 0 && !g.skip_bwd);
+  for (int seg = blockIdx.x; seg < nseg_total; seg += gridDim.x) {
+    const int b = seg / g.spp, si = seg - b * g.spp;
+    const int k0 = si * g.L, k1 = (k0 + g.L < g.nt) ? k0 + g.L : g.nt;
+    double* cur = b0; double* nxt = b1;
+    if (do_fwd) {
+      gs_from_global(cur, g.xs_start + (size_t)seg * 2 * dm, d, m, tid, nth);
+      __syncthreads();
+      for (int k = k0; k < k1; k++) {
+        gs_to_global(g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, cur, d, m, tid, nth);
+        if (k + 1 < k1) {
+          gs_mv_any<false>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
+          __syncthreads();
+          double* t = cur; cur = nxt; nxt = t;
+        }
+      }
+      __syncthreads();
+    }
+    if (do_bwd) {
+      gs_from_global(cur, g.lam_end + (size_t)seg * 2 * dm, d, m, tid, nth);
+      __syncthreads();
+      for (int k = k1 - 1; k >= k0; k--) {
+        gs_to_global(g.LAM + ((size_t)b * (g.nt + 1) + k + 1) * 2 * dm, cur, d, m, tid, nth);
+        gs_mv_any<true>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
+        __syncthreads();
+        double* t = cur; cur = nxt; nxt = t;
+      }
+      if (k0 == 0) gs_to_global(g.LAM + ((size_t)b * (g.nt + 1)) * 2 * dm, cur, d, m, tid, nth);
+      __syncthreads();
+    }
+  }
+}
+
+// one CTA per (slice, control): dJdu[j,k] = sum_{r,c} Re( dU[r][c] * w[r][c] ), w[r][c] = sum_l x_k[c][l] conj(lambda_{k+1}[r][l])
+// (src/gradient_computations.jl:65-74, :217-223)
+__global__ void __launch_bounds__(256) gs_contract_kernel(GS g) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int d = g.d, S = g.S, m = g.m, W = 2 * m, dm = d * m;
+  double* xk = reinterpret_cast<double*>(gsm);   // S rows (zero padded)
+  double* lk = xk + (size_t)S * W;               // d rows
+  __shared__ double red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t sl = blockIdx.x;                  // flat slice index b*nt + k
+  const int j = blockIdx.y;
+  const int b = (int)(sl / g.nt), k = (int)(sl - (size_t)b * g.nt);
+  for (int e = tid; e < (S + d) * W; e += 256) xk[e] = 0.0;
+  __syncthreads();
+  gs_from_global(xk, g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, d, m, tid, 256);
+  gs_from_global(lk, g.LAM + ((size_t)b * (g.nt + 1) + k + 1) * 2 * dm, d, m, tid, 256);
+  __syncthreads();
+  const double* Lre = g.L_ + (sl * g.nc + j) * g.slot;
+  const double* Lim = Lre + (size_t)d * S;
+  const int units = d * S / 2, S2 = S / 2;
+  double s = 0.0;
+  for (int u0 = tid; u0 < units; u0 += 256 * 4) {
+    double2 fr[4], fi[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int u = u0 + i * 256;
+      if (u < units) { fr[i] = __ldg(reinterpret_cast<const double2*>(Lre) + u); fi[i] = __ldg(reinterpret_cast<const double2*>(Lim) + u); }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int u = u0 + i * 256;
+      if (u < units) {
+        const int r = u / S2, c0 = 2 * (u - r * S2);
+        const double* lrow = lk + r * W;
+        const double* x0p = xk + c0 * W;
+        double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
+        for (int l = 0; l < m; l++) {
+          const double2 lam = *reinterpret_cast<const double2*>(lrow + 2 * l);
+          const double2 xa = *reinterpret_cast<const double2*>(x0p + 2 * l);
+          const double2 xb = *reinterpret_cast<const double2*>(x0p + W + 2 * l);
+          w0r = fma(xa.x, lam.x, fma(xa.y, lam.y, w0r)); w0i = fma(xa.y, lam.x, fma(-xa.x, lam.y, w0i));
+          w1r = fma(xb.x, lam.x, fma(xb.y, lam.y, w1r)); w1i = fma(xb.y, lam.x, fma(-xb.x, lam.y, w1i));
+        }
+        s = fma(fr[i].x, w0r, fma(-fi[i].x, w0i, s));
+        s = fma(fr[i].y, w1r, fma(-fi[i].y, w1i, s));
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    g.dJdu[(sl * g.nc) + j] = t;
+  }
 }
 
 }  // namespace qoc
