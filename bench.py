@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- GRAPE fidelity+gradient throughput (slices*pulses/s) of the B200-native path, per BASELINE.json.
 
-A "step" is one full fidelity + gradient evaluation (qoc_eval: K1 expm + Jacobians + segment scan, K2 boundary scan +
-cost, K3 sweeps + gradient contraction) of the workload.  Workload at N = 1: BASELINE.json configs[1], the
+A "step" is one full fidelity + gradient evaluation (qoc_eval: K1 expm + Jacobians + segment scan, K2G two-level
+boundary scan + cost, K3N sweeps + gradient contraction) of the workload.  Workload at N = 1: BASELINE.json configs[1], the
 two_qubit_tunable_bus model (d = 27, m = 1, nc = 1) with 1e4 time slices, single pulse.  At N > 1 every rank
 evaluates its own pulse of that shape (multistart axis, no data-path collective) -> "scaling": "weak".
 
@@ -58,6 +58,21 @@ def fp64_peak_tflops():
     except Exception:
         pass
     return FP64_PEAK_FALLBACK_TFLOPS, "fallback constant (DMMA m8n8k4 measured on this pool in round 1)"
+
+
+def ncu_traffic_bytes(kernel_prefix, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed `ncu --set full`
+    capture (profiles/r01d_ncu_full_summary.json; captured on the bus workload only)."""
+    if workload != "bus":
+        return None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01d_ncu_full_summary.json")))
+        for k in prof["kernels"]:
+            if kernel_prefix in k["name"]:
+                return k["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def build_workload(name, rank, mode):
@@ -363,7 +378,8 @@ def main():
     k1_flops = alg_flops_total - sweep
     k1_tflops = k1_flops / (stage[0] * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "kernel": "k1_kernel (expm + Jacobians + segment scan)",
-                "achieved": k1_tflops, "peak": peak, "unit": "TFLOP/s", "frac": k1_tflops / peak, "traffic": None,
+                "achieved": k1_tflops, "peak": peak, "unit": "TFLOP/s", "frac": k1_tflops / peak,
+                "traffic": ncu_traffic_bytes("k1_kernel", args.workload),
                 "peak_source": peak_src, "k1_ms": float(stage[0]), "k2_ms": float(stage[1]), "k3_ms": float(stage[2]),
                 "alg_flops_per_step": alg_flops_total, "k1_share_of_step": float(stage[0] / stage.sum()),
                 "whole_step_tflops": alg_flops_total * args.steps / (ms * 1e-3) * 1e-12 / world * world}

@@ -738,7 +738,9 @@ static int launch_k2(qoc_handle* h, int phase, bool no_backward, const double* d
     P.sync_target = (unsigned)h->G * h->sync_epoch;
     with_cfg(h->cfg, [&](auto c) {
       typedef decltype(c) C;
-      k2g_kernel<C><<<h->prob.batch * h->G, C::NTHREADS + 32, h->k2g_smem, st>>>(P);
+      // cooperative launch: the CTAs of a pulse wait on one another (per-pulse barrier), so they must all be resident
+      void* args[] = {&P};
+      cudaLaunchCooperativeKernel((void*)k2g_kernel<C>, dim3(h->prob.batch * h->G), dim3(C::NTHREADS + 32), args, h->k2g_smem, st);
       return 0;
     });
   } else
