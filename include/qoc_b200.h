@@ -114,6 +114,15 @@ int qoc_eval(qoc_handle* h, const double* u, double* J_out, double* dJdu_out);
  * stream: a cudaStream_t cast to void* (NULL = default stream).  Skips the stale-u bookkeeping.              */
 int qoc_eval_device(qoc_handle* h, const double* d_u, double* d_J, double* d_dJdu, void* stream);
 
+/* ---- pulse parameterisation around the path -------------------------------------------------------------- */
+/* The immediate caller of the path maps spline coefficients to the pulse and the gradient back
+ * (examples/ipopt_callbacks_exp.jl:13-14 `u = transpose(B*c)` and :28 `dJdc = B'*transpose(dJdu)`).
+ * qoc_set_basis uploads B (Nt x ns, column-major: basis functions at the slice midpoints,
+ * examples/zz_coupling_ipopt_exp.jl:29-38); qoc_eval_coeffs evaluates J and dJ/dc for coefficients
+ * c (ns x nc x batch, column-major) with both skinny products on the device, so only ns*nc numbers cross the bus.  */
+int qoc_set_basis(qoc_handle* h, const double* B, int ns);
+int qoc_eval_coeffs(qoc_handle* h, const double* c, double* J_out, double* dJdc_out);
+
 /* ---- time-segment sharding of ONE long pulse across ranks (one process per GPU) --------------------------- */
 /* A handle created with nt = the LOCAL number of slices evaluates the slices [k_first, k_first+nt) of a longer
  * pulse.  Phase 1 computes the local U_k, dU_k/du_j and the rank propagator S_p = U_last ... U_first

@@ -34,6 +34,8 @@ SYMBOLS = {
     "qoc_gradient": (C.c_int, [_vp, _dp, _dp, _dp]),
     "qoc_eval": (C.c_int, [_vp, _dp, _dp, _dp]),
     "qoc_eval_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "qoc_set_basis": (C.c_int, [_vp, _dp, C.c_int]),
+    "qoc_eval_coeffs": (C.c_int, [_vp, _dp, _dp, _dp]),
     "qoc_shard_phase1_device": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qoc_shard_forward_device": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qoc_shard_backward_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

@@ -12,6 +12,7 @@
 #include "qoc_k23.cuh"
 #include "qoc_sweep.cuh"
 #include "qoc_gpath.cuh"
+#include "qoc_basis.cuh"
 
 using namespace qoc;
 
@@ -47,6 +48,8 @@ struct qoc_handle {
   int gchunk = 0, gnw = 0;
   double* gW = nullptr;       // workspace: gnw slots x gchunk slices
   double* dumax = nullptr;    // max_k |u_jk| per control
+  double *dB = nullptr, *dc = nullptr, *ddc = nullptr;   // spline basis, coefficients, dJ/dc (qoc_set_basis / qoc_eval_coeffs)
+  int ns = 0;
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
   bool gs2 = false;           // second-generation general-path sweeps (no running penalty)
@@ -189,7 +192,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
   cudaSetDevice(h->prob.device);
   double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
-                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg, h->dQ2};
+                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg, h->dQ2, h->dB, h->dc, h->ddc};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->dstatus) cudaFree(h->dstatus);
@@ -1107,4 +1110,46 @@ extern "C" int qoc_debug_k3_timeline(qoc_handle* h, long long* out, int nsteps) 
   cudaFree(h->dbg);
   h->dbg = nullptr; h->dbg_slices = 0;
   return rc;
+}
+
+// ---- pulse parameterisation around the path ------------------------------------------------------
+extern "C" int qoc_set_basis(qoc_handle* h, const double* B, int ns) {
+  if (!h || !B || ns <= 0) return QOC_ERR_INVALID;
+  const qoc_problem& p = h->prob;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  if (h->dB) { cudaFree(h->dB); cudaFree(h->dc); cudaFree(h->ddc); h->dB = h->dc = h->ddc = nullptr; }
+  QOC_CUDA(h, cudaMalloc(&h->dB, (size_t)p.nt * ns * 8));
+  QOC_CUDA(h, cudaMalloc(&h->dc, (size_t)ns * p.nc * p.batch * 8));
+  QOC_CUDA(h, cudaMalloc(&h->ddc, (size_t)ns * p.nc * p.batch * 8));
+  QOC_CUDA(h, cudaMemcpy(h->dB, B, (size_t)p.nt * ns * 8, cudaMemcpyHostToDevice));
+  h->ns = ns;
+  return QOC_OK;
+}
+
+extern "C" int qoc_eval_coeffs(qoc_handle* h, const double* c, double* J_out, double* dJdc_out) {
+  if (!h || !c) return QOC_ERR_INVALID;
+  if (!h->dB) { h->err = "qoc_eval_coeffs needs qoc_set_basis first"; return QOC_ERR_INVALID; }
+  const qoc_problem& p = h->prob;
+  const size_t ncoef = (size_t)h->ns * p.nc * p.batch;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  QOC_CUDA(h, cudaMemcpyAsync(h->dc, c, ncoef * 8, cudaMemcpyHostToDevice, h->stream));
+  const long long total = (long long)p.batch * p.nt * p.nc;
+  const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  basis_expand_kernel<<<grid, 256, 0, h->stream>>>(h->dB, h->dc, h->du, p.nt, h->ns, p.nc, p.batch);
+  int rc = qoc_eval_device(h, h->du, nullptr, nullptr, h->stream);
+  if (rc != QOC_OK) return rc;
+  basis_project_kernel<<<dim3(h->ns, p.nc, p.batch), 256, 0, h->stream>>>(h->dB, h->dg, h->ddc, p.nt, h->ns, p.nc);
+  h->launches += 2;
+  QOC_CUDA(h, cudaGetLastError());
+  if (J_out) QOC_CUDA(h, cudaMemcpyAsync(J_out, h->dJ, (size_t)p.batch * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (dJdc_out) QOC_CUDA(h, cudaMemcpyAsync(dJdc_out, h->ddc, ncoef * 8, cudaMemcpyDeviceToHost, h->stream));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->have_u = false;   // the host never saw this u: a later qoc_gradient(u) has nothing to compare against
+  h->states_valid = p.store_costates != 0;
+  if ((rc = check_status(h)) != QOC_OK) return rc;
+  if ((rc = fetch_flops(h, true)) != QOC_OK) return rc;
+  if (J_out)
+    for (int b = 0; b < p.batch; b++)
+      if (!std::isfinite(J_out[b])) { h->err = "J is not finite"; return QOC_ERR_NOT_FINITE; }
+  return QOC_OK;
 }
