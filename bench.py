@@ -242,6 +242,7 @@ def run_time_sharded(args, rank, world, local_rank, order):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * u[:, lo:hi].size),
                     "d2h_bytes_per_step": int(8 * u.size + 8),
                     "note": "the sharded evaluator is host-driven: u enters from host memory and J, dJdu return to it every step"},
+            # per rank and step: K1, K2G (rank propagator), boundary kernel, K2G (local scan), K3N
             "gpu_launches": int(5 * args.steps * world), "J": J}))
     dist.destroy_process_group()
     return 0

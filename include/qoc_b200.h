@@ -137,6 +137,12 @@ int qoc_shard_forward_device(qoc_handle* h, const double* d_x_start, double* d_x
 int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_end, double* d_dJdu, double* d_lambda_start,
                               void* stream);
 
+/* Phase 2 in one call for the built-in costs: d_S_all = the nranks all-gathered rank propagators (c128 d x d each,
+ * rank order); computes x_start / J / lambda_end on the device (redundantly on every rank, src/penalty_fcns.jl:15-24)
+ * and runs the local boundary scan and sweeps.  d_J: 1 double, d_dJdu: nc x nt_local doubles (device memory).        */
+int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int nranks, int rank, double* d_J, double* d_dJdu,
+                            void* stream);
+
 /* ---- cache getters (the reference returns x as its result, :31; parity tests read the rest) --------------- */
 int qoc_get_states(qoc_handle* h, double* x_out);        /* c128 d x m x (Nt+1) x batch  = cache.x              */
 int qoc_get_costates(qoc_handle* h, double* lam_out);    /* c128 d x m x (Nt+1) x batch  = cache.lambda          */

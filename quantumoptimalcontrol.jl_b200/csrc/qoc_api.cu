@@ -48,6 +48,7 @@ struct qoc_handle {
   int gchunk = 0, gnw = 0;
   double* gW = nullptr;       // workspace: gnw slots x gchunk slices
   double* dumax = nullptr;    // max_k |u_jk| per control
+  double* dbnd = nullptr;     // time sharding: x_start and lambda_end of the local segment (2 x d x m c128)
   double *dB = nullptr, *dc = nullptr, *ddc = nullptr;   // spline basis, coefficients, dJ/dc (qoc_set_basis / qoc_eval_coeffs)
   int ns = 0;
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
@@ -192,7 +193,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
   cudaSetDevice(h->prob.device);
   double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
-                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg, h->dQ2, h->dB, h->dc, h->ddc};
+                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg, h->dQ2, h->dB, h->dc, h->ddc, h->dbnd};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->dstatus) cudaFree(h->dstatus);
@@ -385,6 +386,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   CR(cudaMalloc(&h->dxf, (size_t)p.batch * dmB));
   CR(cudaMalloc(&h->dlam0, (size_t)p.batch * dmB));
   CR(cudaMalloc(&h->dlamf, (size_t)p.batch * dmB));
+  CR(cudaMalloc(&h->dbnd, 2 * dmB));
   CR(cudaMalloc(&h->dJ, (size_t)p.batch * 8));
   CR(cudaMalloc(&h->dg, nsl * p.nc * 8));
   CR(cudaMalloc(&h->dflops, 8));
@@ -726,7 +728,7 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
 
 // phase: 0 forward + cost + backward, 1 forward only, 2 backward only (needs lam_final)
 static int launch_k2(qoc_handle* h, int phase, bool no_backward, const double* d_lam_final, const double* d_x_start,
-                     double* d_J, cudaStream_t st) {
+                     double* d_J, cudaStream_t st, double* d_S_out = nullptr) {
   K23Params q = base_k23(h);
   q.k2_phase = phase;
   q.skip_cost = no_backward ? 1 : 0;
@@ -736,7 +738,7 @@ static int launch_k2(qoc_handle* h, int phase, bool no_backward, const double* d
   if (d_J) q.J = d_J;
   if (h->new_k2 && phase != 3) {
     K2GParams P;
-    P.q = q; P.G = h->G; P.Pg = h->dPg; P.sync = h->dsync;
+    P.q = q; P.G = h->G; P.Pg = h->dPg; P.sync = h->dsync; P.S_out = d_S_out;
     h->sync_epoch += 1;
     P.sync_target = (unsigned)h->G * h->sync_epoch;
     with_cfg(h->cfg, [&](auto c) {
@@ -1040,6 +1042,11 @@ extern "C" int qoc_shard_phase1_device(qoc_handle* h, const double* d_u, double*
   h->launches = 0;
   int rc = launch_k1(h, d_u, true, st);
   if (rc != QOC_OK) return rc;
+  if (h->new_k2) {   // two-level product: group products in parallel, then G - 1 products by one CTA
+    if ((rc = launch_k2(h, 5, true, nullptr, nullptr, nullptr, st, d_S_out)) != QOC_OK) return rc;
+    h->have_u = true;
+    return QOC_OK;
+  }
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
     const size_t smem = (size_t)(3 * h->slot_d + 8 * C::S) * 8;
@@ -1075,6 +1082,32 @@ extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_e
   if (d_lambda_start)
     QOC_CUDA(h, cudaMemcpyAsync(d_lambda_start, h->dlam0, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyDeviceToDevice, st));
   return QOC_OK;
+}
+
+// Phase 2 of the time-sharded evaluation in one call: boundary algebra over the all-gathered rank propagators (on the
+// device, redundantly on every rank), then the local boundary scan and sweeps.  Needs a built-in cost.
+extern "C" int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int nranks, int rank, double* d_J, double* d_dJdu,
+                                       void* stream) {
+  if (!h || !d_S_all || nranks <= 0 || rank < 0 || rank >= nranks) return QOC_ERR_INVALID;
+  if (h->gpath) { h->err = "time sharding is not available on the general (d > 28) path yet"; return QOC_ERR_UNSUPPORTED; }
+  if (h->prob.cost == QOC_COST_NONE) { h->err = "qoc_shard_phase2_device needs a built-in cost"; return QOC_ERR_INVALID; }
+  if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const qoc_problem& p = h->prob;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  ShardBoundary q;
+  q.d = p.d; q.m = p.m; q.nranks = nranks; q.rank = rank; q.cost = p.cost; q.n = p.n;
+  q.S_all = d_S_all; q.x0 = h->dx0; q.T = h->dT; q.x_start = h->dbnd; q.lam_end = h->dbnd + (size_t)2 * p.d * p.m; q.J = d_J ? d_J : h->dJ;
+  shard_boundary_kernel<<<1, 256, (size_t)2 * p.d * p.m * 16, st>>>(q);
+  h->launches += 1;
+  int rc;
+  if (h->new_k2) {
+    if ((rc = launch_k2(h, 4, false, q.lam_end, q.x_start, nullptr, st)) != QOC_OK) return rc;
+  } else {
+    if ((rc = launch_k2(h, 1, true, nullptr, q.x_start, nullptr, st)) != QOC_OK) return rc;
+    if ((rc = launch_k2(h, 2, false, q.lam_end, nullptr, nullptr, st)) != QOC_OK) return rc;
+  }
+  return launch_k3(h, true, true, d_dJdu, st);
 }
 
 // Developer aid (not part of include/qoc_b200.h): runs K1 once on the cached u with clock64() stamps recorded by CTA 0

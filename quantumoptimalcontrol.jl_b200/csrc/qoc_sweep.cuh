@@ -230,6 +230,7 @@ struct K2GParams {
   double* Pg;            // [batch * G] planar slots: group propagators
   unsigned* sync;        // [batch] arrival counters, never reset
   unsigned sync_target;  // G * (launch index): value the counter reaches when every CTA of the pulse has published
+  double* S_out;         // k2_phase 5: c128 column-major d x d product of ALL segment propagators of pulse 0 (time sharding)
 };
 
 // K2G: grid = batch * G CTAs (all co-resident: the host guarantees batch * G <= resident capacity);
@@ -309,9 +310,43 @@ __global__ void __launch_bounds__(C::NTHREADS + 64, 1) k2g_kernel(K2GParams P) {
     __syncthreads();
   }
 
+  const int mode = p.k2_phase;   // 0: forward + cost + backward, 1: forward only, 2: backward only (lam_final),
+                                 // 4: forward from x_start_ext and backward from lam_final, no cost (time sharding),
+                                 // 5: only the product of all segment propagators -> S_out (time sharding, phase 1)
+  if (mode == 5) {
+    // S = P_{G-1} ... P_0 by CTA 0 of the pulse: G - 1 sequential tile products over the freshly published group products
+    if (g != 0) return;
+    auto srcP = [&](int i) { return P.Pg + ((size_t)b * G + i) * slot_d; };
+    if (tid == 0) for (int i = 0; i < SW_NST - 1 && i < G; i++) ring.produce(gi + i, srcP(i));
+    int cur = 0;
+    const int mi = warp / (C::NT / C::BN), nj0 = (warp % (C::NT / C::BN)) * C::BN;
+    for (int i = 0; i < G; i++) {
+      ring.wait_full(gi + i);
+      if (tid == 0 && i + SW_NST - 1 < G) ring.produce(gi + i + SW_NST - 1, srcP(i + SW_NST - 1));
+      Mat Qm; Qm.re = ring.stage(gi + i); Qm.im = Qm.re + d * S;
+      Mat Pc; Pc.re = prod + (size_t)cur * slot_d; Pc.im = Pc.re + d * S;
+      Mat Pn; Pn.re = prod + (size_t)(cur ^ 1) * slot_d; Pn.im = Pn.re + d * S;
+      if (i == 0) {
+        slot_copy(Pn.re, Qm.re, n2, tid, NTH);
+      } else if (warp < C::NBLK) {
+        Acc<C::BN> acc; acc.zero();
+        mm_acc<C, false>(acc, Qm, Pc, mi, nj0, lane);
+        mm_store<C>(Pn, acc, d, mi, nj0, lane, NoEpi());
+      }
+      cur ^= 1;
+      __syncthreads();
+      if (warp < NT && lane == 0) ring.release(gi + i);
+    }
+    const double* Pre = prod + (size_t)cur * slot_d;
+    for (int e = tid; e < d * d; e += NTH) {
+      const int c = e / d, r = e - c * d;
+      reinterpret_cast<double2*>(P.S_out)[e] = make_double2(Pre[r * S + c], Pre[d * S + r * S + c]);
+    }
+    return;
+  }
+
   // ---------------- phases B (walk the groups) and C (walk this group's segments) ----------------
-  const int mode = p.k2_phase;              // 0: forward + cost + backward, 1: forward (+ cost) only, 2: backward only
-  const bool do_fwd = (mode != 2), do_bwd = (mode == 2) || (mode == 0 && !p.skip_cost);
+  const bool do_fwd = (mode != 2), do_bwd = (mode == 2) || (mode == 4) || (mode == 0 && !p.skip_cost);
   const int nB1 = do_fwd ? G : 0, nB2 = do_bwd ? (G - 1 - g) : 0, nC1 = do_fwd ? ngs : 0, nC2 = do_bwd ? ngs : 0;
   const int total = nB1 + nB2 + nC1 + nC2;
   const int gi0 = gi;
@@ -356,9 +391,9 @@ __global__ void __launch_bounds__(C::NTHREADS + 64, 1) k2g_kernel(K2GParams P) {
       if (p.X && p.store_states) ist_to_global(p.X + ((size_t)b * (p.nt + 1) + p.nt) * 2 * dm, cur, d, m, tid, RT);
     }
   }
-  if (mode == 0 || mode == 2) {
+  if (mode == 0 || mode == 2 || mode == 4) {
     // terminal cost and costate:  lambda_N = dJfinal_dx(x_N)     src/gradient_computations.jl:46, penalty_fcns.jl:15-24
-    const bool builtin = do_fwd && p.cost != 2;
+    const bool builtin = do_fwd && p.cost != 2 && mode != 4;
     if (tid < 4) red[tid] = 0.0;
     bar_rec(NT * 32);
     double cr_ = 0.0, ci_ = 0.0;
@@ -427,6 +462,80 @@ __global__ void __launch_bounds__(C::NTHREADS + 64, 1) k2g_kernel(K2GParams P) {
     }
     bar_rec(NT * 32);
     if (g == 0 && p.lam_start && rec) ist_to_global(p.lam_start + (size_t)b * 2 * dm, in, d, m, tid, RT);
+  }
+}
+
+// Boundary algebra of the time-sharded evaluation, redundantly on every rank, one CTA:
+//   x_start(rank) = S_{rank-1} ... S_0 x0,  x_N,  J,  lambda_N = dJfinal_dx(x_N),  lambda_end(rank) = S_{rank+1}' ... S_{P-1}' lambda_N
+// S_all: P consecutive c128 column-major d x d rank propagators (the all-gathered output of phase 1).
+struct ShardBoundary {
+  int d, m, nranks, rank, cost, n;
+  const double* S_all;
+  const double* x0;
+  const double* T;
+  double* x_start;   // c128 d x m
+  double* lam_end;   // c128 d x m
+  double* J;
+};
+
+__global__ void __launch_bounds__(256) shard_boundary_kernel(ShardBoundary q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int d = q.d, m = q.m, dm = d * m, tid = threadIdx.x;
+  double2* xa = reinterpret_cast<double2*>(smem_raw);   // column-major d x m, like the ABI
+  double2* xb = xa + dm;
+  __shared__ double red[2];
+  for (int e = tid; e < dm; e += 256) xa[e] = reinterpret_cast<const double2*>(q.x0)[e];
+  __syncthreads();
+  auto matvec = [&](const double* Sp, bool adj, const double2* in, double2* out) {
+    for (int e = tid; e < dm; e += 256) {
+      const int c = e / d, r = e - c * d;
+      double yr = 0.0, yi = 0.0;
+      for (int k = 0; k < d; k++) {
+        const double2 s = reinterpret_cast<const double2*>(Sp)[adj ? (k + (size_t)d * r) : (r + (size_t)d * k)];
+        const double sr = s.x, si = adj ? -s.y : s.y;
+        const double2 x = in[k + d * c];
+        yr = fma(sr, x.x, fma(-si, x.y, yr));
+        yi = fma(sr, x.y, fma(si, x.x, yi));
+      }
+      out[e] = make_double2(yr, yi);
+    }
+    __syncthreads();
+  };
+  double2* cur = xa; double2* nxt = xb;
+  for (int p = 0; p < q.nranks; p++) {
+    if (p == q.rank) for (int e = tid; e < dm; e += 256) reinterpret_cast<double2*>(q.x_start)[e] = cur[e];
+    matvec(q.S_all + (size_t)p * 2 * d * d, false, cur, nxt);
+    double2* t = cur; cur = nxt; nxt = t;
+  }
+  // cost and terminal costate (src/penalty_fcns.jl:15-24, test/test_gradient_computation.jl:24-25)
+  if (tid < 2) red[tid] = 0.0;
+  __syncthreads();
+  double orr = 0.0, oii = 0.0;
+  for (int e = tid; e < dm; e += 256) {
+    const double2 t = reinterpret_cast<const double2*>(q.T)[e];
+    const double2 x = cur[e];
+    orr += t.x * x.x + t.y * x.y;
+    oii += t.x * x.y - t.y * x.x;
+  }
+  for (int off = 16; off > 0; off >>= 1) { orr += __shfl_xor_sync(0xffffffffu, orr, off); oii += __shfl_xor_sync(0xffffffffu, oii, off); }
+  if ((tid & 31) == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
+  __syncthreads();
+  const double Or = red[0], Oi = red[1], nn = (double)q.n * (double)q.n;
+  double J, cr_, ci_;
+  if (q.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
+  else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
+  if (tid == 0 && q.J) *q.J = J;
+  for (int e = tid; e < dm; e += 256) {
+    const double2 t = reinterpret_cast<const double2*>(q.T)[e];
+    nxt[e] = make_double2(cr_ * t.x - ci_ * t.y, cr_ * t.y + ci_ * t.x);
+  }
+  __syncthreads();
+  { double2* t = cur; cur = nxt; nxt = t; }
+  for (int p = q.nranks - 1; p >= 0; p--) {
+    if (p == q.rank) for (int e = tid; e < dm; e += 256) reinterpret_cast<double2*>(q.lam_end)[e] = cur[e];
+    if (p == q.rank) break;
+    matvec(q.S_all + (size_t)p * 2 * d * d, true, cur, nxt);
+    double2* t = cur; cur = nxt; nxt = t;
   }
 }
 

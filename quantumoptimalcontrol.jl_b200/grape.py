@@ -186,6 +186,7 @@ class GrapeCache:
         if rc != _lib.OK:
             raise QOCError(rc, lib.qoc_last_error(None).decode())
         self._h, self._key, self._cost_key, self._penalty = h, key, None, penalty
+        self._ctor_args = (A0, list(A), x0, penalty)
         self.m = x0c.shape[1]
 
     def _set_cost(self, cost_obj):
@@ -198,6 +199,12 @@ class GrapeCache:
         elif self._cost_key is not None:
             self._check(lib.qoc_set_cost(self._h, COST_NONE, None, 0))
             self._cost_key = None
+
+    def _ensure_x0_cost(self, cost_obj, x0):
+        """Time sharding: (re)create the handle with the pulse's true x0 and install the built-in cost."""
+        A0c, Ac, _, pen = self._ctor_args
+        self._ensure(A0c, Ac, x0, pen)
+        self._set_cost(cost_obj)
 
     def _check(self, rc):
         if rc != _lib.OK:

@@ -76,6 +76,26 @@ class CudaSegmentEngine:
         self._u = u
         return S_cm.t()  # logical (row, col) view of the column-major buffer
 
+    def set_builtin_cost(self, cost, x0):
+        """Built-in cost + initial state for phase2 (the boundary algebra then runs on the device)."""
+        self.cache._ensure_x0_cost(cost, x0)
+
+    def phase2(self, S_all, nranks, rank):
+        """S_all: (nranks, d, d) complex128 tensor of column-major rank propagators, as all-gathered from phase1.
+        -> (J tensor (1,), local gradient (nt_local, nc) tensor), both on the GPU."""
+        J = torch.empty(1, dtype=torch.float64, device=self.device)
+        g = torch.empty((self.nt, self.nc), dtype=torch.float64, device=self.device)
+        self._check(self.lib.qoc_shard_phase2_device(self.cache.handle, self._ptr(S_all), nranks, rank, self._ptr(J), self._ptr(g),
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return J, g
+
+    def phase1_cm(self, u_dev):
+        """u_dev: (nt_local, nc) float64 tensor already on the GPU.  -> S_p as a column-major (d, d) buffer tensor."""
+        S_cm = torch.empty((self.d, self.d), dtype=torch.complex128, device=self.device)
+        self._check(self.lib.qoc_shard_phase1_device(self.cache.handle, self._ptr(u_dev), self._ptr(S_cm),
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return S_cm
+
     def forward(self, x_start):
         xs = x_start.t().contiguous()  # (m, d) row-major == d x m column-major
         xe = torch.empty_like(xs)
@@ -127,9 +147,43 @@ class TimeShardedEvaluator:
         dist.all_gather(out, t, group=self.group)
         return out
 
+    def _evaluate_device(self, u_full):
+        """Built-in cost + CUDA engine: phase 1, ONE all-gather of the rank propagators, phase 2 (boundary algebra, boundary
+        scan and sweeps on the device), ONE all-gather of the gradient segments, a single device -> host copy at the end."""
+        eng = self.engine
+        nc = u_full.shape[0]
+        if not getattr(self, "_dev_ready", False):
+            eng.set_builtin_cost(self.cost, self.x0.cpu().numpy())
+            self._nmax = max(time_partition(self.nt_total, self.world, r)[1] - time_partition(self.nt_total, self.world, r)[0]
+                             for r in range(self.world))
+            self._S_all = torch.empty((self.world, eng.d, eng.d), dtype=torch.complex128, device=self.device)
+            self._g_all = torch.zeros((self.world, self._nmax, nc), dtype=torch.float64, device=self.device)
+            self._g_pad = torch.zeros((self._nmax, nc), dtype=torch.float64, device=self.device)
+            self._dev_ready = True
+        u_dev = torch.from_numpy(np.ascontiguousarray(u_full[:, self.lo:self.hi].T)).to(self.device, non_blocking=True)
+        S = eng.phase1_cm(u_dev)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._S_all, S, group=self.group)
+        else:
+            self._S_all[0].copy_(S)
+        J, g_loc = eng.phase2(self._S_all, self.world, self.rank)
+        self._g_pad[: self.hi - self.lo].copy_(g_loc)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._g_all, self._g_pad, group=self.group)
+        else:
+            self._g_all[0].copy_(self._g_pad)
+        gh = self._g_all.cpu().numpy()
+        g = np.zeros((nc, self.nt_total))
+        for r in range(self.world):
+            lo, hi = time_partition(self.nt_total, self.world, r)
+            g[:, lo:hi] = gh[r, : hi - lo].T
+        return float(J.cpu()[0]), g
+
     def evaluate(self, u_full):
         """u_full: (nc, Nt) on every rank (only the local columns are used).  -> (J, dJdu (nc, Nt) numpy)."""
         u_full = np.asarray(u_full, dtype=np.float64)
+        if isinstance(self.cost, _BuiltinCost) and hasattr(self.engine, "phase2"):
+            return self._evaluate_device(u_full)
         u_loc = u_full[:, self.lo:self.hi]
         # phase 1 + exchange of the boundary propagators
         S = self._all_gather(self.engine.phase1(u_loc))

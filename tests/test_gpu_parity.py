@@ -411,3 +411,31 @@ def test_time_sharding_virtual_ranks_on_one_gpu():
                                        q.setup_infidelity(cfg["T"], cfg["n"])[1], 1003)
     J1, g1 = ev.evaluate(cfg["u"])
     assert_parity(J1, g1, Jo, go)
+
+
+def test_time_sharding_phase2_on_device_virtual_ranks():
+    """The one-call phase 2 (qoc_shard_phase2_device): boundary algebra over the all-gathered rank propagators on the device,
+    two-level local scan from (x_start, lambda_end), sweeps.  P virtual ranks on one GPU, uneven segments."""
+    import torch
+    from qoc_b200 import sharding
+    cfg = o.config_bus(Nt=1003, tgate=35.105)
+    P = 3
+    Jo, go, co = o.evaluate(cfg, order=0)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"])[1]
+    engines = []
+    dev = torch.device("cuda", 0)
+    S_all = torch.empty((P, 27, 27), dtype=torch.complex128, device=dev)
+    for r in range(P):
+        lo, hi = sharding.time_partition(1003, P, r)
+        e = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, cfg["x0"].shape[1], 0, order=0)
+        e.set_builtin_cost(cost, cfg["x0"])
+        u_dev = torch.from_numpy(np.ascontiguousarray(cfg["u"][:, lo:hi].T)).to(dev)
+        S_all[r].copy_(e.phase1_cm(u_dev))
+        engines.append(e)
+    g = np.zeros_like(go)
+    for r in range(P):
+        lo, hi = sharding.time_partition(1003, P, r)
+        J, gl = engines[r].phase2(S_all, P, r)
+        assert abs(float(J.cpu()[0]) - Jo) <= TOL_J
+        g[:, lo:hi] = gl.cpu().numpy().T
+    assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
