@@ -53,7 +53,8 @@ struct qoc_handle {
   int ns = 0;
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
-  bool gs2 = false;           // second-generation general-path sweeps (no running penalty)
+  bool gs2 = false;
+  bool k1_low = true;         // K1 instantiation with the low-degree Pade forms (false when ||A0||_1 alone is far above theta7)           // second-generation general-path sweeps (no running penalty)
   double normA0 = 0.0, normA[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long row_mask64 = 0ull;
   long long* dbg = nullptr;  // developer timeline buffer (qoc_debug_k1_timeline)
@@ -303,10 +304,11 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
       return QOC_ERR_UNSUPPORTED;
     }
     QOC_CUDA(h, cudaSetDevice(p.device));
-    QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
+    QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
+    QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
     QOC_CUDA(h, cudaFuncSetAttribute(k2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k2_smem));
     int occ = 1;
-    QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C>, C::NTHREADS + NSW * 32, h->k1_smem));
+    QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C, true>, C::NTHREADS + NSW * 32, h->k1_smem));
     if (occ < 1) occ = 1;
     const long long target = (long long)h->nsm * occ;
     long long spp = (target + p.batch - 1) / p.batch;
@@ -391,10 +393,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   CR(cudaMalloc(&h->dg, nsl * p.nc * 8));
   CR(cudaMalloc(&h->dflops, 8));
   CR(cudaMalloc(&h->dS, slotB));
-  if (h->gpath) {
-    CR(cudaSetDevice(p.device));
-    CR(cudaMalloc(&h->gW, (size_t)h->gnw * h->gchunk * slotB));
-    CR(cudaMalloc(&h->dumax, 8 * 8));
+  {
     auto norm1 = [&](const double* M) {
       double mx = 0;
       for (int c = 0; c < p.d; c++) { double sm_ = 0; for (int r = 0; r < p.d; r++) sm_ += hypot(M[2 * (r + (size_t)p.d * c)], M[2 * (r + (size_t)p.d * c) + 1]); if (sm_ > mx) mx = sm_; }
@@ -402,6 +401,13 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     };
     h->normA0 = norm1(A0);
     for (int j = 0; j < p.nc; j++) h->normA[j] = norm1(A + (size_t)j * 2 * p.d * p.d);
+    // a performance heuristic only: the [13/13]-only instantiation is always correct
+    h->k1_low = h->normA0 <= 2.0;
+  }
+  if (h->gpath) {
+    CR(cudaSetDevice(p.device));
+    CR(cudaMalloc(&h->gW, (size_t)h->gnw * h->gchunk * slotB));
+    CR(cudaMalloc(&h->dumax, 8 * 8));
   }
   if (h->new_k2) {
     CR(cudaMalloc(&h->dPg, (size_t)p.batch * h->G * slotB));
@@ -713,11 +719,18 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   k.A0p = h->dA0p; k.Ap = h->dAp; k.u = d_u; k.U = h->dU; k.L = h->dL; k.Q = h->dQ;
   k.flops = h->dflops; k.status = h->dstatus;
   k.theta13 = (p.order == QOC_ORDER_FRECHET) ? 4.74 : 5.4;
+  // degree switch points: Higham-2005 table as rounded by the reference's dependency (Taylor mode: only expm is
+  // approximated), Al-Mohy-Higham l_m for the Frechet pair.  QOC_PADE13=1 forces the [13/13] form (A/B measurements).
+  k.theta5 = (p.order == QOC_ORDER_FRECHET) ? 0.2 : 0.25;
+  k.theta7 = (p.order == QOC_ORDER_FRECHET) ? 0.783 : 0.95;
+  { const char* f13 = getenv("QOC_PADE13"); if (f13 && f13[0] == '1') { k.theta5 = -1.0; k.theta7 = -1.0; } }
   k.dbg = h->dbg; k.dbg_slices = h->dbg_slices; k.dbg_flags = h->dbg_flags;
   QOC_CUDA(h, cudaMemsetAsync(h->dflops, 0, 8, st));
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
-    k1_kernel<C><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);  // NW compute warps + 4 service warps
+    // NW compute warps + 4 service warps
+    if (h->k1_low) k1_kernel<C, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
+    else k1_kernel<C, false><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
     return 0;
   });
   h->launches += 1;  // kernels only (the flop-counter memset is not counted)

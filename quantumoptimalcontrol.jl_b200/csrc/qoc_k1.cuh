@@ -37,6 +37,8 @@ struct K1Params {
   double* flops;           // accumulated algorithmic flops (F_alg) over slices
   int* status;             // set to QOC_ERR_SINGULAR (8) on a zero pivot
   double theta13;          // scaling threshold: 5.4 (Higham-2005 / reference) or 4.74 (Frechet, Al-Mohy-Higham)
+  double theta5, theta7;   // ||X||_1 <= theta5: [5/5] Pade, <= theta7: [7/7], else [13/13] with scaling
+                           // (0.25 / 0.95 in Taylor mode = the reference's expm table, 0.2 / 0.783 in Frechet mode)
   long long* dbg;          // optional timeline of CTA 0: [slice][16] clock64 stamps (NULL in production)
   int dbg_slices;
   int dbg_flags;           // bit 0: skip the service inverse (timing experiment, results invalid)
@@ -48,6 +50,9 @@ struct K1Params {
   } while (0)
 
 // Pade-13 coefficients b0..b13
+// Pade-5 and Pade-7 coefficients
+__constant__ double c_b5[6] = {30240., 15120., 3360., 420., 30., 1.};
+__constant__ double c_b7[8] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
 __constant__ double c_b13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
                                  129060195264000.,   10559470521600.,    670442572800.,    33522128640.,
                                  1323241920.,        40840800.,          960960.,          16380.,
@@ -207,8 +212,8 @@ struct K1Ctx {
 template <int S>
 struct DualEpi {
   LinEpi<S> base;
-  Mat dst2, n1, n2;
-  double k0, k1, k2;
+  Mat dst2, n1, n2, n3;
+  double k0, k1, k2, k3, kI;   // dst2 = k0 * dst + k1 * n1 + k2 * n2 + k3 * n3 + kI * I
   int d;
   __device__ __forceinline__ void operator()(int row, int col, double& r0, double& i0, double& r1, double& i1) const {
     base(row, col, r0, i0, r1, i1);
@@ -218,9 +223,40 @@ struct DualEpi {
     double2 wr, wi;
     wr.x = k0 * r0 + k1 * a.x + k2 * c.x; wi.x = k0 * i0 + k1 * b.x + k2 * e.x;
     wr.y = k0 * r1 + k1 * a.y + k2 * c.y; wi.y = k0 * i1 + k1 * b.y + k2 * e.y;
+    if (k3 != 0.0) {
+      double2 f = *reinterpret_cast<const double2*>(n3.re + o), g = *reinterpret_cast<const double2*>(n3.im + o);
+      wr.x = fma(k3, f.x, wr.x); wr.y = fma(k3, f.y, wr.y); wi.x = fma(k3, g.x, wi.x); wi.y = fma(k3, g.y, wi.y);
+    }
+    if (row == col) wr.x += kI;
+    if (row == col + 1) wr.y += kI;
     if (col + 1 >= d) { wr.y = 0.0; wi.y = 0.0; }
     *reinterpret_cast<double2*>(dst2.re + o) = wr;
     *reinterpret_cast<double2*>(dst2.im + o) = wi;
+  }
+};
+
+// epilogue for Lu of the low-degree Frechet forms: acc = Lu, Lv = c1 m1 + c2 m2 + c3 m3 is a pure linear combination
+// evaluated at the output position;  writes S = Lu + Lv into `sdst` and returns D = Lu - Lv
+template <int S>
+struct DiffSumLinEpi {
+  Mat sdst, m1, m2, m3;
+  double c1, c2, c3;
+  int d;
+  __device__ __forceinline__ void operator()(int row, int col, double& r0, double& i0, double& r1, double& i1) const {
+    const int o = row * S + col;
+    double2 a = *reinterpret_cast<const double2*>(m1.re + o), b = *reinterpret_cast<const double2*>(m1.im + o);
+    double2 lr = make_double2(c1 * a.x, c1 * a.y), li = make_double2(c1 * b.x, c1 * b.y);
+    a = *reinterpret_cast<const double2*>(m2.re + o); b = *reinterpret_cast<const double2*>(m2.im + o);
+    lr.x = fma(c2, a.x, lr.x); lr.y = fma(c2, a.y, lr.y); li.x = fma(c2, b.x, li.x); li.y = fma(c2, b.y, li.y);
+    if (c3 != 0.0) {
+      a = *reinterpret_cast<const double2*>(m3.re + o); b = *reinterpret_cast<const double2*>(m3.im + o);
+      lr.x = fma(c3, a.x, lr.x); lr.y = fma(c3, a.y, lr.y); li.x = fma(c3, b.x, li.x); li.y = fma(c3, b.y, li.y);
+    }
+    double2 sr = make_double2(r0 + lr.x, r1 + lr.y), si = make_double2(i0 + li.x, i1 + li.y);
+    if (col + 1 >= d) { sr.y = 0.0; si.y = 0.0; }
+    *reinterpret_cast<double2*>(sdst.re + o) = sr;
+    *reinterpret_cast<double2*>(sdst.im + o) = si;
+    r0 -= lr.x; r1 -= lr.y; i0 -= li.x; i1 -= li.y;
   }
 };
 
@@ -376,7 +412,7 @@ struct GenMap {
   static constexpr int RPT = (C::DMAX + G - 1) / G;  // rows per thread (1 or 2)
 };
 
-template <class C>
+template <class C, bool LOW>
 __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, const double2 (&a0r)[2], const double2 (&a0i)[2],
                                                const double (&uj)[8], bool need_x, SvcScratch* sc) {
   typedef GenMap<C> GM;
@@ -410,7 +446,7 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
   }
   if (act) *reinterpret_cast<float2*>(&sc->colsum[r0][2 * cp]) = make_float2(cs0, cs1);
   c.cbar();
-  int sq = 0;
+  int sq = 0, qdeg = 13;
   {
     float ps = 0.f;
     if (c.lane < d) {
@@ -420,7 +456,9 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ps = fmaxf(ps, __shfl_xor_sync(0xffffffffu, ps, off));
     float t = (float)p.theta13;
-    while (ps > t && sq < 60) { t *= 2.f; sq++; }
+    if (LOW && ps <= (float)p.theta5) qdeg = 5;
+    else if (LOW && ps <= (float)p.theta7) qdeg = 7;
+    else { while (ps > t && sq < 60) { t *= 2.f; sq++; } }
   }
   const double scl = __hiloint2double((1023 - sq) << 20, 0);  // 2^-sq exactly
   const Mat mX = c.S(sX), mA = c.S(sA);
@@ -438,7 +476,7 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
     }
   }
   c.cbar();
-  return sq;
+  return LOW ? (sq | (qdeg << 8)) : sq;
 }
 
 // [13/13] Pade: powers, W, U = A W, and N = V - U.  Leaves A2, A4, A6, W for the Frechet part.
@@ -451,7 +489,7 @@ __device__ __forceinline__ void pade13_build_N(K1Ctx<C>& c, Mat U, Mat N) {
   {  // A6 = A2 A4, and W1 = b13 A6 + b11 A4 + b9 A2 written by the same epilogue
     DualEpi<C::S> e;
     e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
-    e.dst2 = WZ; e.n1 = A4; e.n2 = A2; e.k0 = b[13]; e.k1 = b[11]; e.k2 = b[9]; e.d = c.d;
+    e.dst2 = WZ; e.n1 = A4; e.n2 = A2; e.n3 = A2; e.k0 = b[13]; e.k1 = b[11]; e.k2 = b[9]; e.k3 = 0.0; e.kI = 0.0; e.d = c.d;
     c.mm1(A6, A2, A4, e);
   }
   c.mm1(W, A6, WZ, c.epi(1.0, b[7], A6, b[5], A4, b[3], A2, b[1]));
@@ -477,6 +515,64 @@ __device__ __forceinline__ void pade13_build_N(K1Ctx<C>& c, Mat U, Mat N) {
   c.mm1(N, A6, WZ, ne);
 }
 
+// [5/5] and [7/7] Pade for small ||X||_1 (no scaling): U = A (b_q A^{q-1} + ... + b_3 A^2 + b_1 I), V = even part.
+// Leaves A2, A4 (, A6) and W (the bracket of U) for the Frechet part; N = V - U comes out of the U product's epilogue.
+template <class C>
+__device__ __forceinline__ void pade_low_build_N(K1Ctx<C>& c, Mat U, Mat N, int q) {
+  Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), A6 = c.S(sA6), W = c.S(sW);
+  c.mm1(A2, A, A, NoEpi());
+  if (q == 5) {
+    const double* b = c_b5;
+    DualEpi<C::S> e;   // A4 = A2 A2 ; W = b5 A4 + b3 A2 + b1 I
+    e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
+    e.dst2 = W; e.n1 = A2; e.n2 = A2; e.n3 = A2; e.k0 = b[5]; e.k1 = b[3]; e.k2 = 0.0; e.k3 = 0.0; e.kI = b[1]; e.d = c.d;
+    c.mm1(A4, A2, A2, e);
+    DualEpi<C::S> u;   // U = A W ; N = -U + b4 A4 + b2 A2 + b0 I
+    u.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
+    u.dst2 = N; u.n1 = A4; u.n2 = A2; u.n3 = A2; u.k0 = -1.0; u.k1 = b[4]; u.k2 = b[2]; u.k3 = 0.0; u.kI = b[0]; u.d = c.d;
+    c.mm1(U, A, W, u);
+  } else {
+    const double* b = c_b7;
+    c.mm1(A4, A2, A2, NoEpi());
+    DualEpi<C::S> e;   // A6 = A2 A4 ; W = b7 A6 + b5 A4 + b3 A2 + b1 I
+    e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
+    e.dst2 = W; e.n1 = A4; e.n2 = A2; e.n3 = A2; e.k0 = b[7]; e.k1 = b[5]; e.k2 = b[3]; e.k3 = 0.0; e.kI = b[1]; e.d = c.d;
+    c.mm1(A6, A2, A4, e);
+    DualEpi<C::S> u;   // U = A W ; N = -U + b6 A6 + b4 A4 + b2 A2 + b0 I
+    u.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
+    u.dst2 = N; u.n1 = A6; u.n2 = A4; u.n3 = A2; u.k0 = -1.0; u.k1 = b[6]; u.k2 = b[4]; u.k3 = b[2]; u.kI = b[0]; u.d = c.d;
+    c.mm1(U, A, W, u);
+  }
+}
+
+// Frechet derivative of the [5/5] / [7/7] Pade approximant (Al-Mohy & Higham 2009, eq. (6.3) ff.): Lw and Lv are pure
+// linear combinations of M2, M4 (, M6), so the whole part 1 is 3 (4) two-product phases.
+template <class C>
+__device__ __forceinline__ void frechet_low_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat Sst, int q) {
+  Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), W = c.S(sW), M2 = c.S(sM2), M4 = c.S(sM4), M6 = c.S(sM6), Lw = c.S(sLw);
+  c.mm2(M2, A, E, E, A, NoEpi());
+  DiffSumLinEpi<C::S> ds;
+  ds.sdst = Sst; ds.d = c.d;
+  if (q == 5) {
+    const double* b = c_b5;
+    DualEpi<C::S> e;   // M4 = A2 M2 + M2 A2 ; Lw = b5 M4 + b3 M2
+    e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
+    e.dst2 = Lw; e.n1 = M2; e.n2 = M2; e.n3 = M2; e.k0 = b[5]; e.k1 = b[3]; e.k2 = 0.0; e.k3 = 0.0; e.kI = 0.0; e.d = c.d;
+    c.mm2(M4, A2, M2, M2, A2, e);
+    ds.m1 = M4; ds.m2 = M2; ds.m3 = M2; ds.c1 = b[4]; ds.c2 = b[2]; ds.c3 = 0.0;
+  } else {
+    const double* b = c_b7;
+    c.mm2(M4, A2, M2, M2, A2, NoEpi());
+    DualEpi<C::S> e;   // M6 = A4 M2 + M4 A2 ; Lw = b7 M6 + b5 M4 + b3 M2
+    e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
+    e.dst2 = Lw; e.n1 = M4; e.n2 = M2; e.n3 = M2; e.k0 = b[7]; e.k1 = b[5]; e.k2 = b[3]; e.k3 = 0.0; e.kI = 0.0; e.d = c.d;
+    c.mm2(M6, A4, M2, M4, A2, e);
+    ds.m1 = M6; ds.m2 = M4; ds.m3 = M2; ds.c1 = b[6]; ds.c2 = b[4]; ds.c3 = b[2];
+  }
+  // Lu = A Lw + E W ; D = Lu - Lv -> Dst, S = Lu + Lv -> Sst
+  c.mm2(Dst, A, Lw, E, W, ds);
+}
+
 // Exact Frechet derivative L(A, E) of the Pade approximant (Al-Mohy & Higham 2009, Alg. 6.4), i.e. the (1,2) block of
 // r13([[A,E],[0,A]]) with the block-triangular structure made explicit.  E is the UNSCALED control operator
 // (L is linear in E; the factor 2^-s is applied to the result).  part 1: everything that does not need N^-1.
@@ -491,7 +587,7 @@ __device__ __forceinline__ void frechet13_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat
   {  // M6 = A4 M2 + M4 A2 ; T = Lw1 = b13 M6 + b11 M4 + b9 M2 from the same epilogue
     DualEpi<C::S> e;
     e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
-    e.dst2 = T; e.n1 = M4; e.n2 = M2; e.k0 = b[13]; e.k1 = b[11]; e.k2 = b[9]; e.d = c.d;
+    e.dst2 = T; e.n1 = M4; e.n2 = M2; e.n3 = M2; e.k0 = b[13]; e.k1 = b[11]; e.k2 = b[9]; e.k3 = 0.0; e.kI = 0.0; e.d = c.d;
     c.mm2(M6, A4, M2, M4, A2, e);
   }
   c.lc(WZ, b[13], A6, b[11], A4, b[9], A2, 0.0);  // W1 again (WZ held Z1)
@@ -543,7 +639,9 @@ __device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, Mat Aj, Mat out, in
   c.mm4(out, AjX, X2, XAj, X2, X2, AjX, X2, XAj, c.epi(1.0 / 24.0, 1.0, c.S(sLw), 0.0, Aj, 0.0, Aj, 0.0));
 }
 
-template <class C>
+// LOW: the [5/5] / [7/7] forms are compiled in.  The host instantiates LOW = false when the drift alone puts every slice far
+// above theta7 (the bus config): the extra code paths cost the [13/13]-only path 3 % (measured) even when never taken.
+template <class C, bool LOW>
 __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int S = C::S;
@@ -634,12 +732,14 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
   };
   // (D, S) = (Lu - Lv, Lu + Lv) homes per control: roles k1_role_D(j), k1_role_S(j)
   int par = 0;
-  int sq = 0;
+  int sq = 0, qd = 13;   // squarings and Pade degree of the slice whose N is being inverted / whose tail comes next
   const unsigned slot_bytes = (unsigned)slot_d * 8u;
   if (it.valid()) {
     load_u(it);
-    sq = build_generator<C>(p, c, a0r, a0i, uj, need_x, sc);
-    pade13_build_N<C>(c, c.fixed(sU0), c.fixed(sN0));
+    sq = build_generator<C, LOW>(p, c, a0r, a0i, uj, need_x, sc);
+    if (LOW) { qd = sq >> 8; sq &= 255; }
+    if (!LOW || qd == 13) pade13_build_N<C>(c, c.fixed(sU0), c.fixed(sN0));
+    else pade_low_build_N<C>(c, c.fixed(sU0), c.fixed(sN0), qd);
     bar_arrive_i<BAR_NREADY>(NALL);
   }
 
@@ -649,7 +749,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
     const int seg = it.seg;
     const size_t slice = (size_t)it.b * p.nt + it.k;
     const double scl = __hiloint2double((1023 - sq) << 20, 0);  // 2^-sq
-    const int sq_cur = sq;
+    const int sq_cur = sq, q_cur = LOW ? qd : 13;
     QOC_STAMP(0);
     WorkIter nx = it;
     nx.next();
@@ -674,15 +774,18 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
       } else {
         // control 0 last: its (D, S) stay in (sM2, sLv), which the other controls' part1 uses as workspace (sM2)
         for (int j = nc - 1; j >= 0; j--)
-          frechet13_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)));
+          if (!LOW || q_cur == 13) frechet13_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)));
+          else frechet_low_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)), q_cur);
       }
     }
     QOC_STAMP(1);
 
     // ---- software pipeline: generator and Pade denominator of the NEXT slice while N^-1(k) is being formed ----
     if (nx.valid()) {
-      sq = build_generator<C>(p, c, a0r, a0i, uj, need_x, sc);
-      pade13_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
+      sq = build_generator<C, LOW>(p, c, a0r, a0i, uj, need_x, sc);
+      if (LOW) { qd = sq >> 8; sq &= 255; }
+      if (!LOW || qd == 13) pade13_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
+      else pade_low_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)), qd);
       bar_arrive_p<BAR_NREADY>(par ^ 1, NALL);
     }
     QOC_STAMP(2);
@@ -752,9 +855,10 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
     }
     if (c.tid == 0) {
       double G = 0.0;
+      const double pi_q = q_cur == 13 ? 6.0 : q_cur == 7 ? 4.0 : 3.0;   // products of the Pade approximant as executed
       if (p.want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0)
-                                 : (2.0 * 6 + 2.0 * sq_cur + 2.0);
-      my_flops += M * ((6.0 + sq_cur + 4.0 / 3.0) + nc * G);
+                                 : (2.0 * pi_q + 2.0 * sq_cur + 2.0);
+      my_flops += M * ((pi_q + sq_cur + 4.0 / 3.0) + nc * G);
     }
     QOC_STAMP(5);
     dbg_i++;
