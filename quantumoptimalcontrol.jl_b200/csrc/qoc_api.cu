@@ -590,7 +590,19 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
   if (bound > theta) sq = (int)ceil(log2(bound / theta));
   if (sq < 0) sq = 0;
   const double sc = ldexp(1.0, -sq);
-  const double* b = kB13;
+  // Pade degree from the same bound (uniform over the launch): [5/5] / [7/7] without scaling for small norms
+  static const double kB5[6] = {30240., 15120., 3360., 420., 30., 1.};
+  static const double kB7[8] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
+  int q = 13;
+  {
+    const char* f13 = getenv("QOC_PADE13");
+    if (!(f13 && f13[0] == '1')) {
+      if (bound <= (taylor ? 0.25 : 0.2)) q = 5;
+      else if (bound <= (taylor ? 0.95 : 0.783)) q = 7;
+    }
+  }
+  const double pi_q = q == 13 ? 6.0 : q == 7 ? 4.0 : 3.0;
+  const double* b = q == 13 ? kB13 : q == 7 ? kB7 : kB5;
   enum { A = 0, X, A2, A4, A6, W1, Z1, Wm, V, U, R, M2, M4, M6, T1, T2, Lw, Lv, Dd, Ss, RH, TMP, TMPR, L0 };
   GRun g{h, st, 0, (d + 31) / 32};
   const GOp A0op{h->dA0p, 0};
@@ -602,11 +614,20 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
     h->launches++;
     g.mm1(A2, g.W(A), g.W(A));
     g.mm1(A4, g.W(A2), g.W(A2));
-    g.mm1(A6, g.W(A2), g.W(A4));
-    { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[13], b[11], b[9]}; g.lin(W1, 3, D, be); }
-    { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[12], b[10], b[8]}; g.lin(Z1, 3, D, be); }
-    { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[7], b[5], b[3]}; g.mm1(Wm, g.W(A6), g.W(W1), 1.0, 3, D, be, b[1]); }
-    { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[6], b[4], b[2]}; g.mm1(V, g.W(A6), g.W(Z1), 1.0, 3, D, be, b[0]); }
+    if (q == 13) {
+      g.mm1(A6, g.W(A2), g.W(A4));
+      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[13], b[11], b[9]}; g.lin(W1, 3, D, be); }
+      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[12], b[10], b[8]}; g.lin(Z1, 3, D, be); }
+      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[7], b[5], b[3]}; g.mm1(Wm, g.W(A6), g.W(W1), 1.0, 3, D, be, b[1]); }
+      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[6], b[4], b[2]}; g.mm1(V, g.W(A6), g.W(Z1), 1.0, 3, D, be, b[0]); }
+    } else if (q == 7) {   // U = A (b7 A6 + b5 A4 + b3 A2 + b1 I), V = b6 A6 + b4 A4 + b2 A2 + b0 I
+      g.mm1(A6, g.W(A2), g.W(A4));
+      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[7], b[5], b[3]}; g.lin(Wm, 3, D, be, b[1]); }
+      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[6], b[4], b[2]}; g.lin(V, 3, D, be, b[0]); }
+    } else {               // U = A (b5 A4 + b3 A2 + b1 I), V = b4 A4 + b2 A2 + b0 I
+      { GOp D[2] = {g.W(A4), g.W(A2)}; double be[2] = {b[5], b[3]}; g.lin(Wm, 2, D, be, b[1]); }
+      { GOp D[2] = {g.W(A4), g.W(A2)}; double be[2] = {b[4], b[2]}; g.lin(V, 2, D, be, b[0]); }
+    }
     g.mm1(U, g.W(A), g.W(Wm));
     { GOp D[2] = {g.W(V), g.W(U)}; double be[2] = {1.0, -1.0}; g.lin(V, 2, D, be); }   // N = V - U (in place: elementwise)
     g_inverse_kernel<<<nb, 256, (size_t)d * 36, st>>>(d, h->S, g.Wp(V), h->slot_d, h->dstatus);
@@ -643,11 +664,20 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
         // exact Frechet derivative, structured block-triangular evaluation (Al-Mohy & Higham 2009, Alg. 6.4)
         g.mm2(M2, g.W(A), E, E, g.W(A));
         g.mm2(M4, g.W(A2), g.W(M2), g.W(M2), g.W(A2));
-        g.mm2(M6, g.W(A4), g.W(M2), g.W(M4), g.W(A2));
-        { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[13], b[11], b[9]}; g.lin(T1, 3, D, be); }
-        { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[12], b[10], b[8]}; g.lin(T2, 3, D, be); }
-        { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[7], b[5], b[3]}; g.mm2(Lw, g.W(A6), g.W(T1), g.W(M6), g.W(W1), 1.0, 3, D, be); }
-        { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[6], b[4], b[2]}; g.mm2(Lv, g.W(A6), g.W(T2), g.W(M6), g.W(Z1), 1.0, 3, D, be); }
+        if (q == 13) {
+          g.mm2(M6, g.W(A4), g.W(M2), g.W(M4), g.W(A2));
+          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[13], b[11], b[9]}; g.lin(T1, 3, D, be); }
+          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[12], b[10], b[8]}; g.lin(T2, 3, D, be); }
+          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[7], b[5], b[3]}; g.mm2(Lw, g.W(A6), g.W(T1), g.W(M6), g.W(W1), 1.0, 3, D, be); }
+          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[6], b[4], b[2]}; g.mm2(Lv, g.W(A6), g.W(T2), g.W(M6), g.W(Z1), 1.0, 3, D, be); }
+        } else if (q == 7) {   // Lw, Lv are linear combinations of M6, M4, M2
+          g.mm2(M6, g.W(A4), g.W(M2), g.W(M4), g.W(A2));
+          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[7], b[5], b[3]}; g.lin(Lw, 3, D, be); }
+          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[6], b[4], b[2]}; g.lin(Lv, 3, D, be); }
+        } else {
+          { GOp D[2] = {g.W(M4), g.W(M2)}; double be[2] = {b[5], b[3]}; g.lin(Lw, 2, D, be); }
+          { GOp D[2] = {g.W(M4), g.W(M2)}; double be[2] = {b[4], b[2]}; g.lin(Lv, 2, D, be); }
+        }
         { GOp D[1] = {g.W(Lv)}; double be[1] = {-1.0}; g.mm2(Dd, g.W(A), g.W(Lw), E, g.W(Wm), 1.0, 1, D, be); }        // D = Lu - Lv
         { GOp D[2] = {g.W(Dd), g.W(Lv)}; double be[2] = {1.0, 2.0}; g.lin(Ss, 2, D, be); }                          // S = Lu + Lv
         { GOp D[1] = {g.W(Ss)}; double be[1] = {1.0}; g.mm1(RH, g.W(Dd), Rop, 1.0, 1, D, be); }                       // rhs = S + D R
@@ -679,8 +709,8 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
   {
     const double M = 8.0 * d * d * (double)d;
     double G = 0.0;
-    if (want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0) : (2.0 * 6 + 2.0 * sq + 2.0);
-    const double f = M * ((6.0 + sq + 4.0 / 3.0) + nc * G) * (double)nsl;
+    if (want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0) : (2.0 * pi_q + 2.0 * sq + 2.0);
+    const double f = M * ((pi_q + sq + 4.0 / 3.0) + nc * G) * (double)nsl;
     QOC_CUDA(h, cudaMemcpyAsync(h->dflops, &f, 8, cudaMemcpyHostToDevice, st));
   }
   h->have_jac = want_jac;
