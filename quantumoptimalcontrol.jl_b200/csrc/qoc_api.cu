@@ -487,7 +487,7 @@ struct GRun {
     for (int i = 0; i < npairs; i++) { g.A[i] = A[i]; g.B[i] = B[i]; }
     for (int i = 0; i < nadd; i++) { g.D[i] = D[i]; g.beta[i] = beta[i]; }
     g.C = C; g.cstride = cstride;
-    g_gemm_kernel<<<dim3(tiles, tiles, nb), 256, 0, st>>>(g);
+    g_gemm_launch(g, nb, st);
     h->launches++;
   }
   void mm1(int c, GOp a, GOp b, double alpha = 1.0, int nadd = 0, const GOp* D = nullptr, const double* beta = nullptr, double gamma = 0.0) const {
@@ -523,7 +523,7 @@ static int gpath_build_Q(qoc_handle* h, cudaStream_t st) {
       for (int i = 0; i < npairs; i++) { g.A[i] = A[i]; g.B[i] = B[i]; }
       for (int i = 0; i < nadd; i++) { g.D[i] = D[i]; g.beta[i] = 1.0; }
       g.C = C + G.first * slot; g.cstride = slot; g.cinner = G.inner; g.cstride2 = (long long)spp * slot;
-      g_gemm_kernel<<<dim3(tiles, tiles, G.count), 256, 0, st>>>(g);
+      g_gemm_launch(g, G.count, st);
       h->launches++;
     };
     auto Uop = [&](int t) { return GOp{h->dU + (G.first * L + t) * slot, (long long)L * slot, G.inner, (long long)p.nt * slot}; };

@@ -35,17 +35,40 @@ struct GGemm {
   long long cstride2;
 };
 
-typedef Cfg<4, 36, 8> GTile;  // 32 x 32 output tile, 32-wide k chunks, shared tiles with row stride 36
+#ifndef QOC_3M
+#error "qoc_gpath.cuh assumes the 3M complex product (Acc carries T1/T2/T3)"
+#endif
 
+// C = alpha (A1 B1 [+ A2 B2 ...]) + sum_q beta_q D_q + gamma I  for a batch of slices.
+// CTA tile (32 WM) x (16 WN): 8 warps as 4 x 2, each warp WM x WN tiles of 8 x 8 (WM, WN = 1, 2: 32 x 32 for small d;
+// 2, 4: 64 x 64, half the L2 -> shared traffic per flop and half the shared loads per DMMA, for d >= 64).
+// Operands are staged global -> shared per 32-wide k chunk.  8x8 tiles and k-steps that lie entirely outside the
+// d x d matrix are skipped (warp-uniform predicates; d = 40 fills 25 of the 64 tiles of its 2 x 2 CTA grid and 10 of
+// 16 k-steps), the zero padding of the staged tiles covers the partial ones.
+template <int WM, int WN>
 __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
-  constexpr int TS = GTile::S;
-  __shared__ __align__(16) double sm[4][32 * TS];  // A.re, A.im, B.re, B.im
+  constexpr int TM = 32 * WM, TN = 16 * WN;   // CTA tile
+  constexpr int AS = 36, BS = TN + 4;         // shared row strides (= 4 mod 8: conflict-free fragment loads)
+  extern __shared__ __align__(16) unsigned char gsm_raw[];
+  double* smAr = reinterpret_cast<double*>(gsm_raw);
+  double* smAi = smAr + TM * AS;
+  double* smBr = smAi + TM * AS;
+  double* smBi = smBr + 32 * BS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int mi = warp / 2, nj0 = (warp % 2) * 2;
+  const int wm = warp >> 1, wn = warp & 1;
   const int s = blockIdx.z, tm = blockIdx.y, tn = blockIdx.x;
   const int d = g.d, S = g.S, plane = d * S;
-  Acc<2> acc;
-  acc.zero();
+  const int gq = lane >> 2, q4 = lane & 3;
+  double T1[WM][WN][2], T2[WM][WN][2], T3[WM][WN][2];
+#pragma unroll
+  for (int a = 0; a < WM; a++)
+#pragma unroll
+    for (int b = 0; b < WN; b++) { T1[a][b][0] = T1[a][b][1] = T2[a][b][0] = T2[a][b][1] = T3[a][b][0] = T3[a][b][1] = 0.0; }
+  bool rowv[WM], colv[WN];
+#pragma unroll
+  for (int a = 0; a < WM; a++) rowv[a] = tm * TM + (wm * WM + a) * 8 < d;
+#pragma unroll
+  for (int b = 0; b < WN; b++) colv[b] = tn * TN + (wn * WN + b) * 8 < d;
   const int nkc = (d + 31) / 32;
   for (int p = 0; p < g.npairs; p++) {
     const double* Ag = g.A[p].p + g.A[p].off(s);
@@ -53,59 +76,101 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
     for (int kc = 0; kc < nkc; kc++) {
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
+      for (int i = 0; i < 2 * WM; i++) {          // A tile: TM rows x 32 columns
         const int e = tid + i * 256, r = e >> 4, c = (e & 15) * 2;
-        {
-          const int gr = tm * 32 + r, gc = kc * 32 + c;
-          double2 vr = make_double2(0.0, 0.0), vi = vr;
-          if (gr < d && gc < d) {
-            vr = *reinterpret_cast<const double2*>(Ag + (size_t)gr * S + gc);
-            vi = *reinterpret_cast<const double2*>(Ag + plane + (size_t)gr * S + gc);
-          }
-          *reinterpret_cast<double2*>(&sm[0][r * TS + c]) = vr;
-          *reinterpret_cast<double2*>(&sm[1][r * TS + c]) = vi;
+        const int gr = tm * TM + r, gc = kc * 32 + c;
+        double2 vr = make_double2(0.0, 0.0), vi = vr;
+        if (gr < d && gc < d) {
+          vr = *reinterpret_cast<const double2*>(Ag + (size_t)gr * S + gc);
+          vi = *reinterpret_cast<const double2*>(Ag + plane + (size_t)gr * S + gc);
         }
-        {
-          const int gr = kc * 32 + r, gc = tn * 32 + c;
-          double2 vr = make_double2(0.0, 0.0), vi = vr;
-          if (gr < d && gc < d) {
-            vr = *reinterpret_cast<const double2*>(Bg + (size_t)gr * S + gc);
-            vi = *reinterpret_cast<const double2*>(Bg + plane + (size_t)gr * S + gc);
-          }
-          *reinterpret_cast<double2*>(&sm[2][r * TS + c]) = vr;
-          *reinterpret_cast<double2*>(&sm[3][r * TS + c]) = vi;
+        *reinterpret_cast<double2*>(&smAr[r * AS + c]) = vr;
+        *reinterpret_cast<double2*>(&smAi[r * AS + c]) = vi;
+      }
+#pragma unroll
+      for (int i = 0; i < WN; i++) {              // B tile: 32 rows x TN columns
+        const int e = tid + i * 256, r = e / (TN / 2), c = (e % (TN / 2)) * 2;
+        const int gr = kc * 32 + r, gc = tn * TN + c;
+        double2 vr = make_double2(0.0, 0.0), vi = vr;
+        if (gr < d && gc < d) {
+          vr = *reinterpret_cast<const double2*>(Bg + (size_t)gr * S + gc);
+          vi = *reinterpret_cast<const double2*>(Bg + plane + (size_t)gr * S + gc);
         }
+        *reinterpret_cast<double2*>(&smBr[r * BS + c]) = vr;
+        *reinterpret_cast<double2*>(&smBi[r * BS + c]) = vi;
       }
       __syncthreads();
-      Mat At, Bt;
-      At.re = sm[0]; At.im = sm[1]; Bt.re = sm[2]; Bt.im = sm[3];
-      mm_acc<GTile, false>(acc, At, Bt, mi, nj0, lane);
+      const int kvalid = d - kc * 32;
+      const int kmax = kvalid >= 32 ? 8 : (kvalid + 3) / 4;
+      if (rowv[0] && colv[0]) {
+        const double* are = smAr + (wm * WM * 8 + gq) * AS + q4;
+        const double* aim = smAi + (wm * WM * 8 + gq) * AS + q4;
+        const double* bre = smBr + q4 * BS + wn * WN * 8 + gq;
+        const double* bim = smBi + q4 * BS + wn * WN * 8 + gq;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+          if (ks < kmax) {
+            double ar[WM], ai[WM], as[WM];
+#pragma unroll
+            for (int a = 0; a < WM; a++) { ar[a] = are[a * 8 * AS + ks * 4]; ai[a] = aim[a * 8 * AS + ks * 4]; as[a] = ar[a] + ai[a]; }
+#pragma unroll
+            for (int b = 0; b < WN; b++) {
+              if (colv[b]) {
+                const double br = bre[ks * 4 * BS + b * 8], bi = bim[ks * 4 * BS + b * 8];
+                const double bs = br + bi;
+#pragma unroll
+                for (int a = 0; a < WM; a++) {
+                  if (rowv[a]) {
+                    dmma(T1[a][b][0], T1[a][b][1], ar[a], br);
+                    dmma(T2[a][b][0], T2[a][b][1], ai[a], bi);
+                    dmma(T3[a][b][0], T3[a][b][1], as[a], bs);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
     }
   }
-  acc.finish();
-  const int row = tm * 32 + mi * 8 + (lane >> 2);
   double* Cg = g.C + (g.cinner > 0 ? (long long)(s / g.cinner) * g.cstride2 + (long long)(s % g.cinner) * g.cstride
                                    : (long long)s * g.cstride);
 #pragma unroll
-  for (int n = 0; n < 2; n++) {
-    const int col = tn * 32 + (nj0 + n) * 8 + 2 * (lane & 3);
-    if (row < d && col < d) {
-      double r0 = g.alpha * acc.re[n][0], r1 = g.alpha * acc.re[n][1];
-      double i0 = g.alpha * acc.im[n][0], i1 = g.alpha * acc.im[n][1];
-      const size_t o = (size_t)row * S + col;
-      for (int q = 0; q < g.nadd; q++) {
-        const double* Dg = g.D[q].p + g.D[q].off(s);
-        const double2 a = *reinterpret_cast<const double2*>(Dg + o), b = *reinterpret_cast<const double2*>(Dg + plane + o);
-        r0 = fma(g.beta[q], a.x, r0); r1 = fma(g.beta[q], a.y, r1);
-        i0 = fma(g.beta[q], b.x, i0); i1 = fma(g.beta[q], b.y, i1);
+  for (int a = 0; a < WM; a++) {
+    const int row = tm * TM + (wm * WM + a) * 8 + gq;
+#pragma unroll
+    for (int b = 0; b < WN; b++) {
+      const int col = tn * TN + (wn * WN + b) * 8 + 2 * q4;
+      if (row < d && col < d) {
+        // 3M: Re = T1 - T2, Im = T3 - T1 - T2
+        double r0 = g.alpha * (T1[a][b][0] - T2[a][b][0]), r1 = g.alpha * (T1[a][b][1] - T2[a][b][1]);
+        double i0 = g.alpha * ((T3[a][b][0] - T1[a][b][0]) - T2[a][b][0]), i1 = g.alpha * ((T3[a][b][1] - T1[a][b][1]) - T2[a][b][1]);
+        const size_t o = (size_t)row * S + col;
+        for (int q = 0; q < g.nadd; q++) {
+          const double* Dg = g.D[q].p + g.D[q].off(s);
+          const double2 u = *reinterpret_cast<const double2*>(Dg + o), v = *reinterpret_cast<const double2*>(Dg + plane + o);
+          r0 = fma(g.beta[q], u.x, r0); r1 = fma(g.beta[q], u.y, r1);
+          i0 = fma(g.beta[q], v.x, i0); i1 = fma(g.beta[q], v.y, i1);
+        }
+        if (row == col) r0 += g.gamma;
+        if (row == col + 1) r1 += g.gamma;
+        if (col + 1 >= d) { r1 = 0.0; i1 = 0.0; }
+        *reinterpret_cast<double2*>(Cg + o) = make_double2(r0, r1);
+        *reinterpret_cast<double2*>(Cg + plane + o) = make_double2(i0, i1);
       }
-      if (row == col) r0 += g.gamma;
-      if (row == col + 1) r1 += g.gamma;
-      if (col + 1 >= d) { r1 = 0.0; i1 = 0.0; }
-      *reinterpret_cast<double2*>(Cg + o) = make_double2(r0, r1);
-      *reinterpret_cast<double2*>(Cg + plane + o) = make_double2(i0, i1);
     }
   }
+}
+
+// host-side launch helper.  Measured on B200 (synthetic d = 64 / 128 / 256, cavity d = 80): 64 x 64 tiles (WM, WN = 2, 4;
+// 168 registers, one CTA per SM) are 10-50 % SLOWER than 32 x 32 (80 registers, three CTAs per SM) because the operand
+// staging is synchronous and only co-resident CTAs hide it; 64 x 32 at two CTAs per SM is a wash.  Larger tiles need an
+// asynchronous (cp.async / TMA) double buffer first -- DESIGN.md section 7.
+static inline void g_gemm_launch(const GGemm& g, int nb, cudaStream_t st) {
+  constexpr int WM = 1, WN = 2;
+  const size_t smem = (size_t)(2 * 32 * WM * 36 + 2 * 32 * (16 * WN + 4)) * 8;
+  const int tiles = (g.d + 31) / 32;
+  g_gemm_kernel<WM, WN><<<dim3(tiles, tiles, nb), 256, smem, st>>>(g);
 }
 
 // X[s] = (A0 + sum_j u[s][j] A_j) * scale ;  optionally the unscaled generator too (Taylor mode)

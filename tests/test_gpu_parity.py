@@ -439,3 +439,21 @@ def test_time_sharding_phase2_on_device_virtual_ranks():
         assert abs(float(J.cpu()[0]) - Jo) <= TOL_J
         g[:, lo:hi] = gl.cpu().numpy().T
     assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+
+
+@pytest.mark.parametrize("d,scale", [(7, 0.1), (16, 0.2), (20, 0.05), (24, 0.25), (27, 0.04), (27, 0.2), (28, 0.12)])
+def test_low_pade_degrees_every_shape_class(d, scale):
+    """||X_k||_1 below the [5/5] / [7/7] switch points (0.2 / 0.783 Frechet, 0.25 / 0.95 Taylor) in every shape class:
+    the low-degree Pade forms and their structured Frechet derivatives against the oracle (which selects its own degree)."""
+    cfg = o.config_synthetic(d, 12, nc=2, m=2, seed=77 + d)
+    cfg["A0"] = cfg["A0"] * scale
+    cfg["A"] = [a * scale for a in cfg["A"]]
+    for order in (0, 3):
+        Jo, go, co = o.evaluate(cfg, order=order)
+        J, g, cache = gpu_eval(cfg, order)
+        assert_parity(J, g, Jo, go)
+        assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-13
+        if order == 0:   # exact Frechet derivative itself
+            dU_o = np.array([[o.expm_frechet_sps(o.generator(cfg["A0"], cfg["A"], cfg["u"][:, k]), a)[1] for a in cfg["A"]]
+                             for k in range(cfg["u"].shape[1])])
+            assert np.abs(cache.dUkdu - dU_o).max() < 1e-13
