@@ -556,7 +556,7 @@ static int gpath_sweep2(qoc_handle* h, int mode, bool skip_bwd, bool want_grad, 
   const int grid = h->nseg < h->nsm * 4 ? h->nseg : h->nsm * 4;
   gs_seg_kernel<<<grid, GS_NW * 32, st_smem, st>>>(g, h->nseg);
   h->launches++;
-  if (want_grad && (mode == 2 || (mode == 0 && !skip_bwd))) {
+  if (want_grad && (mode == 2 || mode == 4 || (mode == 0 && !skip_bwd))) {
     const size_t c_smem = (size_t)(h->S + p.d) * 2 * p.m * 8;
     if (c_smem > 40 * 1024) QOC_CUDA(h, cudaFuncSetAttribute(gs_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
     gs_contract_kernel<<<dim3((unsigned)((size_t)p.batch * p.nt), p.nc), 256, c_smem, st>>>(g);
@@ -1079,12 +1079,33 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) kq_reduce_kernel(const double*
 extern "C" int qoc_shard_phase1_device(qoc_handle* h, const double* d_u, double* d_S_out, void* stream) {
   if (!h || !d_u || !d_S_out) return QOC_ERR_INVALID;
   if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
-  if (h->gpath) { h->err = "time sharding is not available on the general (d > 28) path yet"; return QOC_ERR_UNSUPPORTED; }
+  if (h->gpath && !h->gs2) { h->err = "time sharding on the general path needs the two-level sweeps (no running penalty)"; return QOC_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
   h->launches = 0;
   int rc = launch_k1(h, d_u, true, st);
   if (rc != QOC_OK) return rc;
+  if (h->gpath) {
+    // S = Q_{spp-1} ... Q_0: spp - 1 single products through the batched GEMM (the chain is short: spp ~ sqrt(nt))
+    const long long slot = h->slot_d;
+    double* bufs[2] = {h->dQ2, h->dQ2 + slot};   // dQ2 is free once the Q_seg are in dQ (nseg >= 2 slots)
+    const double* cur = h->dQ;
+    for (int s = 1; s < h->spp; s++) {
+      GGemm g;
+      memset(&g, 0, sizeof g);
+      g.d = h->prob.d; g.S = h->S; g.nb = 1; g.npairs = 1; g.alpha = 1.0;
+      g.A[0] = GOp{h->dQ + (size_t)s * slot, 0}; g.B[0] = GOp{cur, 0};
+      g.C = bufs[s & 1]; g.cstride = 0;
+      g_gemm_launch(g, 1, st);
+      h->launches++;
+      cur = bufs[s & 1];
+    }
+    planar_to_c128_kernel<<<32, 256, 0, st>>>(cur, h->prob.d, h->S, d_S_out);
+    h->launches++;
+    QOC_CUDA(h, cudaGetLastError());
+    h->have_u = true;
+    return QOC_OK;
+  }
   if (h->new_k2) {   // two-level product: group products in parallel, then G - 1 products by one CTA
     if ((rc = launch_k2(h, 5, true, nullptr, nullptr, nullptr, st, d_S_out)) != QOC_OK) return rc;
     h->have_u = true;
@@ -1132,7 +1153,7 @@ extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_e
 extern "C" int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int nranks, int rank, double* d_J, double* d_dJdu,
                                        void* stream) {
   if (!h || !d_S_all || nranks <= 0 || rank < 0 || rank >= nranks) return QOC_ERR_INVALID;
-  if (h->gpath) { h->err = "time sharding is not available on the general (d > 28) path yet"; return QOC_ERR_UNSUPPORTED; }
+  if (h->gpath && !h->gs2) { h->err = "time sharding on the general path needs the two-level sweeps (no running penalty)"; return QOC_ERR_UNSUPPORTED; }
   if (h->prob.cost == QOC_COST_NONE) { h->err = "qoc_shard_phase2_device needs a built-in cost"; return QOC_ERR_INVALID; }
   if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -1144,6 +1165,7 @@ extern "C" int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int
   shard_boundary_kernel<<<1, 256, (size_t)2 * p.d * p.m * 16, st>>>(q);
   h->launches += 1;
   int rc;
+  if (h->gpath) return gpath_sweep2(h, 4, false, true, q.lam_end, q.x_start, nullptr, d_dJdu, st);
   if (h->new_k2) {
     if ((rc = launch_k2(h, 4, false, q.lam_end, q.x_start, nullptr, st)) != QOC_OK) return rc;
   } else {

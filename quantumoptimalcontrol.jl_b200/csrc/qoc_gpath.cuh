@@ -556,7 +556,8 @@ __device__ __forceinline__ void gs_from_global(double* xs, const double* g, int 
 struct GS {
   int d, S, m, nc, nt, cost, n;
   int spp, L;          // segments per pulse, slices per segment (the last segment may be shorter)
-  int mode;            // 0: forward + cost + backward, 1: forward (+ cost unless skip_cost) only, 2: backward only
+  int mode;            // 0: forward + cost + backward, 1: forward only, 2: backward only (lam_final),
+                       // 4: forward from x_start_ext and backward from lam_final, no cost (time sharding)
   int skip_bwd;        // mode 0 without the backward part (propagate with a built-in cost)
   long long slot;
   const double* U;     // [b*nt + k]
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
   for (int e = tid; e < 2 * rows_pad * W; e += nth) b0[e] = 0.0;
   __syncthreads();
   double* cur = b0; double* nxt = b1;
-  const bool do_fwd = g.mode != 2, do_bwd = g.mode == 2 || (g.mode == 0 && !g.skip_bwd);
+  const bool do_fwd = g.mode != 2, do_bwd = g.mode == 2 || g.mode == 4 || (g.mode == 0 && !g.skip_bwd);
   if (do_fwd) {
     gs_from_global(cur, g.x_start_ext ? g.x_start_ext + (size_t)b * 2 * dm : g.x0, d, m, tid, nth);
     __syncthreads();
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
     gs_to_global(g.X + ((size_t)b * (g.nt + 1) + g.nt) * 2 * dm, cur, d, m, tid, nth);
   }
   if (g.mode == 1) return;
-  const bool builtin = do_fwd && g.cost != 2;
+  const bool builtin = do_fwd && g.cost != 2 && g.mode != 4;
   if (tid < 4) red[tid] = 0.0;
   __syncthreads();
   double cr_ = 0.0, ci_ = 0.0;
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_seg_kernel(GS g, int nseg_total
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nth = blockDim.x;
   for (int e = tid; e < 2 * rows_pad * W; e += nth) b0[e] = 0.0;
   __syncthreads();
-  const bool do_fwd = g.mode != 2, do_bwd = g.mode == 2 || (g.mode == 0 && !g.skip_bwd);
+  const bool do_fwd = g.mode != 2, do_bwd = g.mode == 2 || g.mode == 4 || (g.mode == 0 && !g.skip_bwd);
   for (int seg = blockIdx.x; seg < nseg_total; seg += gridDim.x) {
     const int b = seg / g.spp, si = seg - b * g.spp;
     const int k0 = si * g.L, k1 = (k0 + g.L < g.nt) ? k0 + g.L : g.nt;
@@ -745,6 +746,14 @@ __global__ void __launch_bounds__(256) gs_contract_kernel(GS g) {
     double t = 0.0;
     for (int w = 0; w < 8; w++) t += red[w];
     g.dJdu[(sl * g.nc) + j] = t;
+  }
+}
+
+// planar slot -> c128 column-major d x d (rank propagator hand-over of the time-sharded general path)
+__global__ void planar_to_c128_kernel(const double* P, int d, int S, double* out) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d * d; e += gridDim.x * blockDim.x) {
+    const int c = e / d, r = e - c * d;
+    reinterpret_cast<double2*>(out)[e] = make_double2(P[(size_t)r * S + c], P[(size_t)d * S + (size_t)r * S + c]);
   }
 }
 

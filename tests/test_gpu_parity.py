@@ -457,3 +457,38 @@ def test_low_pade_degrees_every_shape_class(d, scale):
             dU_o = np.array([[o.expm_frechet_sps(o.generator(cfg["A0"], cfg["A"], cfg["u"][:, k]), a)[1] for a in cfg["A"]]
                              for k in range(cfg["u"].shape[1])])
             assert np.abs(cache.dUkdu - dU_o).max() < 1e-13
+
+
+def test_time_sharding_general_path_virtual_ranks():
+    """Time-segment sharding on the general path (d > 28): rank propagators through the batched GEMM chain, boundary algebra
+    on the device, two-level sweeps from (x_start, lambda_end).  P = 3 virtual ranks on one GPU, uneven segments."""
+    import torch
+    from qoc_b200 import sharding
+    cfg = o.config_synthetic(32, 61, nc=2, m=3, seed=9)
+    P = 3
+    Jo, go, co = o.evaluate(cfg, order=0)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"])[1] if cfg["cost"] == o.COST_INFIDELITY else q.setup_infidelity_abs_trace(cfg["T"])[1]
+    dev = torch.device("cuda", 0)
+    S_all = torch.empty((P, 32, 32), dtype=torch.complex128, device=dev)
+    engines = []
+    for r in range(P):
+        lo, hi = sharding.time_partition(61, P, r)
+        e = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, cfg["x0"].shape[1], 0, order=0)
+        e.set_builtin_cost(cost, cfg["x0"])
+        u_dev = torch.from_numpy(np.ascontiguousarray(cfg["u"][:, lo:hi].T)).to(dev)
+        S_all[r].copy_(e.phase1_cm(u_dev))
+        engines.append(e)
+    # the rank propagators themselves
+    for r in range(P):
+        lo, hi = sharding.time_partition(61, P, r)
+        Sr = np.eye(32, dtype=complex)
+        for k in range(lo, hi):
+            Sr = co["Uk"][k] @ Sr
+        assert np.abs(S_all[r].cpu().numpy().T - Sr).max() < 1e-12
+    g = np.zeros_like(go)
+    for r in range(P):
+        lo, hi = sharding.time_partition(61, P, r)
+        J, gl = engines[r].phase2(S_all, P, r)
+        assert abs(float(J.cpu()[0]) - Jo) <= TOL_J
+        g[:, lo:hi] = gl.cpu().numpy().T
+    assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
