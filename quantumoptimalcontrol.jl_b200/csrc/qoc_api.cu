@@ -54,6 +54,7 @@ struct qoc_handle {
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
   bool gs2 = false;
+  bool k1_realh = false;      // K1 real-Hamiltonian fast path (Re A0 = Re A_j = 0, Frechet mode, [13/13] instantiation)
   bool k1_low = true;         // K1 instantiation with the low-degree Pade forms (false when ||A0||_1 alone is far above theta7)           // second-generation general-path sweeps (no running penalty)
   double normA0 = 0.0, normA[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long row_mask64 = 0ull;
@@ -306,6 +307,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     QOC_CUDA(h, cudaSetDevice(p.device));
     QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
     QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
+    QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
     QOC_CUDA(h, cudaFuncSetAttribute(k2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k2_smem));
     int occ = 1;
     QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C, true>, C::NTHREADS + NSW * 32, h->k1_smem));
@@ -403,6 +405,15 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     for (int j = 0; j < p.nc; j++) h->normA[j] = norm1(A + (size_t)j * 2 * p.d * p.d);
     // a performance heuristic only: the [13/13]-only instantiation is always correct
     h->k1_low = h->normA0 <= 2.0;
+    // real-Hamiltonian fast path of K1: every generator plane Re(A0), Re(A_j) exactly zero (X = -i H dt with a real H),
+    // exact-Frechet / expm-only mode, [13/13] instantiation.  QOC_NO_REALH=1 switches it off (A/B measurements).
+    {
+      bool re0 = true;
+      for (size_t e = 0; e < (size_t)p.d * p.d && re0; e++) re0 = (A0[2 * e] == 0.0);
+      for (size_t e = 0; e < (size_t)p.nc * p.d * p.d && re0; e++) re0 = (A[2 * e] == 0.0);
+      const char* off = getenv("QOC_NO_REALH");
+      h->k1_realh = re0 && !h->k1_low && p.order == QOC_ORDER_FRECHET && !(off && off[0] == '1');
+    }
   }
   if (h->gpath) {
     CR(cudaSetDevice(p.device));
@@ -759,7 +770,8 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
     // NW compute warps + 4 service warps
-    if (h->k1_low) k1_kernel<C, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
+    if (h->k1_realh) k1_kernel<C, false, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
+    else if (h->k1_low) k1_kernel<C, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
     else k1_kernel<C, false><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
     return 0;
   });

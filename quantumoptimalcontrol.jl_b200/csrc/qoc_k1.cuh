@@ -199,6 +199,78 @@ struct K1Ctx {
     e.alpha = alpha; e.c1 = c1; e.c2 = c2; e.c3 = c3; e.cI = cI; e.m1 = m1; e.m2 = m2; e.m3 = m3;
     return e;
   }
+
+  // ---- real-plane tile products (real-Hamiltonian fast path): one DMMA chain per tile, no 3M sums ----
+  // acc += A * B for this warp's 1 x BN tiles, A and B single real planes (row stride S)
+  __device__ __forceinline__ void racc(double (&acc)[C::BN][2], const double* A, const double* B) const {
+    const double* ap = A + (mi * 8 + (lane >> 2)) * C::S + (lane & 3);
+    const double* bp = B + (lane & 3) * C::S + nj0 * 8 + (lane >> 2);
+#pragma unroll
+    for (int ks = 0; ks < C::KS; ks++) {
+      const double a = ap[ks * 4];
+#pragma unroll
+      for (int n = 0; n < C::BN; n++) dmma(acc[n][0], acc[n][1], a, bp[ks * 4 * C::S + n * 8]);
+    }
+  }
+  // acc1 += A * B1, acc2 += A * B2 (left fragments loaded once)
+  __device__ __forceinline__ void racc_ab2(double (&acc1)[C::BN][2], double (&acc2)[C::BN][2], const double* A,
+                                           const double* B1, const double* B2) const {
+    const double* ap = A + (mi * 8 + (lane >> 2)) * C::S + (lane & 3);
+    const int bo = (lane & 3) * C::S + nj0 * 8 + (lane >> 2);
+#pragma unroll
+    for (int ks = 0; ks < C::KS; ks++) {
+      const double a = ap[ks * 4];
+#pragma unroll
+      for (int n = 0; n < C::BN; n++) {
+        dmma(acc1[n][0], acc1[n][1], a, B1[bo + ks * 4 * C::S + n * 8]);
+        dmma(acc2[n][0], acc2[n][1], a, B2[bo + ks * 4 * C::S + n * 8]);
+      }
+    }
+  }
+  // acc1 += A1 * B, acc2 += A2 * B (right fragments loaded once)
+  __device__ __forceinline__ void racc_a2b(double (&acc1)[C::BN][2], double (&acc2)[C::BN][2], const double* A1,
+                                           const double* A2, const double* B) const {
+    const int ao = (mi * 8 + (lane >> 2)) * C::S + (lane & 3);
+    const double* bp = B + (lane & 3) * C::S + nj0 * 8 + (lane >> 2);
+#pragma unroll
+    for (int ks = 0; ks < C::KS; ks++) {
+      const double a1 = A1[ao + ks * 4], a2 = A2[ao + ks * 4];
+#pragma unroll
+      for (int n = 0; n < C::BN; n++) {
+        const double bv = bp[ks * 4 * C::S + n * 8];
+        dmma(acc1[n][0], acc1[n][1], a1, bv);
+        dmma(acc2[n][0], acc2[n][1], a2, bv);
+      }
+    }
+  }
+  // f(o, row, col, v0, v1, last) for the two adjacent elements (row, col), (row, col + 1) of every owned tile; o = row * S + col,
+  // last = (col + 1 is a pad column).  f does the stores itself (rst()).
+  template <class F>
+  __device__ __forceinline__ void rstore(const double (&acc)[C::BN][2], F f) const {
+    const int row = mi * 8 + (lane >> 2);
+#pragma unroll
+    for (int n = 0; n < C::BN; n++) {
+      const int col = (nj0 + n) * 8 + 2 * (lane & 3);
+      if (row < d && col < d) f(row * C::S + col, row, col, acc[n][0], acc[n][1], col + 1 >= d);
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void rstore2(const double (&acc1)[C::BN][2], const double (&acc2)[C::BN][2], F f) const {
+    const int row = mi * 8 + (lane >> 2);
+#pragma unroll
+    for (int n = 0; n < C::BN; n++) {
+      const int col = (nj0 + n) * 8 + 2 * (lane & 3);
+      if (row < d && col < d) f(row * C::S + col, row, col, acc1[n][0], acc1[n][1], acc2[n][0], acc2[n][1], col + 1 >= d);
+    }
+  }
+  static __device__ __forceinline__ void rst(double* plane, int o, double v0, double v1, bool last) {
+    *reinterpret_cast<double2*>(plane + o) = make_double2(v0, last ? 0.0 : v1);
+  }
+  static __device__ __forceinline__ double2 rld(const double* plane, int o) { return *reinterpret_cast<const double2*>(plane + o); }
+  static __device__ __forceinline__ void rzero(double (&acc)[C::BN][2]) {
+#pragma unroll
+    for (int n = 0; n < C::BN; n++) acc[n][0] = acc[n][1] = 0.0;
+  }
   __device__ __forceinline__ void swap(int a, int b) {
     const int sa = __shfl_sync(0xffffffffu, role_slot, a), sb = __shfl_sync(0xffffffffu, role_slot, b);
     if (lane == a) role_slot = sb;
@@ -412,7 +484,7 @@ struct GenMap {
   static constexpr int RPT = (C::DMAX + G - 1) / G;  // rows per thread (1 or 2)
 };
 
-template <class C, bool LOW>
+template <class C, bool LOW, bool REALH>
 __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, const double2 (&a0r)[2], const double2 (&a0i)[2],
                                                const double (&uj)[8], bool need_x, SvcScratch* sc) {
   typedef GenMap<C> GM;
@@ -432,16 +504,23 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
 #pragma unroll
       for (int j = 0; j < 8; j++)
         if (j < nc) {
-          const double2 wr = reinterpret_cast<const double2*>(c.E0.re + (size_t)j * c.slot_d)[e];
+          if (!REALH) {
+            const double2 wr = reinterpret_cast<const double2*>(c.E0.re + (size_t)j * c.slot_d)[e];
+            xr[t].x = fma(uj[j], wr.x, xr[t].x); xr[t].y = fma(uj[j], wr.y, xr[t].y);
+          }
           const double2 wi = reinterpret_cast<const double2*>(c.E0.im + (size_t)j * c.slot_d)[e];
-          xr[t].x = fma(uj[j], wr.x, xr[t].x); xr[t].y = fma(uj[j], wr.y, xr[t].y);
           xi[t].x = fma(uj[j], wi.x, xi[t].x); xi[t].y = fma(uj[j], wi.y, xi[t].y);
         }
       // 1-norm in single precision (it only picks the number of squarings)
-      const float ax = (float)xr[t].x, bx = (float)xi[t].x, ay = (float)xr[t].y, by = (float)xi[t].y;
-      const float m0 = ax * ax + bx * bx, m1 = ay * ay + by * by;
-      cs0 += m0 * __frsqrt_rn(fmaxf(m0, 1e-37f));
-      cs1 += m1 * __frsqrt_rn(fmaxf(m1, 1e-37f));
+      if (REALH) {
+        cs0 += fabsf((float)xi[t].x);
+        cs1 += fabsf((float)xi[t].y);
+      } else {
+        const float ax = (float)xr[t].x, bx = (float)xi[t].x, ay = (float)xr[t].y, by = (float)xi[t].y;
+        const float m0 = ax * ax + bx * bx, m1 = ay * ay + by * by;
+        cs0 += m0 * __frsqrt_rn(fmaxf(m0, 1e-37f));
+        cs1 += m1 * __frsqrt_rn(fmaxf(m1, 1e-37f));
+      }
     }
   }
   if (act) *reinterpret_cast<float2*>(&sc->colsum[r0][2 * cp]) = make_float2(cs0, cs1);
@@ -471,7 +550,7 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
         reinterpret_cast<double2*>(mX.re)[e] = xr[t];
         reinterpret_cast<double2*>(mX.im)[e] = xi[t];
       }
-      reinterpret_cast<double2*>(mA.re)[e] = make_double2(xr[t].x * scl, xr[t].y * scl);
+      if (!REALH) reinterpret_cast<double2*>(mA.re)[e] = make_double2(xr[t].x * scl, xr[t].y * scl);
       reinterpret_cast<double2*>(mA.im)[e] = make_double2(xi[t].x * scl, xi[t].y * scl);
     }
   }
@@ -602,6 +681,127 @@ __device__ __forceinline__ void frechet13_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat
   c.mm2(Dst, A, Lw, E, W, ds);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Real-Hamiltonian fast path.  When A0 and every A_j have a zero real plane (X = -i H dt with a REAL H, e.g. the
+// tunable-bus model) every matrix of the [13/13] Pade / Frechet part 1 is either purely real (A2, A4, A6, W, V, M2, M4,
+// M6, Lw, Lv) or purely imaginary (A, E, U, Lu): each complex product collapses to ONE real tile product (no 3M sums),
+// stored in one plane of its slot.  The free planes carry the second member of (W1, Z1) and (Lw1, Lz1), which removes
+// the lincomb phases and lets the W/V and Lw/Lv pairs share a phase and their left fragments.  Only N^-1 and the tail
+// (R, rhs, L, squarings, segment product) are general complex.  Notation: A = i a, E = i e, U = i u, Lu = i lu.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ void pade13_build_N_realh(K1Ctx<C>& c, Mat U, Mat N) {
+  typedef K1Ctx<C> X;
+  const double* b = c_b13;
+  const Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), A6 = c.S(sA6), WZ = c.S(sWZ), W = c.S(sW);
+  double acc[C::BN][2], acc2[C::BN][2];
+  X::rzero(acc);
+  c.racc(acc, A.im, A.im);                       // A2 = -(a a)
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) { X::rst(A2.re, o, -v0, -v1, last); });
+  c.cbar();
+  X::rzero(acc);
+  c.racc(acc, A2.re, A2.re);                     // A4
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) { X::rst(A4.re, o, v0, v1, last); });
+  c.cbar();
+  X::rzero(acc);
+  c.racc(acc, A2.re, A4.re);                     // A6 ; W1 -> WZ.re, Z1 -> WZ.im from the same epilogue
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) {
+    const double2 a4 = X::rld(A4.re, o), a2 = X::rld(A2.re, o);
+    X::rst(A6.re, o, v0, v1, last);
+    X::rst(WZ.re, o, fma(b[13], v0, fma(b[11], a4.x, b[9] * a2.x)), fma(b[13], v1, fma(b[11], a4.y, b[9] * a2.y)), last);
+    X::rst(WZ.im, o, fma(b[12], v0, fma(b[10], a4.x, b[8] * a2.x)), fma(b[12], v1, fma(b[10], a4.y, b[8] * a2.y)), last);
+  });
+  c.cbar();
+  X::rzero(acc); X::rzero(acc2);
+  c.racc_ab2(acc, acc2, A6.re, WZ.re, WZ.im);    // W = A6 W1 + b7 A6 + b5 A4 + b3 A2 + b1 I ; V = A6 Z1 + b6 A6 + ... + b0 I -> N.re
+  c.rstore2(acc, acc2, [&](int o, int row, int col, double w0, double w1, double v0, double v1, bool last) {
+    const double2 a6 = X::rld(A6.re, o), a4 = X::rld(A4.re, o), a2 = X::rld(A2.re, o);
+    w0 += fma(b[7], a6.x, fma(b[5], a4.x, b[3] * a2.x)); w1 += fma(b[7], a6.y, fma(b[5], a4.y, b[3] * a2.y));
+    v0 += fma(b[6], a6.x, fma(b[4], a4.x, b[2] * a2.x)); v1 += fma(b[6], a6.y, fma(b[4], a4.y, b[2] * a2.y));
+    if (row == col) { w0 += b[1]; v0 += b[0]; }
+    if (row == col + 1) { w1 += b[1]; v1 += b[0]; }
+    X::rst(W.re, o, w0, w1, last);
+    X::rst(N.re, o, v0, v1, last);
+  });
+  c.cbar();
+  X::rzero(acc);
+  c.racc(acc, A.im, W.re);                       // u = a W ; N = V - U  ->  N.im = -u
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) {
+    X::rst(U.im, o, v0, v1, last);
+    X::rst(N.im, o, -v0, -v1, last);
+  });
+  c.cbar();
+}
+
+// part 1 of the Frechet derivative for a purely imaginary direction E = i e.  On exit Dst = Lu - Lv, Sst = Lu + Lv (complex).
+template <class C>
+__device__ __forceinline__ void frechet13_part1_realh(K1Ctx<C>& c, Mat E, Mat Dst, Mat Sst) {
+  typedef K1Ctx<C> X;
+  const double* b = c_b13;
+  const Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), A6 = c.S(sA6), WZ = c.S(sWZ), W = c.S(sW), M2 = c.S(sM2),
+            M4 = c.S(sM4), M6 = c.S(sM6), T = c.S(sT), Lw = c.S(sLw);
+  double acc[C::BN][2], acc2[C::BN][2];
+  X::rzero(acc);
+  c.racc(acc, A.im, E.im);                       // M2 = A E + E A = -(a e + e a)
+  c.racc(acc, E.im, A.im);
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) { X::rst(M2.re, o, -v0, -v1, last); });
+  c.cbar();
+  X::rzero(acc);
+  c.racc(acc, A2.re, M2.re);                     // M4 = A2 M2 + M2 A2
+  c.racc(acc, M2.re, A2.re);
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) { X::rst(M4.re, o, v0, v1, last); });
+  c.cbar();
+  X::rzero(acc);
+  c.racc(acc, A4.re, M2.re);                     // M6 = A4 M2 + M4 A2 ; Lw1 -> T.re, Lz1 -> T.im
+  c.racc(acc, M4.re, A2.re);
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) {
+    const double2 m4 = X::rld(M4.re, o), m2 = X::rld(M2.re, o);
+    X::rst(M6.re, o, v0, v1, last);
+    X::rst(T.re, o, fma(b[13], v0, fma(b[11], m4.x, b[9] * m2.x)), fma(b[13], v1, fma(b[11], m4.y, b[9] * m2.y)), last);
+    X::rst(T.im, o, fma(b[12], v0, fma(b[10], m4.x, b[8] * m2.x)), fma(b[12], v1, fma(b[10], m4.y, b[8] * m2.y)), last);
+  });
+  c.cbar();
+  X::rzero(acc); X::rzero(acc2);
+  c.racc_ab2(acc, acc2, A6.re, T.re, T.im);      // Lw = A6 Lw1 + M6 W1 + b7 M6 + b5 M4 + b3 M2
+  c.racc_ab2(acc, acc2, M6.re, WZ.re, WZ.im);    // Lv = A6 Lz1 + M6 Z1 + b6 M6 + b4 M4 + b2 M2   -> Sst.re
+  c.rstore2(acc, acc2, [&](int o, int, int, double w0, double w1, double v0, double v1, bool last) {
+    const double2 m6 = X::rld(M6.re, o), m4 = X::rld(M4.re, o), m2 = X::rld(M2.re, o);
+    w0 += fma(b[7], m6.x, fma(b[5], m4.x, b[3] * m2.x)); w1 += fma(b[7], m6.y, fma(b[5], m4.y, b[3] * m2.y));
+    v0 += fma(b[6], m6.x, fma(b[4], m4.x, b[2] * m2.x)); v1 += fma(b[6], m6.y, fma(b[4], m4.y, b[2] * m2.y));
+    X::rst(Lw.re, o, w0, w1, last);
+    X::rst(Sst.re, o, v0, v1, last);
+  });
+  c.cbar();
+  X::rzero(acc);
+  c.racc(acc, A.im, Lw.re);                      // lu = a Lw + e W ;  D = Lu - Lv = -Lv + i lu,  S = Lu + Lv = Lv + i lu
+  c.racc(acc, E.im, W.re);
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) {
+    const double2 lv = X::rld(Sst.re, o);
+    X::rst(Dst.re, o, -lv.x, -lv.y, last);
+    X::rst(Dst.im, o, v0, v1, last);
+    X::rst(Sst.im, o, v0, v1, last);
+  });
+  c.cbar();
+}
+
+// R = I + 2 N^-1 U for a purely imaginary U = i u:  N^-1 (i u) = -Ni u + i Nr u
+template <class C>
+__device__ __forceinline__ void tail_R_realh(K1Ctx<C>& c, Mat R, Mat Ninv, Mat U) {
+  typedef K1Ctx<C> X;
+  double acc[C::BN][2], acc2[C::BN][2];
+  X::rzero(acc); X::rzero(acc2);
+  c.racc_a2b(acc, acc2, Ninv.im, Ninv.re, U.im);
+  c.rstore2(acc, acc2, [&](int o, int row, int col, double r0, double r1, double i0, double i1, bool last) {
+    r0 = -2.0 * r0; r1 = -2.0 * r1;
+    if (row == col) r0 += 1.0;
+    if (row == col + 1) r1 += 1.0;
+    X::rst(R.re, o, r0, r1, last);
+    X::rst(R.im, o, 2.0 * i0, 2.0 * i1, last);
+  });
+  c.cbar();
+}
+
 // The reference's truncated Taylor series (src/gradient_computations.jl:177-213) with dt = 1.
 // X (unscaled generator) in s[sX]; result -> out.  Uses sM2, sM4, sM6, sLw as scratch.
 template <class C>
@@ -641,8 +841,11 @@ __device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, Mat Aj, Mat out, in
 
 // LOW: the [5/5] / [7/7] forms are compiled in.  The host instantiates LOW = false when the drift alone puts every slice far
 // above theta7 (the bus config): the extra code paths cost the [13/13]-only path 3 % (measured) even when never taken.
-template <class C, bool LOW>
+// REALH: real-Hamiltonian fast path (exact Frechet or expm-only mode, [13/13] form only; the host selects it when the real
+// planes of A0 and of every A_j are exactly zero).
+template <class C, bool LOW, bool REALH = false>
 __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1Params p) {
+  static_assert(!(LOW && REALH), "the real-Hamiltonian path is built for the [13/13] form only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int S = C::S;
   constexpr int NALL = C::NTHREADS + NSW * 32;
@@ -736,9 +939,10 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
   const unsigned slot_bytes = (unsigned)slot_d * 8u;
   if (it.valid()) {
     load_u(it);
-    sq = build_generator<C, LOW>(p, c, a0r, a0i, uj, need_x, sc);
+    sq = build_generator<C, LOW, REALH>(p, c, a0r, a0i, uj, need_x, sc);
     if (LOW) { qd = sq >> 8; sq &= 255; }
-    if (!LOW || qd == 13) pade13_build_N<C>(c, c.fixed(sU0), c.fixed(sN0));
+    if (REALH) pade13_build_N_realh<C>(c, c.fixed(sU0), c.fixed(sN0));
+    else if (!LOW || qd == 13) pade13_build_N<C>(c, c.fixed(sU0), c.fixed(sN0));
     else pade_low_build_N<C>(c, c.fixed(sU0), c.fixed(sN0), qd);
     bar_arrive_i<BAR_NREADY>(NALL);
   }
@@ -774,7 +978,8 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
       } else {
         // control 0 last: its (D, S) stay in (sM2, sLv), which the other controls' part1 uses as workspace (sM2)
         for (int j = nc - 1; j >= 0; j--)
-          if (!LOW || q_cur == 13) frechet13_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)));
+          if (REALH) frechet13_part1_realh<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)));
+          else if (!LOW || q_cur == 13) frechet13_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)));
           else frechet_low_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)), q_cur);
       }
     }
@@ -782,9 +987,10 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
 
     // ---- software pipeline: generator and Pade denominator of the NEXT slice while N^-1(k) is being formed ----
     if (nx.valid()) {
-      sq = build_generator<C, LOW>(p, c, a0r, a0i, uj, need_x, sc);
+      sq = build_generator<C, LOW, REALH>(p, c, a0r, a0i, uj, need_x, sc);
       if (LOW) { qd = sq >> 8; sq &= 255; }
-      if (!LOW || qd == 13) pade13_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
+      if (REALH) pade13_build_N_realh<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
+      else if (!LOW || qd == 13) pade13_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
       else pade_low_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)), qd);
       bar_arrive_p<BAR_NREADY>(par ^ 1, NALL);
     }
@@ -795,7 +1001,8 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
     QOC_STAMP(3);
     const Mat Ninv = c.fixed(sN0 + par), U = c.fixed(sU0 + par);
     // R = N^-1 (V + U) = N^-1 (N + 2U) = I + 2 N^-1 U   (R lives in role sT; results ping-pong by swapping roles)
-    c.mm1(c.S(sT), Ninv, U, c.epi(2.0, 0.0, U, 0.0, U, 0.0, U, 1.0));
+    if (REALH) tail_R_realh<C>(c, c.S(sT), Ninv, U);
+    else c.mm1(c.S(sT), Ninv, U, c.epi(2.0, 0.0, U, 0.0, U, 0.0, U, 1.0));
     if (p.want_jac && !taylor) {
       {
         const Mat R = c.S(sT), rhs = c.S(sM4);
