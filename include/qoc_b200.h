@@ -162,6 +162,11 @@ double qoc_stage_ms(const qoc_handle* h, int stage);
 /* algorithmic flops (SURVEY.md 8d F_alg) of the last call, with the Pade degree / squarings actually chosen
  * per slice, summed over slices and pulses.                                                                  */
 double qoc_last_alg_flops(const qoc_handle* h);
+/* flops EXECUTED by K1's DMMA tile loops in the last call: zero-padded (8 NT)^2 x (4 KS) real tile products, three per
+ * complex product (3M scheme), one per product on the real-Hamiltonian path.  0 on the general (d > 28) path.
+ * A diagnostic next to qoc_last_alg_flops: the roofline fraction is quoted on the algorithmic figure, this one says how
+ * busy the FP64 tensor pipe actually was.                                                                        */
+double qoc_last_exec_flops(const qoc_handle* h);
 int qoc_version(void);
 
 #ifdef __cplusplus

@@ -50,6 +50,7 @@ SYMBOLS = {
     "qoc_set_profiling": (C.c_int, [_vp, C.c_int]),
     "qoc_stage_ms": (C.c_double, [_vp, C.c_int]),
     "qoc_last_alg_flops": (C.c_double, [_vp]),
+    "qoc_last_exec_flops": (C.c_double, [_vp]),
     "qoc_version": (C.c_int, []),
 }
 

@@ -74,7 +74,7 @@ struct qoc_handle {
   bool profiling = false;
   cudaEvent_t ev[4];
   double stage_ms[3] = {0, 0, 0};
-  double alg_flops = 0.0;
+  double alg_flops = 0.0, k1_exec_flops = 0.0;
   std::string err;
 };
 
@@ -190,6 +190,7 @@ extern "C" double qoc_stage_ms(const qoc_handle* h, int stage) {
   return (h && stage >= 0 && stage < 3) ? h->stage_ms[stage] : -1.0;
 }
 extern "C" double qoc_last_alg_flops(const qoc_handle* h) { return h ? h->alg_flops : 0.0; }
+extern "C" double qoc_last_exec_flops(const qoc_handle* h) { return h ? h->k1_exec_flops : 0.0; }
 
 extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
@@ -393,7 +394,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   CR(cudaMalloc(&h->dbnd, 2 * dmB));
   CR(cudaMalloc(&h->dJ, (size_t)p.batch * 8));
   CR(cudaMalloc(&h->dg, nsl * p.nc * 8));
-  CR(cudaMalloc(&h->dflops, 8));
+  CR(cudaMalloc(&h->dflops, 16));
   CR(cudaMalloc(&h->dS, slotB));
   {
     auto norm1 = [&](const double* M) {
@@ -722,7 +723,8 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
     double G = 0.0;
     if (want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0) : (2.0 * pi_q + 2.0 * sq + 2.0);
     const double f = M * ((pi_q + sq + 4.0 / 3.0) + nc * G) * (double)nsl;
-    QOC_CUDA(h, cudaMemcpyAsync(h->dflops, &f, 8, cudaMemcpyHostToDevice, st));
+    const double f2[2] = {f, 0.0};   // executed flops are not tracked on the general path
+    QOC_CUDA(h, cudaMemcpyAsync(h->dflops, f2, 16, cudaMemcpyHostToDevice, st));
   }
   h->have_jac = want_jac;
   if (h->gs2) return gpath_build_Q(h, st);
@@ -766,7 +768,7 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   k.theta7 = (p.order == QOC_ORDER_FRECHET) ? 0.783 : 0.95;
   { const char* f13 = getenv("QOC_PADE13"); if (f13 && f13[0] == '1') { k.theta5 = -1.0; k.theta7 = -1.0; } }
   k.dbg = h->dbg; k.dbg_slices = h->dbg_slices; k.dbg_flags = h->dbg_flags;
-  QOC_CUDA(h, cudaMemsetAsync(h->dflops, 0, 8, st));
+  QOC_CUDA(h, cudaMemsetAsync(h->dflops, 0, 16, st));
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
     // NW compute warps + 4 service warps
@@ -925,9 +927,10 @@ extern "C" int qoc_eval_device(qoc_handle* h, const double* d_u, double* d_J, do
 }
 
 static int fetch_flops(qoc_handle* h, bool grad) {
-  double f = 0;
-  QOC_CUDA(h, cudaMemcpy(&f, h->dflops, 8, cudaMemcpyDeviceToHost));
-  h->alg_flops = f + sweep_flops(h->prob, grad);
+  double f[2] = {0, 0};
+  QOC_CUDA(h, cudaMemcpy(f, h->dflops, 16, cudaMemcpyDeviceToHost));
+  h->alg_flops = f[0] + sweep_flops(h->prob, grad);
+  h->k1_exec_flops = f[1];
   return QOC_OK;
 }
 

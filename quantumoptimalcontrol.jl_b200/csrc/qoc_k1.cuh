@@ -34,7 +34,7 @@ struct K1Params {
   double* U;               // [batch*nt] planar slots
   double* L;               // [(b*nt + k)*nc + j] planar slots
   double* Q;               // [nseg] planar slots
-  double* flops;           // accumulated algorithmic flops (F_alg) over slices
+  double* flops;           // [0] accumulated algorithmic flops (F_alg) over slices, [1] flops executed by the DMMA tile loops
   int* status;             // set to QOC_ERR_SINGULAR (8) on a zero pivot
   double theta13;          // scaling threshold: 5.4 (Higham-2005 / reference) or 4.74 (Frechet, Al-Mohy-Higham)
   double theta5, theta7;   // ||X||_1 <= theta5: [5/5] Pade, <= theta7: [7/7], else [13/13] with scaling
@@ -75,7 +75,7 @@ __host__ __device__ constexpr int k1_pad_rows(int d) {
 // named barriers: 1 = compute warps, 6 = service warps, 2/3 = "N ready" (even/odd slice), 4/5 = "N^-1 ready".
 // The ids are IMMEDIATES in the SASS (a register id makes ptxas reserve all 16 hardware barriers for the CTA, which caps
 // the number of co-resident CTAs of the small shape classes).
-enum : int { BAR_C = 1, BAR_NREADY = 2, BAR_NINV = 4, BAR_SVC = 6 };
+enum : int { BAR_C = 1, BAR_NREADY = 2, BAR_NINV = 4, BAR_SVC = 6 /* and 7: pivot steps, by step parity */ };
 template <int ID>
 __device__ __forceinline__ void bar_sync_i(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
 template <int ID>
@@ -153,7 +153,14 @@ struct K1Ctx {
   }
   __device__ __forceinline__ Mat E(int j) const { Mat m; m.re = E0.re + (size_t)j * slot_d; m.im = E0.im + (size_t)j * slot_d; return m; }
   __device__ __forceinline__ Mat extra(int i) const { Mat m; m.re = X0.re + (size_t)i * slot_d; m.im = X0.im + (size_t)i * slot_d; return m; }
-  __device__ __forceinline__ void cbar() { bar_sync_i<BAR_C>(C::NTHREADS); mark(); }
+  // fence_next: the slots written in this phase leave through the copy engine right after its barrier -- every thread
+  // makes its generic-proxy writes visible to the async proxy before it arrives
+  bool fence_next = false;
+  __device__ __forceinline__ void cbar() {
+    if (fence_next) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); fence_next = false; }
+    bar_sync_i<BAR_C>(C::NTHREADS);
+    mark();
+  }
 
   // dst = epilogue(sum of products); one compute-warp barrier at the end
   template <class F>
@@ -366,22 +373,54 @@ struct DiffSumEpi {
 constexpr int NSW = 4;  // service warps
 
 struct SvcScratch {
-  double2 gbuf[2][32];
-  double2 rowbuf[2][32];
-  double2 pinv[2];
-  int pidx[2];
+  double2 gbuf[2][32];   // multipliers W[.][k] / pivot of the step, double-buffered by step parity
+  double2 rowbuf[2][32]; // (unused by the look-ahead inverse; keeps the layout the host sizes)
+  double2 pinv[2];       // 1 / pivot
+  int pidx[2];           // pivot lane p, or -1 - p when the pivot is exactly zero
   int ok;             // cleared to 0 by a service warp that meets a zero pivot
   int pad_;
   float colsum[22][32];  // partial column sums of the generator build, one row per row group (compute warps)
 };
 
-__device__ __forceinline__ void bar_svc() { bar_sync_i<BAR_SVC>(NSW * 32); }
+// 1 / x for x > 0: MUFU.RCP64H seed (SFU, ~20 bits, full double exponent range) + one cubic step = 3 dependent FP64
+// instructions instead of the ~12 of an IEEE division -- the service warps' FP64 instructions each wait behind a DMMA.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  // one cubic step r (1 + e + e^2), e = 1 - x r: 3 dependent FP64 instructions, error e^3 ~ 2^-60
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+}
 
+// pivot search in column (cr, ci) over the lanes that have not pivoted yet + multipliers of the step -> scratch[par]
+__device__ __forceinline__ void svc_publish(SvcScratch* sc, int par, double cr, double ci, bool used, int lane) {
+  const double mag = cr * cr + ci * ci;
+  // arg-max without touching the FP64 pipe: for mag >= 0 the high word of the double is a monotone key
+  // (sign 0, exponent, 20 mantissa bits -- plenty for a pivot choice); low 5 bits carry the lane.
+  const unsigned key = used ? 0u : (((unsigned)__double2hiint(mag) & ~31u) | (unsigned)(31 - lane));
+  const unsigned best = __reduce_max_sync(0xffffffffu, key);
+  const int p = 31 - (int)(best & 31u);
+  const bool okp = (best >> 5) != 0u;
+  // every lane inverts its own candidate concurrently with the reduction; the pivot lane's value is picked
+  const double den = fast_rcp(mag);
+  const double ir = cr * den, ii = -ci * den;
+  const double pir = __shfl_sync(0xffffffffu, ir, p), pii = __shfl_sync(0xffffffffu, ii, p);  // 1/pivot
+  sc->gbuf[par][lane] = make_double2(cr * pir - ci * pii, cr * pii + ci * pir);
+  if (lane == 0) { sc->pinv[par] = make_double2(pir, pii); sc->pidx[par] = okp ? p : -1 - p; }
+}
+
+// One CTA-level hand-over per pivot step: the owner of pivot column k publishes (multipliers, 1/pivot, pivot lane) and
+// ARRIVES on the step's named barrier, the other three warps SYNC on it.  The pivot row never goes through shared memory:
+// every warp reads the entries of its own columns from its own lane p by shuffle.  Look-ahead: the warp that owns column
+// k+1 updates that column first, runs the pivot search of step k+1 and publishes before it updates its remaining
+// columns, so the dependent chain of a step is (one column update -> |.|^2 -> arg-max -> reciprocal -> multipliers)
+// and the bulk of the rank-1 update is off the critical path.
 template <class C>
 __device__ __noinline__ bool service_inverse(Mat N, int d, SvcScratch* sc, int sw, int lane) {
   constexpr int S = C::S;
   constexpr int DM = C::DMAX;
   constexpr int CL = DM / NSW;  // local columns; DMAX is a multiple of 4
+  static_assert(NSW == 4 && DM % NSW == 0, "cyclic column ownership over four service warps");
   double wr[CL], wi[CL];
 #pragma unroll
   for (int c = 0; c < CL; c++) {
@@ -393,64 +432,57 @@ __device__ __noinline__ bool service_inverse(Mat N, int d, SvcScratch* sc, int s
   bool used = lane >= DM;
   int mycol = -1;
   bool ok = true;
-  int par = 0;
+  if (sw == 0) {  // step 0 has no look-ahead: its owner publishes up front
+    svc_publish(sc, 0, wr[0], wi[0], used, lane);
+    bar_arrive_i<BAR_SVC>(NSW * 32);
+  }
 #pragma unroll 1
   for (int kk = 0; kk < CL; kk++) {
 #pragma unroll
     for (int o = 0; o < NSW; o++) {
-      if (sw == o) {  // owner of pivot column k = NSW*kk + o: it sits at local position 0
-        const double mag = wr[0] * wr[0] + wi[0] * wi[0];
-        // arg-max without touching the FP64 pipe: for mag >= 0 the high word of the double is a monotone key
-        // (sign 0, exponent, 20 mantissa bits -- plenty for a pivot choice); low 5 bits carry the lane.
-        const unsigned key = used ? 0u : (((unsigned)__double2hiint(mag) & ~31u) | (unsigned)(31 - lane));
-        const unsigned best = __reduce_max_sync(0xffffffffu, key);
-        const int p = 31 - (int)(best & 31u);
-        const bool okp = (best >> 5) != 0u;
-        // every lane inverts its own candidate concurrently with the reduction; the pivot lane's value is picked
-        const double den = 1.0 / mag;
-        const double ir = wr[0] * den, ii = -wi[0] * den;
-        const double pir = __shfl_sync(0xffffffffu, ir, p), pii = __shfl_sync(0xffffffffu, ii, p);  // 1/pivot
-        sc->gbuf[par][lane] = make_double2(wr[0] * pir - wi[0] * pii, wr[0] * pii + wi[0] * pir);
-        if (lane == 0) { sc->pinv[par] = make_double2(pir, pii); sc->pidx[par] = okp ? p : -1 - p; }
-      }
-      bar_svc();
-      int p = sc->pidx[par];
+      const int sp = o & 1;   // step parity: k = NSW*kk + o and NSW is even
+      const bool owner = (sw == o);
+      if (owner) __syncwarp();
+      else if (sp) bar_sync_i<BAR_SVC + 1>(NSW * 32);
+      else bar_sync_i<BAR_SVC>(NSW * 32);
+      int p = sc->pidx[sp];
       if (p < 0) { ok = false; p = -1 - p; }
       const bool isp = (lane == p);
-      if (isp) {
-#pragma unroll
-        for (int c = 0; c < CL; c++) sc->rowbuf[par][NSW * c + sw] = make_double2(wr[c], wi[c]);
-        used = true;
-        mycol = NSW * kk + o;
-      }
-      bar_svc();
-      const double2 pinv = sc->pinv[par];
-      double2 g = sc->gbuf[par][lane];
+      const double2 pinv = sc->pinv[sp];
+      double2 g = sc->gbuf[sp][lane];
+      if (isp) { used = true; mycol = NSW * kk + o; g = make_double2(-pinv.x, -pinv.y); }
       // lanes != p: W[c] -= (W[k]/piv) * row[c];  lane p: W[c] = row[c]/piv  == 0 - (-1/piv) * row[c]
-      if (isp) {
-        g = make_double2(-pinv.x, -pinv.y);
-#pragma unroll
-        for (int c = 0; c < CL; c++) { wr[c] = 0.0; wi[c] = 0.0; }
-      }
-      if (sw == o) {
-        // note: the owner's rowbuf entries are indexed by CURRENT register position
+      if (owner) {
+        // the pivot column sits at register position 0; the window shifts by one and the new column is appended
 #pragma unroll
         for (int c = 1; c < CL; c++) {
-          const double2 r = sc->rowbuf[par][NSW * c + sw];
-          wr[c - 1] = fma(-g.x, r.x, fma(g.y, r.y, wr[c]));
-          wi[c - 1] = fma(-g.x, r.y, fma(-g.y, r.x, wi[c]));
+          const double rr = __shfl_sync(0xffffffffu, wr[c], p), ri = __shfl_sync(0xffffffffu, wi[c], p);
+          const double br = isp ? 0.0 : wr[c], bi = isp ? 0.0 : wi[c];
+          wr[c - 1] = fma(-g.x, rr, fma(g.y, ri, br));
+          wi[c - 1] = fma(-g.x, ri, fma(-g.y, rr, bi));
         }
         wr[CL - 1] = isp ? pinv.x : -g.x;
         wi[CL - 1] = isp ? pinv.y : -g.y;
       } else {
+        const bool next_owner = (sw == ((o + 1) & (NSW - 1))) && (NSW * kk + o + 1 < DM);
+        {
+          const double rr = __shfl_sync(0xffffffffu, wr[0], p), ri = __shfl_sync(0xffffffffu, wi[0], p);
+          const double br = isp ? 0.0 : wr[0], bi = isp ? 0.0 : wi[0];
+          wr[0] = fma(-g.x, rr, fma(g.y, ri, br));
+          wi[0] = fma(-g.x, ri, fma(-g.y, rr, bi));
+        }
+        if (next_owner) {
+          svc_publish(sc, sp ^ 1, wr[0], wi[0], used, lane);
+          if (sp) bar_arrive_i<BAR_SVC>(NSW * 32); else bar_arrive_i<BAR_SVC + 1>(NSW * 32);
+        }
 #pragma unroll
-        for (int c = 0; c < CL; c++) {
-          const double2 r = sc->rowbuf[par][NSW * c + sw];
-          wr[c] = fma(-g.x, r.x, fma(g.y, r.y, wr[c]));
-          wi[c] = fma(-g.x, r.y, fma(-g.y, r.x, wi[c]));
+        for (int c = 1; c < CL; c++) {
+          const double rr = __shfl_sync(0xffffffffu, wr[c], p), ri = __shfl_sync(0xffffffffu, wi[c], p);
+          const double br = isp ? 0.0 : wr[c], bi = isp ? 0.0 : wi[c];
+          wr[c] = fma(-g.x, rr, fma(g.y, ri, br));
+          wi[c] = fma(-g.x, ri, fma(-g.y, rr, bi));
         }
       }
-      par ^= 1;
     }
   }
   // every window has rotated CL times: local position c holds column NSW*c + sw again.  Scatter into the slot
@@ -858,9 +890,13 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
   c.d = d;
   c.slot_d = slot_d;
   c.n2 = slot_d / 2;
-  c.tid = threadIdx.x;
+  // The four service warps are the FIRST warps of the CTA (one per SM sub-partition), the compute warps follow: when a
+  // service DFMA and a compute DMMA are both ready the scheduler then tends to pick the (older) service warp, which
+  // shortens the dependent chain of a pivot step.  c.tid / c.warp are the compute-side indices.
+  const int wid = threadIdx.x >> 5;
+  c.tid = (int)threadIdx.x - NSW * 32;
   c.lane = threadIdx.x & 31;
-  c.warp = threadIdx.x >> 5;
+  c.warp = wid - NSW;
   c.mi = c.warp / (C::NT / C::BN);
   c.nj0 = (c.warp % (C::NT / C::BN)) * C::BN;
   c.base = base;
@@ -873,7 +909,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
   const int pad_rows = k1_pad_rows<C>(d);
   double* tail = base + (size_t)nslots * slot_d;
   SvcScratch* sc = reinterpret_cast<SvcScratch*>(tail + pad_rows * S);
-  const bool is_service = (c.warp >= C::NW);
+  const bool is_service = (wid < NSW);
   const bool taylor = (p.order != 0);
 
   // zero everything once (pad columns must be exactly zero, all pad reads finite), then load the control operators
@@ -894,7 +930,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
   if (is_service) {
     // =============================== service warps: one inverse per slice ===============================
     const int lane = c.lane;
-    const int sw = c.warp - C::NW;
+    const int sw = wid;
     bool all_ok = true;
     int par = 0;
     int dbg_i = (sw == 0) ? 0 : (1 << 30);
@@ -914,8 +950,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
   }
 
   // =============================== compute warps ===============================
-  double my_flops = 0.0;
-  const double M = 8.0 * d * d * (double)d;
+  long long my_thirds = 0, my_real = 0;   // algorithmic products (thirds), executed real tile products
   int dbg_i = (c.warp == 0) ? 0 : (1 << 30);
   if (p.dbg && (p.dbg_flags & 2) && blockIdx.x == 0 && c.warp == 0) { c.stamp = p.dbg + 16 * p.dbg_slices; c.stamp_left = 4096; }
   // A0 stays in registers for the whole launch
@@ -1013,29 +1048,36 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
           c.mm1(Dj, Ninv, rhs, c.epi(scl, 0.0, Ninv, 0.0, Ninv, 0.0, Ninv, 0.0));
         }
       }
-      // squaring phase: L <- R L + L R ; R <- R R   (results land in scratch roles sM6 / sLw, then the roles swap)
+      // squaring phase: L <- R L + L R ; R <- R R   (results land in scratch roles sM6 / sLw, then the roles swap).
+      // The last control's L product and the R product share one barrier interval (independent outputs).
+      if (sq_cur == 0) { fence_async_smem(); c.cbar(); }   // (L_j were written by the phases above)
       for (int t = 0; t < sq_cur; t++) {
         const Mat R = c.S(sT);
         for (int j = 0; j < nc; j++) {
           const Mat Lj = c.S(k1_role_D(j));
-          c.mm2(c.S(sM6), R, Lj, Lj, R, NoEpi());
-          c.swap(sM6, k1_role_D(j));
+          Acc<C::BN> acc; acc.zero();
+          mm_acc<C, false>(acc, R, Lj, c.mi, c.nj0, c.lane);
+          mm_acc<C, false>(acc, Lj, R, c.mi, c.nj0, c.lane);
+          mm_store<C>(c.S(sM6), acc, c.d, c.mi, c.nj0, c.lane, NoEpi());
+          if (j + 1 < nc) { c.cbar(); c.swap(sM6, k1_role_D(j)); }   // sM6 is the scratch of the next control
         }
+        c.fence_next = (t + 1 == sq_cur);
         c.mm1(c.S(sLw), R, R, NoEpi());
+        c.swap(sM6, k1_role_D(nc - 1));
         c.swap(sT, sLw);
       }
     } else {
+      if (sq_cur == 0) { fence_async_smem(); c.cbar(); }
       for (int t = 0; t < sq_cur; t++) {
         const Mat R = c.S(sT);
+        c.fence_next = (t + 1 == sq_cur);
         c.mm1(c.S(sLw), R, R, NoEpi());
         c.swap(sT, sLw);
       }
     }
     const Mat R = c.S(sT);
-    // U_k and dU_k/du_j leave through the copy engine (TMA bulk store); all generic-proxy writes of the slots were
-    // ordered by the barrier that ended the last product, the proxy fence makes them visible to the async proxy
-    fence_async_smem();
-    c.cbar();
+    // U_k and dU_k/du_j leave through the copy engine (TMA bulk store); all generic-proxy writes of the slots were made
+    // visible to the async proxy (fence.proxy.async) before the barrier that ended the last product
     {
       const bool stL = p.want_jac && !taylor;
       if (c.tid == 0 && !(p.dbg_flags & 4)) bulk_store(p.U + slice * slot_d, R.re, slot_bytes);
@@ -1060,12 +1102,23 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
       slot_copy(p.Q + (size_t)seg * slot_d, c.S(sQ).re, c.n2, c.tid, C::NTHREADS);
       c.cbar();
     }
-    if (c.tid == 0) {
-      double G = 0.0;
-      const double pi_q = q_cur == 13 ? 6.0 : q_cur == 7 ? 4.0 : 3.0;   // products of the Pade approximant as executed
-      if (p.want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0)
-                                 : (2.0 * pi_q + 2.0 * sq_cur + 2.0);
-      my_flops += M * ((pi_q + sq_cur + 4.0 / 3.0) + nc * G);
+    {
+      // algorithmic product count of the slice in thirds of a d^3 complex product (integer: an FP64 accumulation on one
+      // thread sits behind the DMMAs of its sub-partition and made warp 0 late for the next barrier)
+      const int pi_q = q_cur == 13 ? 6 : q_cur == 7 ? 4 : 3;   // products of the Pade approximant as executed
+      int G = 0;
+      if (p.want_jac) G = taylor ? (p.order == 1 ? 0 : p.order == 2 ? 2 : p.order == 3 ? 5 : 10) : (2 * pi_q + 2 * sq_cur + 2);
+      my_thirds += 3 * (pi_q + sq_cur) + 4 + 3 * nc * G;
+      // executed: padded (8 NT)^2 x (4 KS) real tile products; a complex product is 3 of them (3M), one on the real-plane path
+      const int nj = p.want_jac ? nc : 0;
+      int ex;
+      if (REALH) ex = 6 + 12 * nj + 2 + 3 * (2 * nj + sq_cur * (1 + 2 * nj)) + (first_of_seg ? 0 : 3);
+      else {
+        const int padeP = q_cur == 13 ? 6 : q_cur == 7 ? 4 : 3;
+        const int jacP = taylor ? (p.order <= 1 ? 0 : p.order == 2 ? 2 : p.order == 3 ? 5 : 10) : 2 * padeP + 2 + 2 * sq_cur;
+        ex = 3 * (padeP + 1 + sq_cur + nj * jacP + (first_of_seg ? 0 : 1));
+      }
+      my_real += ex;
     }
     QOC_STAMP(5);
     dbg_i++;
@@ -1074,7 +1127,10 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
   }
   if (c.tid == 0) {
     bulk_wait_all();
-    if (my_flops != 0.0) atomicAdd(p.flops, my_flops);
+    if (my_thirds != 0) {
+      atomicAdd(p.flops, (8.0 * d * d * (double)d) * ((double)my_thirds / 3.0));
+      atomicAdd(p.flops + 1, 2.0 * (8 * C::NT) * (8 * C::NT) * (4 * C::KS) * (double)my_real);
+    }
   }
 }
 

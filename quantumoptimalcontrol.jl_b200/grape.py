@@ -260,6 +260,9 @@ class GrapeCache:
     def alg_flops(self):
         return _lib.load().qoc_last_alg_flops(self._h)
 
+    def exec_flops(self):
+        return _lib.load().qoc_last_exec_flops(self._h)
+
     def set_profiling(self, on=True):
         self._check(_lib.load().qoc_set_profiling(self._h, 1 if on else 0))
 

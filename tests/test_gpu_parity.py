@@ -492,3 +492,39 @@ def test_time_sharding_general_path_virtual_ranks():
         assert abs(float(J.cpu()[0]) - Jo) <= TOL_J
         g[:, lo:hi] = gl.cpu().numpy().T
     assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+
+
+@pytest.mark.parametrize("d,nc,m,scale,sym", [(27, 1, 1, 6.0, True), (27, 2, 3, 3.0, True), (28, 1, 2, 11.0, False),
+                                               (24, 2, 2, 2.5, True), (20, 3, 1, 4.0, False), (16, 2, 4, 9.0, True),
+                                               (12, 1, 2, 2.2, True), (9, 2, 4, 5.0, False), (5, 1, 1, 30.0, True)])
+def test_real_hamiltonian_fast_path_every_shape_class(d, nc, m, scale, sym, monkeypatch):
+    """Generators with an exactly zero real plane (X = -i H dt, H real: symmetric as in the tunable-bus model, and
+    non-symmetric, which the ABI does not forbid) above the low-degree switch take K1's real-plane instantiation.
+    Against the oracle, against the general complex instantiation (QOC_NO_REALH=1), and U_k / dU_k themselves."""
+    rng = np.random.default_rng(300 + d)
+    def realH():
+        H = rng.standard_normal((d, d))
+        return (H + H.T) / 2 if sym else H
+    H0 = realH(); H0 *= scale / np.abs(H0).sum(axis=0).max()
+    A = []
+    for _ in range(nc):
+        Hj = realH(); A.append(-1j * Hj / np.abs(Hj).sum(axis=0).max())
+    x0 = np.eye(d, m, dtype=complex)
+    Tq, _ = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+    cfg = dict(A0=-1j * H0, A=A, u=rng.uniform(-0.5, 0.5, (nc, 20)), x0=x0, T=Tq[:, :m].copy(), cost=o.COST_INFIDELITY, n=m)
+    Jo, go, co = o.evaluate(cfg, order=0)
+    J, g, cache = gpu_eval(cfg, 0)
+    assert_parity(J, g, Jo, go)
+    tolU = 1e-12 * max(1.0, np.abs(co["Uk"]).max())
+    assert np.abs(cache.Uk_vec - co["Uk"]).max() < tolU
+    dU = np.array(cache.dUkdu)
+    monkeypatch.setenv("QOC_NO_REALH", "1")
+    J2, g2, cache2 = gpu_eval(cfg, 0)
+    assert_parity(J, g, J2, g2)   # (non-symmetric H: the state norm grows and |J| is huge -- relative, as in assert_parity)
+    assert np.abs(cache.Uk_vec - cache2.Uk_vec).max() < tolU
+    assert np.abs(dU - np.array(cache2.dUkdu)).max() < 1e-11 * max(1.0, np.abs(dU).max())
+    # propagate-only (expm without Jacobians) goes through the same instantiation
+    monkeypatch.delenv("QOC_NO_REALH")
+    cache3 = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=0)
+    q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cache3)
+    assert np.abs(cache3.x - co["x"]).max() < 1e-12 * max(1.0, np.abs(co["x"]).max())
