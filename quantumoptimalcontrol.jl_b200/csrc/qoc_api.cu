@@ -54,6 +54,7 @@ struct qoc_handle {
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
   bool gs2 = false;
+  bool k1_sym = false;        // ... with symmetric H0, H_j: Pade denominator inverted through the real SPD matrix N N^dagger
   bool k1_realh = false;      // K1 real-Hamiltonian fast path (Re A0 = Re A_j = 0, Frechet mode, [13/13] instantiation)
   bool k1_low = true;         // K1 instantiation with the low-degree Pade forms (false when ||A0||_1 alone is far above theta7)           // second-generation general-path sweeps (no running penalty)
   double normA0 = 0.0, normA[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -414,6 +415,18 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
       for (size_t e = 0; e < (size_t)p.nc * p.d * p.d && re0; e++) re0 = (A[2 * e] == 0.0);
       const char* off = getenv("QOC_NO_REALH");
       h->k1_realh = re0 && !h->k1_low && p.order == QOC_ORDER_FRECHET && !(off && off[0] == '1');
+      // ... and all of them symmetric (H real symmetric, X_k skew-Hermitian): the Pade denominator is inverted through the
+      // real SPD matrix N N^dagger.  QOC_NO_REALH=2 keeps the real-plane path but switches this off.
+      bool sy = h->k1_realh && !(off && off[0] == '2');
+      for (int r = 0; r < p.d && sy; r++)
+        for (int cc = 0; cc < r && sy; cc++) {
+          sy = (A0[2 * (r + (size_t)p.d * cc) + 1] == A0[2 * (cc + (size_t)p.d * r) + 1]);
+          for (int j = 0; j < p.nc && sy; j++) {
+            const double* Aj = A + (size_t)j * 2 * p.d * p.d;
+            sy = (Aj[2 * (r + (size_t)p.d * cc) + 1] == Aj[2 * (cc + (size_t)p.d * r) + 1]);
+          }
+        }
+      h->k1_sym = sy;
     }
   }
   if (h->gpath) {
@@ -758,7 +771,7 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   const qoc_problem& p = h->prob;
   K1Params k;
   k.d = p.d; k.nc = p.nc; k.nt = p.nt; k.batch = p.batch; k.order = p.order;
-  k.nseg = h->nseg; k.seg_per_pulse = h->spp; k.want_jac = want_jac ? 1 : 0;
+  k.nseg = h->nseg; k.seg_per_pulse = h->spp; k.want_jac = want_jac ? 1 : 0; k.sym = h->k1_sym ? 1 : 0;
   k.A0p = h->dA0p; k.Ap = h->dAp; k.u = d_u; k.U = h->dU; k.L = h->dL; k.Q = h->dQ;
   k.flops = h->dflops; k.status = h->dstatus;
   k.theta13 = (p.order == QOC_ORDER_FRECHET) ? 4.74 : 5.4;

@@ -28,6 +28,7 @@ struct K1Params {
   int d, nc, nt, batch, order;
   int nseg, seg_per_pulse;
   int want_jac;            // 0: expm only (propagate without gradient)
+  int sym;                 // real-Hamiltonian path only: H0 and every H_j symmetric (X_k skew-Hermitian): N^-1 = N^dagger (N N^dagger)^-1
   const double* A0p;       // planar slot
   const double* Ap;        // nc planar slots
   const double* u;         // nc x nt x batch
@@ -500,6 +501,89 @@ __device__ __noinline__ bool service_inverse(Mat N, int d, SvcScratch* sc, int s
   return ok;
 }
 
+
+// ---- real variant (real-symmetric-Hamiltonian path: the matrix to invert is M = N N^dagger = V^2 + u^2, real SPD) ----
+__device__ __forceinline__ void svc_publish_real(SvcScratch* sc, int par, double cv, bool used, int lane) {
+  const unsigned key = used ? 0u : ((((unsigned)__double2hiint(cv) & 0x7fffffffu) & ~31u) | (unsigned)(31 - lane));
+  const unsigned best = __reduce_max_sync(0xffffffffu, key);
+  const int p = 31 - (int)(best & 31u);
+  const bool okp = (best >> 5) != 0u;
+  const double inv = copysign(fast_rcp(fabs(cv)), cv);
+  const double pr = __shfl_sync(0xffffffffu, inv, p);
+  sc->gbuf[par][lane] = make_double2(cv * pr, 0.0);
+  if (lane == 0) { sc->pinv[par] = make_double2(pr, 0.0); sc->pidx[par] = okp ? p : -1 - p; }
+}
+
+// same hand-over / look-ahead scheme as service_inverse, one real plane (row stride S), a quarter of the FP64 work
+template <class C>
+__device__ __noinline__ bool service_inverse_real(double* N, int d, SvcScratch* sc, int sw, int lane) {
+  constexpr int S = C::S;
+  constexpr int DM = C::DMAX;
+  constexpr int CL = DM / NSW;
+  double w[CL];
+#pragma unroll
+  for (int c = 0; c < CL; c++) {
+    const int col = NSW * c + sw;
+    const bool v = (lane < d) && (col < d);
+    w[c] = v ? N[lane * S + col] : ((lane == col && lane >= d) ? 1.0 : 0.0);
+  }
+  bool used = lane >= DM;
+  int mycol = -1;
+  bool ok = true;
+  if (sw == 0) {
+    svc_publish_real(sc, 0, w[0], used, lane);
+    bar_arrive_i<BAR_SVC>(NSW * 32);
+  }
+#pragma unroll 1
+  for (int kk = 0; kk < CL; kk++) {
+#pragma unroll
+    for (int o = 0; o < NSW; o++) {
+      const int sp = o & 1;
+      const bool owner = (sw == o);
+      if (owner) __syncwarp();
+      else if (sp) bar_sync_i<BAR_SVC + 1>(NSW * 32);
+      else bar_sync_i<BAR_SVC>(NSW * 32);
+      int p = sc->pidx[sp];
+      if (p < 0) { ok = false; p = -1 - p; }
+      const bool isp = (lane == p);
+      const double pinv = sc->pinv[sp].x;
+      double g = sc->gbuf[sp][lane].x;
+      if (isp) { used = true; mycol = NSW * kk + o; g = -pinv; }
+      if (owner) {
+#pragma unroll
+        for (int c = 1; c < CL; c++) {
+          const double rr = __shfl_sync(0xffffffffu, w[c], p);
+          w[c - 1] = fma(-g, rr, isp ? 0.0 : w[c]);
+        }
+        w[CL - 1] = isp ? pinv : -g;
+      } else {
+        const bool next_owner = (sw == ((o + 1) & (NSW - 1))) && (NSW * kk + o + 1 < DM);
+        {
+          const double rr = __shfl_sync(0xffffffffu, w[0], p);
+          w[0] = fma(-g, rr, isp ? 0.0 : w[0]);
+        }
+        if (next_owner) {
+          svc_publish_real(sc, sp ^ 1, w[0], used, lane);
+          if (sp) bar_arrive_i<BAR_SVC>(NSW * 32); else bar_arrive_i<BAR_SVC + 1>(NSW * 32);
+        }
+#pragma unroll
+        for (int c = 1; c < CL; c++) {
+          const double rr = __shfl_sync(0xffffffffu, w[c], p);
+          w[c] = fma(-g, rr, isp ? 0.0 : w[c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CL; c++) {
+    const int j = NSW * c + sw;
+    const unsigned bal = __ballot_sync(0xffffffffu, mycol == j);
+    const int pj = __ffs(bal) - 1;
+    if (j < d && mycol >= 0 && mycol < d && pj >= 0 && pj < d) N[mycol * S + pj] = w[c];
+  }
+  return ok;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // compute warps
 // ---------------------------------------------------------------------------------------------------------------------
@@ -722,8 +806,12 @@ __device__ __forceinline__ void frechet13_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat
 // the lincomb phases and lets the W/V and Lw/Lv pairs share a phase and their left fragments.  Only N^-1 and the tail
 // (R, rhs, L, squarings, segment product) are general complex.  Notation: A = i a, E = i e, U = i u, Lu = i lu.
 // ---------------------------------------------------------------------------------------------------------------------
+// sym (H real symmetric): V and u are symmetric and commute, N N^dagger = (V - iu)(V + iu) = V^2 + u^2 =: M is real SPD with
+// cond(M) = cond(N)^2 ~ 1 (|q13(i lambda)| is nearly constant on the scaled spectrum), so the service warps invert the
+// REAL matrix M (a quarter of the FP64 instructions, which have to squeeze between the compute warps' DMMAs) and the
+// tail forms N^-1 = (V + iu) M^-1 with two real products.  N.re keeps V, N.im carries M / M^-1.
 template <class C>
-__device__ __forceinline__ void pade13_build_N_realh(K1Ctx<C>& c, Mat U, Mat N) {
+__device__ __forceinline__ void pade13_build_N_realh(K1Ctx<C>& c, Mat U, Mat N, bool sym) {
   typedef K1Ctx<C> X;
   const double* b = c_b13;
   const Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), A6 = c.S(sA6), WZ = c.S(sWZ), W = c.S(sW);
@@ -761,7 +849,28 @@ __device__ __forceinline__ void pade13_build_N_realh(K1Ctx<C>& c, Mat U, Mat N) 
   c.racc(acc, A.im, W.re);                       // u = a W ; N = V - U  ->  N.im = -u
   c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) {
     X::rst(U.im, o, v0, v1, last);
-    X::rst(N.im, o, -v0, -v1, last);
+    if (!sym) X::rst(N.im, o, -v0, -v1, last);
+  });
+  c.cbar();
+  if (sym) {
+    X::rzero(acc);
+    c.racc(acc, N.re, N.re);                     // M = V V + u u
+    c.racc(acc, U.im, U.im);
+    c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) { X::rst(N.im, o, v0, v1, last); });
+    c.cbar();
+  }
+}
+
+// sym tail: N^-1 = (V + iu) M^-1  (V in N.re, M^-1 in N.im, u in U.im) -> Ninv
+template <class C>
+__device__ __forceinline__ void tail_Ninv_realh_sym(K1Ctx<C>& c, Mat Ninv, Mat N, Mat U) {
+  typedef K1Ctx<C> X;
+  double acc[C::BN][2], acc2[C::BN][2];
+  X::rzero(acc); X::rzero(acc2);
+  c.racc_a2b(acc, acc2, N.re, U.im, N.im);
+  c.rstore2(acc, acc2, [&](int o, int, int, double r0, double r1, double i0, double i1, bool last) {
+    X::rst(Ninv.re, o, r0, r1, last);
+    X::rst(Ninv.im, o, i0, i1, last);
   });
   c.cbar();
 }
@@ -938,7 +1047,10 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
       QOC_STAMP(8);
       bar_sync_p<BAR_NREADY>(par, NALL);         // compute warps have formed N = V - U of this slice
       QOC_STAMP(9);
-      if (!(p.dbg_flags & 1)) all_ok &= service_inverse<C>(c.fixed(sN0 + par), d, sc, sw, lane);
+      if (!(p.dbg_flags & 1)) {
+        if (REALH && p.sym) all_ok &= service_inverse_real<C>(c.fixed(sN0 + par).im, d, sc, sw, lane);
+        else all_ok &= service_inverse<C>(c.fixed(sN0 + par), d, sc, sw, lane);
+      }
       QOC_STAMP(10);
       bar_arrive_p<BAR_NINV>(par, NALL);         // N^-1 is in place
       dbg_i++;
@@ -976,7 +1088,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
     load_u(it);
     sq = build_generator<C, LOW, REALH>(p, c, a0r, a0i, uj, need_x, sc);
     if (LOW) { qd = sq >> 8; sq &= 255; }
-    if (REALH) pade13_build_N_realh<C>(c, c.fixed(sU0), c.fixed(sN0));
+    if (REALH) pade13_build_N_realh<C>(c, c.fixed(sU0), c.fixed(sN0), p.sym != 0);
     else if (!LOW || qd == 13) pade13_build_N<C>(c, c.fixed(sU0), c.fixed(sN0));
     else pade_low_build_N<C>(c, c.fixed(sU0), c.fixed(sN0), qd);
     bar_arrive_i<BAR_NREADY>(NALL);
@@ -1024,7 +1136,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
     if (nx.valid()) {
       sq = build_generator<C, LOW, REALH>(p, c, a0r, a0i, uj, need_x, sc);
       if (LOW) { qd = sq >> 8; sq &= 255; }
-      if (REALH) pade13_build_N_realh<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
+      if (REALH) pade13_build_N_realh<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)), p.sym != 0);
       else if (!LOW || qd == 13) pade13_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)));
       else pade_low_build_N<C>(c, c.fixed(sU0 + (par ^ 1)), c.fixed(sN0 + (par ^ 1)), qd);
       bar_arrive_p<BAR_NREADY>(par ^ 1, NALL);
@@ -1034,7 +1146,12 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
     // ---- tail(k) ----
     bar_sync_p<BAR_NINV>(par, NALL);
     QOC_STAMP(3);
-    const Mat Ninv = c.fixed(sN0 + par), U = c.fixed(sU0 + par);
+    Mat Ninv = c.fixed(sN0 + par);
+    const Mat U = c.fixed(sU0 + par);
+    if (REALH && p.sym) {   // N^-1 = (V + iu) M^-1 into the (free until the squarings) Lw slot
+      tail_Ninv_realh_sym<C>(c, c.S(sLw), Ninv, U);
+      Ninv = c.S(sLw);
+    }
     // R = N^-1 (V + U) = N^-1 (N + 2U) = I + 2 N^-1 U   (R lives in role sT; results ping-pong by swapping roles)
     if (REALH) tail_R_realh<C>(c, c.S(sT), Ninv, U);
     else c.mm1(c.S(sT), Ninv, U, c.epi(2.0, 0.0, U, 0.0, U, 0.0, U, 1.0));
@@ -1112,7 +1229,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
       // executed: padded (8 NT)^2 x (4 KS) real tile products; a complex product is 3 of them (3M), one on the real-plane path
       const int nj = p.want_jac ? nc : 0;
       int ex;
-      if (REALH) ex = 6 + 12 * nj + 2 + 3 * (2 * nj + sq_cur * (1 + 2 * nj)) + (first_of_seg ? 0 : 3);
+      if (REALH) ex = 6 + (p.sym ? 4 : 0) + 12 * nj + 2 + 3 * (2 * nj + sq_cur * (1 + 2 * nj)) + (first_of_seg ? 0 : 3);
       else {
         const int padeP = q_cur == 13 ? 6 : q_cur == 7 ? 4 : 3;
         const int jacP = taylor ? (p.order <= 1 ? 0 : p.order == 2 ? 2 : p.order == 3 ? 5 : 10) : 2 * padeP + 2 + 2 * sq_cur;

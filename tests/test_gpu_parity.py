@@ -523,6 +523,12 @@ def test_real_hamiltonian_fast_path_every_shape_class(d, nc, m, scale, sym, monk
     assert_parity(J, g, J2, g2)   # (non-symmetric H: the state norm grows and |J| is huge -- relative, as in assert_parity)
     assert np.abs(cache.Uk_vec - cache2.Uk_vec).max() < tolU
     assert np.abs(dU - np.array(cache2.dUkdu)).max() < 1e-11 * max(1.0, np.abs(dU).max())
+    if sym:   # the symmetric case inverts N through the real SPD matrix N N^dagger; "2" keeps the complex in-kernel inverse
+        monkeypatch.setenv("QOC_NO_REALH", "2")
+        J4, g4, cache4 = gpu_eval(cfg, 0)
+        assert_parity(J4, g4, Jo, go)
+        assert np.abs(cache4.Uk_vec - co["Uk"]).max() < tolU
+        assert np.abs(dU - np.array(cache4.dUkdu)).max() < 1e-11 * max(1.0, np.abs(dU).max())
     # propagate-only (expm without Jacobians) goes through the same instantiation
     monkeypatch.delenv("QOC_NO_REALH")
     cache3 = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=0)
