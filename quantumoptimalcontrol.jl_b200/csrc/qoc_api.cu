@@ -9,6 +9,7 @@
 
 #include "../../include/qoc_b200.h"
 #include "qoc_k1.cuh"
+#include "qoc_k1s.cuh"
 #include "qoc_k23.cuh"
 #include "qoc_sweep.cuh"
 #include "qoc_gpath.cuh"
@@ -54,6 +55,7 @@ struct qoc_handle {
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
   bool gs2 = false;
+  bool k1s_ok = false;        // d <= 9, nc <= 4: the warp-per-slice small-dimension kernel serves the exact-Frechet / expm-only mode
   bool k1_sym = false;        // ... with symmetric H0, H_j: Pade denominator inverted through the real SPD matrix N N^dagger
   bool k1_realh = false;      // K1 real-Hamiltonian fast path (Re A0 = Re A_j = 0, Frechet mode, [13/13] instantiation)
   bool k1_low = true;         // K1 instantiation with the low-degree Pade forms (false when ||A0||_1 alone is far above theta7)           // second-generation general-path sweeps (no running penalty)
@@ -311,13 +313,33 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
     QOC_CUDA(h, cudaFuncSetAttribute(k1_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem));
     QOC_CUDA(h, cudaFuncSetAttribute(k2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k2_smem));
+    {
+      const char* off = getenv("QOC_NO_K1S");
+      h->k1s_ok = p.d <= K1S_DMAX && p.nc <= K1S_MAXNC && C::S == 12 && !(off && off[0] == '1') &&
+                  k1s_smem_bytes(p.nc) <= (size_t)dp.sharedMemPerBlockOptin;
+      if (h->k1s_ok)
+        QOC_CUDA(h, cudaFuncSetAttribute(k1s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1s_smem_bytes(p.nc)));
+    }
     int occ = 1;
     QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C, true>, C::NTHREADS + NSW * 32, h->k1_smem));
     if (occ < 1) occ = 1;
-    const long long target = (long long)h->nsm * occ;
+    long long target = (long long)h->nsm * occ;
+    if (h->k1s_ok && p.order == QOC_ORDER_FRECHET && target < (long long)h->nsm * K1S_WPB) target = (long long)h->nsm * K1S_WPB;
     long long spp = (target + p.batch - 1) / p.batch;
     if (spp < 1) spp = 1;
     if (spp > p.nt) spp = p.nt;
+    if (h->k1s_ok && p.order == QOC_ORDER_FRECHET && p.batch > 1) {
+      // K1S workers (warps) take whole segments: pick the segment count that wastes least of the last wave
+      // (4096 pulses on 1184 workers: 1 segment per pulse fills 3.46 waves, 2 fill 6.92)
+      const long long W = (long long)h->nsm * K1S_WPB;
+      double best = 1e30; long long bs = spp;
+      for (long long s2 = spp; s2 < spp + 6 && s2 <= p.nt; s2++) {
+        const long long ns = s2 * p.batch, waves = (ns + W - 1) / W;
+        const double waste = (double)(waves * W) / (double)ns + 0.01 * (double)(s2 - spp);
+        if (waste < best - 1e-9) { best = waste; bs = s2; }
+      }
+      spp = bs;
+    }
     // K3 keeps the forward states of a segment in shared memory: cap the segment length
     const int ngrp = p.nc < 2 ? p.nc : 2;
     h->k3_threads = C::NT * 32 * (1 + ngrp);
@@ -785,7 +807,11 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
     // NW compute warps + 4 service warps
-    if (h->k1_realh) k1_kernel<C, false, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
+    if (h->k1s_ok && p.order == QOC_ORDER_FRECHET) {
+      // small-dimension form: one warp per segment, no CTA barriers (qoc_k1s.cuh)
+      const int ctas = (h->nseg + K1S_WPB - 1) / K1S_WPB;
+      k1s_kernel<<<ctas < h->nsm ? ctas : h->nsm, K1S_WPB * 32, k1s_smem_bytes(p.nc), st>>>(k, h->S);
+    } else if (h->k1_realh) k1_kernel<C, false, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
     else if (h->k1_low) k1_kernel<C, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
     else k1_kernel<C, false><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
     return 0;
