@@ -430,13 +430,13 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     // a performance heuristic only: the [13/13]-only instantiation is always correct
     h->k1_low = h->normA0 <= 2.0;
     // real-Hamiltonian fast path of K1: every generator plane Re(A0), Re(A_j) exactly zero (X = -i H dt with a real H),
-    // exact-Frechet / expm-only mode, [13/13] instantiation.  QOC_NO_REALH=1 switches it off (A/B measurements).
+    // [13/13] instantiation, every gradient mode.  QOC_NO_REALH=1 switches it off (A/B measurements).
     {
       bool re0 = true;
       for (size_t e = 0; e < (size_t)p.d * p.d && re0; e++) re0 = (A0[2 * e] == 0.0);
       for (size_t e = 0; e < (size_t)p.nc * p.d * p.d && re0; e++) re0 = (A[2 * e] == 0.0);
       const char* off = getenv("QOC_NO_REALH");
-      h->k1_realh = re0 && !h->k1_low && p.order == QOC_ORDER_FRECHET && !(off && off[0] == '1');
+      h->k1_realh = re0 && !h->k1_low && !(off && off[0] == '1');   // every gradient mode (exact Frechet, Taylor 1..4, expm only)
       // ... and all of them symmetric (H real symmetric, X_k skew-Hermitian): the Pade denominator is inverted through the
       // real SPD matrix N N^dagger.  QOC_NO_REALH=2 keeps the real-plane path but switches this off.
       bool sy = h->k1_realh && !(off && off[0] == '2');

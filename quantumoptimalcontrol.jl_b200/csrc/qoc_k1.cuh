@@ -980,10 +980,57 @@ __device__ __forceinline__ void taylor_jacobian(K1Ctx<C>& c, Mat Aj, Mat out, in
   c.mm4(out, AjX, X2, XAj, X2, X2, AjX, X2, XAj, c.epi(1.0 / 24.0, 1.0, c.S(sLw), 0.0, Aj, 0.0, Aj, 0.0));
 }
 
+
+// The reference's truncated Taylor series on the real-Hamiltonian path: X = i x, A_j = i e, so A_j X = -e x, X A_j = -x e and
+// X^2 = -x x are real, the third-order terms are imaginary and the fourth-order terms real: 2 / 5 / 9 real products
+// in two phases instead of 2 / 5 / 10 complex ones.  Same association order as src/gradient_computations.jl:194-211.
+template <class C>
+__device__ __forceinline__ void taylor_jacobian_realh(K1Ctx<C>& c, Mat Aj, Mat out, int order) {
+  typedef K1Ctx<C> X;
+  if (order <= 1) {
+    slot_copy(out.re, Aj.re, c.n2, c.tid, C::NTHREADS);
+    c.cbar();
+    return;
+  }
+  const Mat Xm = c.S(sX), AjX = c.S(sM2), XAj = c.S(sM4), X2 = c.S(sM6);
+  double acc[C::BN][2], acc2[C::BN][2];
+  X::rzero(acc);
+  c.racc(acc, Aj.im, Xm.im);
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) { X::rst(AjX.re, o, -v0, -v1, last); });
+  X::rzero(acc);
+  c.racc(acc, Xm.im, Aj.im);
+  c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) { X::rst(XAj.re, o, -v0, -v1, last); });
+  if (order >= 4) {
+    X::rzero(acc);
+    c.racc(acc, Xm.im, Xm.im);
+    c.rstore(acc, [&](int o, int, int, double v0, double v1, bool last) { X::rst(X2.re, o, -v0, -v1, last); });
+  }
+  c.cbar();
+  // out.re = (A_j X + X A_j) / 2 [+ (A_j X X^2 + X A_j X^2 + X^2 A_j X + X^2 X A_j) / 24] ; out.im = e [+ (A_j X x + X A_j x + x X A_j) / 6]
+  X::rzero(acc); X::rzero(acc2);
+  if (order >= 3) {
+    c.racc(acc, AjX.re, Xm.im);
+    c.racc(acc, XAj.re, Xm.im);
+    c.racc(acc, Xm.im, XAj.re);
+  }
+  if (order >= 4) {
+    c.racc(acc2, AjX.re, X2.re);
+    c.racc(acc2, XAj.re, X2.re);
+    c.racc(acc2, X2.re, AjX.re);
+    c.racc(acc2, X2.re, XAj.re);
+  }
+  c.rstore2(acc, acc2, [&](int o, int, int, double t0, double t1, double q0, double q1, bool last) {
+    const double2 ax = X::rld(AjX.re, o), xa = X::rld(XAj.re, o), e = X::rld(Aj.im, o);
+    X::rst(out.re, o, fma(1.0 / 24.0, q0, 0.5 * (ax.x + xa.x)), fma(1.0 / 24.0, q1, 0.5 * (ax.y + xa.y)), last);
+    X::rst(out.im, o, fma(1.0 / 6.0, t0, e.x), fma(1.0 / 6.0, t1, e.y), last);
+  });
+  c.cbar();
+}
+
 // LOW: the [5/5] / [7/7] forms are compiled in.  The host instantiates LOW = false when the drift alone puts every slice far
 // above theta7 (the bus config): the extra code paths cost the [13/13]-only path 3 % (measured) even when never taken.
-// REALH: real-Hamiltonian fast path (exact Frechet or expm-only mode, [13/13] form only; the host selects it when the real
-// planes of A0 and of every A_j are exactly zero).
+// REALH: real-Hamiltonian fast path ([13/13] form only, every gradient mode; the host selects it when the real planes of A0
+// and of every A_j are exactly zero).
 template <class C, bool LOW, bool REALH = false>
 __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1Params p) {
   static_assert(!(LOW && REALH), "the real-Hamiltonian path is built for the [13/13] form only");
@@ -1116,7 +1163,8 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
         for (int j = 0; j < nc; j++) {
           if (c.tid == 0) bulk_wait_read();   // the previous bulk store out of sT has been read
           c.cbar();
-          taylor_jacobian<C>(c, c.E(j), c.S(sT), p.order);
+          if (REALH) taylor_jacobian_realh<C>(c, c.E(j), c.S(sT), p.order);
+          else taylor_jacobian<C>(c, c.E(j), c.S(sT), p.order);
           fence_async_smem();
           c.cbar();
           const Mat Tj = c.S(sT);
@@ -1229,7 +1277,8 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
       // executed: padded (8 NT)^2 x (4 KS) real tile products; a complex product is 3 of them (3M), one on the real-plane path
       const int nj = p.want_jac ? nc : 0;
       int ex;
-      if (REALH) ex = 6 + (p.sym ? 4 : 0) + 12 * nj + 2 + 3 * (2 * nj + sq_cur * (1 + 2 * nj)) + (first_of_seg ? 0 : 3);
+      if (REALH && taylor) ex = 6 + (p.sym ? 4 : 0) + 2 + nj * (p.order <= 1 ? 0 : p.order == 2 ? 2 : p.order == 3 ? 5 : 10) + 3 * sq_cur + (first_of_seg ? 0 : 3);
+      else if (REALH) ex = 6 + (p.sym ? 4 : 0) + 12 * nj + 2 + 3 * (2 * nj + sq_cur * (1 + 2 * nj)) + (first_of_seg ? 0 : 3);
       else {
         const int padeP = q_cur == 13 ? 6 : q_cur == 7 ? 4 : 3;
         const int jacP = taylor ? (p.order <= 1 ? 0 : p.order == 2 ? 2 : p.order == 3 ? 5 : 10) : 2 * padeP + 2 + 2 * sq_cur;

@@ -534,3 +534,30 @@ def test_real_hamiltonian_fast_path_every_shape_class(d, nc, m, scale, sym, monk
     cache3 = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=0)
     q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cache3)
     assert np.abs(cache3.x - co["x"]).max() < 1e-12 * max(1.0, np.abs(co["x"]).max())
+
+
+@pytest.mark.parametrize("d,nc,m,scale", [(27, 1, 1, 6.0), (20, 2, 3, 3.0), (12, 1, 2, 9.0), (9, 2, 4, 5.0)])
+def test_real_hamiltonian_fast_path_taylor_orders(d, nc, m, scale, monkeypatch):
+    """The reference's truncated Taylor Jacobian (orders 1..4) on the real-plane instantiation: against the oracle's same-order
+    formula and against the general complex instantiation."""
+    rng = np.random.default_rng(900 + d)
+    def symH():
+        H = rng.standard_normal((d, d))
+        return (H + H.T) / 2
+    H0 = symH(); H0 *= scale / np.abs(H0).sum(axis=0).max()
+    A = []
+    for _ in range(nc):
+        Hj = symH(); A.append(-1j * Hj / np.abs(Hj).sum(axis=0).max())
+    Tq, _ = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+    cfg = dict(A0=-1j * H0, A=A, u=rng.uniform(-0.5, 0.5, (nc, 16)), x0=np.eye(d, m, dtype=complex), T=Tq[:, :m].copy(),
+               cost=o.COST_INFIDELITY, n=m)
+    for order in (1, 2, 3, 4):
+        Jo, go, co = o.evaluate(cfg, order=order)
+        J, g, cache = gpu_eval(cfg, order)
+        assert_parity(J, g, Jo, go)
+        dU = np.array(cache.dUkdu)
+        monkeypatch.setenv("QOC_NO_REALH", "1")
+        J2, g2, cache2 = gpu_eval(cfg, order)
+        monkeypatch.delenv("QOC_NO_REALH")
+        assert_parity(J, g, J2, g2)
+        assert np.abs(dU - np.array(cache2.dUkdu)).max() < 1e-11 * max(1.0, np.abs(dU).max())
