@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
 // 168 registers, one CTA per SM) are 10-50 % SLOWER than 32 x 32 (80 registers, three CTAs per SM) because the operand
 // staging is synchronous and only co-resident CTAs hide it; 64 x 32 at two CTAs per SM is a wash.  Larger tiles need an
 // asynchronous (cp.async / TMA) double buffer first -- DESIGN.md section 7.
+// (A register double buffer -- global loads of chunk i+1 issued behind the hand-over of chunk i -- was measured too: 5-8 % SLOWER
+// at every tile shape, 90 instead of 80 registers; the kernel is not bound by the exposed load latency.)
 static inline void g_gemm_launch(const GGemm& g, int nb, cudaStream_t st) {
   constexpr int WM = 1, WN = 2;
   const size_t smem = (size_t)(2 * 32 * WM * 36 + 2 * 32 * (16 * WN + 4)) * 8;

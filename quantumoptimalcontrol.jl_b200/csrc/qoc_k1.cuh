@@ -275,6 +275,21 @@ struct K1Ctx {
     *reinterpret_cast<double2*>(plane + o) = make_double2(v0, last ? 0.0 : v1);
   }
   static __device__ __forceinline__ double2 rld(const double* plane, int o) { return *reinterpret_cast<const double2*>(plane + o); }
+  // L = P + P^T on this warp's tiles (complex-symmetric squaring step of the real-symmetric-Hamiltonian path)
+  __device__ __forceinline__ void sym_add(Mat L, Mat P) const {
+    const int row = mi * 8 + (lane >> 2);
+#pragma unroll
+    for (int n = 0; n < C::BN; n++) {
+      const int col = (nj0 + n) * 8 + 2 * (lane & 3);
+      if (row < d && col < d) {
+        const int o = row * C::S + col, ot = col * C::S + row;
+        const bool last = col + 1 >= d;
+        const double2 pr = rld(P.re, o), pi = rld(P.im, o);
+        rst(L.re, o, pr.x + P.re[ot], pr.y + P.re[ot + C::S], last);
+        rst(L.im, o, pi.x + P.im[ot], pi.y + P.im[ot + C::S], last);
+      }
+    }
+  }
   static __device__ __forceinline__ void rzero(double (&acc)[C::BN][2]) {
 #pragma unroll
     for (int n = 0; n < C::BN; n++) acc[n][0] = acc[n][1] = 0.0;
@@ -1216,6 +1231,29 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
       // squaring phase: L <- R L + L R ; R <- R R   (results land in scratch roles sM6 / sLw, then the roles swap).
       // The last control's L product and the R product share one barrier interval (independent outputs).
       if (sq_cur == 0) { fence_async_smem(); c.cbar(); }   // (L_j were written by the phases above)
+      // Real symmetric H: R and every L_j are complex SYMMETRIC (exp(-i(H0 + u H1)) is, for every u), so L R = (R L)^T and
+      // L <- P + P^T with ONE product P = R L; the transposed add of control j rides in the next product phase.
+      if (REALH && p.sym) {
+        for (int t = 0; t < sq_cur; t++) {
+          const Mat R = c.S(sT);
+          for (int j = 0; j < nc; j++) {
+            Acc<C::BN> acc; acc.zero();
+            mm_acc<C, false>(acc, R, c.S(k1_role_D(j)), c.mi, c.nj0, c.lane);
+            mm_store<C>(c.S((j & 1) ? sM4 : sM6), acc, c.d, c.mi, c.nj0, c.lane, NoEpi());
+            if (j > 0) c.sym_add(c.S(k1_role_D(j - 1)), c.S(((j - 1) & 1) ? sM4 : sM6));
+            c.cbar();
+          }
+          {
+            Acc<C::BN> acc; acc.zero();
+            mm_acc<C, false>(acc, R, R, c.mi, c.nj0, c.lane);
+            mm_store<C>(c.S(sLw), acc, c.d, c.mi, c.nj0, c.lane, NoEpi());
+            c.sym_add(c.S(k1_role_D(nc - 1)), c.S(((nc - 1) & 1) ? sM4 : sM6));
+            c.fence_next = (t + 1 == sq_cur);
+            c.cbar();
+          }
+          c.swap(sT, sLw);
+        }
+      } else
       for (int t = 0; t < sq_cur; t++) {
         const Mat R = c.S(sT);
         for (int j = 0; j < nc; j++) {
@@ -1278,7 +1316,7 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
       const int nj = p.want_jac ? nc : 0;
       int ex;
       if (REALH && taylor) ex = 6 + (p.sym ? 4 : 0) + 2 + nj * (p.order <= 1 ? 0 : p.order == 2 ? 2 : p.order == 3 ? 5 : 10) + 3 * sq_cur + (first_of_seg ? 0 : 3);
-      else if (REALH) ex = 6 + (p.sym ? 4 : 0) + 12 * nj + 2 + 3 * (2 * nj + sq_cur * (1 + 2 * nj)) + (first_of_seg ? 0 : 3);
+      else if (REALH) ex = 6 + (p.sym ? 4 : 0) + 12 * nj + 2 + 3 * (2 * nj + sq_cur * (1 + (p.sym ? 1 : 2) * nj)) + (first_of_seg ? 0 : 3);
       else {
         const int padeP = q_cur == 13 ? 6 : q_cur == 7 ? 4 : 3;
         const int jacP = taylor ? (p.order <= 1 ? 0 : p.order == 2 ? 2 : p.order == 3 ? 5 : 10) : 2 * padeP + 2 + 2 * sq_cur;
