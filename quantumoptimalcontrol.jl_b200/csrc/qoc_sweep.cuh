@@ -548,7 +548,9 @@ __global__ void __launch_bounds__(256) shard_boundary_kernel(ShardBoundary q) {
 constexpr int K3N_CW = 7;  // contraction warps
 
 template <class C>
-__global__ void __launch_bounds__((C::NT + 1 + K3N_CW) * 32, 1) k3n_kernel(K23Params p, int seg_cap) {
+// (small shape classes: 2 CTAs per SM -- the per-segment recurrence is a latency chain, co-resident segments are what
+// keeps the SM busy; d = 9 batch: 2.72 ms at one CTA per SM, 2.09 ms at two (96 registers), 2.55 ms at three (64 registers, spills))
+__global__ void __launch_bounds__((C::NT + 1 + K3N_CW) * 32, (C::NT <= 2) ? 2 : 1) k3n_kernel(K23Params p, int seg_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int S = C::S;
   constexpr int NT = C::NT;
