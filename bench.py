@@ -62,11 +62,11 @@ def fp64_peak_tflops():
 
 def ncu_traffic_bytes(kernel_prefix, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed `ncu --set full`
-    capture (profiles/r01e_ncu_full_summary.json; captured on the bus workload only)."""
+    capture (profiles/r01f_ncu_full_summary.json; captured on the bus workload only)."""
     if workload != "bus":
         return None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01e_ncu_full_summary.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01f_ncu_full_summary.json")))
         for k in prof["kernels"]:
             if kernel_prefix in k["name"]:
                 return k["traffic_bytes_per_launch"]
