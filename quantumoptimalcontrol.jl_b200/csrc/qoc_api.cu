@@ -55,7 +55,7 @@ struct qoc_handle {
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
   bool gs2 = false;
-  bool k1s_ok = false;        // d <= 9, nc <= 4: the warp-per-slice small-dimension kernel serves the exact-Frechet / expm-only mode
+  bool k1s_ok = false;        // d <= 9, nc <= 4: the warp-per-slice small-dimension kernel
   bool k1_sym = false;        // ... with symmetric H0, H_j: Pade denominator inverted through the real SPD matrix N N^dagger
   bool k1_realh = false;      // K1 real-Hamiltonian fast path (Re A0 = Re A_j = 0, Frechet mode, [13/13] instantiation)
   bool k1_low = true;         // K1 instantiation with the low-degree Pade forms (false when ||A0||_1 alone is far above theta7)           // second-generation general-path sweeps (no running penalty)
@@ -324,11 +324,11 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C, true>, C::NTHREADS + NSW * 32, h->k1_smem));
     if (occ < 1) occ = 1;
     long long target = (long long)h->nsm * occ;
-    if (h->k1s_ok && p.order == QOC_ORDER_FRECHET && target < (long long)h->nsm * K1S_WPB) target = (long long)h->nsm * K1S_WPB;
+    if (h->k1s_ok && target < (long long)h->nsm * K1S_WPB) target = (long long)h->nsm * K1S_WPB;
     long long spp = (target + p.batch - 1) / p.batch;
     if (spp < 1) spp = 1;
     if (spp > p.nt) spp = p.nt;
-    if (h->k1s_ok && p.order == QOC_ORDER_FRECHET && p.batch > 1) {
+    if (h->k1s_ok && p.batch > 1) {
       // K1S workers (warps) take whole segments: pick the segment count that wastes least of the last wave
       // (4096 pulses on 1184 workers: 1 segment per pulse fills 3.46 waves, 2 fill 6.92)
       const long long W = (long long)h->nsm * K1S_WPB;
@@ -807,7 +807,7 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
     // NW compute warps + 4 service warps
-    if (h->k1s_ok && p.order == QOC_ORDER_FRECHET) {
+    if (h->k1s_ok) {
       // small-dimension form: one warp per segment, no CTA barriers (qoc_k1s.cuh)
       const int ctas = (h->nseg + K1S_WPB - 1) / K1S_WPB;
       k1s_kernel<<<ctas < h->nsm ? ctas : h->nsm, K1S_WPB * 32, k1s_smem_bytes(p.nc), st>>>(k, h->S);

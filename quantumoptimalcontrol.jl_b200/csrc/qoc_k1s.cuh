@@ -1,4 +1,4 @@
-// qoc_k1s.cuh -- K1S: the small-dimension form of K1 (d <= 9: two qutrits, qubit pairs, ...), exact-Frechet / expm-only mode.
+// qoc_k1s.cuh -- K1S: the small-dimension form of K1 (d <= 9: two qutrits, qubit pairs, ...), every gradient mode.
 //
 // Same arithmetic and the same outputs as k1_kernel (generator, Pade [5/5] / [7/7] / [13/13] expm with scaling and
 // squaring, block-triangular Frechet derivative per control, running segment product; U_k, dU_k/du_j and Q_seg in the
@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(K1S_WPB * 32, 1) k1s_kernel(K1Params p, int S)
 #pragma unroll
       for (int e = 0; e < 3; e++) { a.v[e].x *= scl; a.v[e].y *= scl; }
       c.st(c.M(sA_), a);
+      const bool taylor = (p.order != 0);
+      if (taylor && p.want_jac && p.order >= 2) c.st(c.M(sS_), x);   // the unscaled generator, operand of the Taylor Jacobian
       __syncwarp();
 
       // ---- Pade numerator / denominator: U = A W, N = V - U ----
@@ -318,8 +320,48 @@ __global__ void __launch_bounds__(K1S_WPB * 32, 1) k1s_kernel(K1Params p, int S)
       c.st(c.M(sR_), rr3);
       __syncwarp();
 
+      // ---- the reference's truncated Taylor Jacobian (src/gradient_computations.jl:177-213, dt = 1, same association
+      //      order): E + (EX + XE)/2 + (EX X + XE X + X XE)/6 + (EX X2 + XE X2 + X2 EX + X2 XE)/24 ----
+      if (p.want_jac && taylor) {
+        for (int j = 0; j < nc; j++) {
+          const double2* E = c.E + (size_t)j * K1S_MSZ;
+          C3 out = c.ld(E);
+          if (p.order >= 2) {
+            C3 ex = K1SCtx::zero(), xe = K1SCtx::zero();
+            c.macc(ex, E, c.M(sS_));
+            c.macc(xe, c.M(sS_), E);
+            c.st(c.M(sM2_), ex);
+            c.st(c.M(sM4_), xe);
+            if (p.order >= 4) {
+              C3 x2 = K1SCtx::zero();
+              c.macc(x2, c.M(sS_), c.M(sS_));
+              c.st(c.M(sM6_), x2);
+            }
+            __syncwarp();
+            axpy3(out, 0.5, ex);
+            axpy3(out, 0.5, xe);
+            if (p.order >= 3) {
+              C3 t3 = K1SCtx::zero();
+              c.macc(t3, c.M(sM2_), c.M(sS_));
+              c.macc(t3, c.M(sM4_), c.M(sS_));
+              c.macc(t3, c.M(sS_), c.M(sM4_));
+              axpy3(out, 1.0 / 6.0, t3);
+            }
+            if (p.order >= 4) {
+              C3 t4 = K1SCtx::zero();
+              c.macc(t4, c.M(sM2_), c.M(sM6_));
+              c.macc(t4, c.M(sM4_), c.M(sM6_));
+              c.macc(t4, c.M(sM6_), c.M(sM2_));
+              c.macc(t4, c.M(sM6_), c.M(sM4_));
+              axpy3(out, 1.0 / 24.0, t4);
+            }
+            __syncwarp();   // every lane has read EX / XE / X2 before the next control overwrites them
+          }
+          k1s_store_slot(c, p.L + (slice * nc + j) * slot_d, S, out);
+        }
+      }
       // ---- exact Frechet derivative per control (Al-Mohy & Higham 2009, Alg. 6.4; E unscaled, 2^-s on the result) ----
-      if (p.want_jac) {
+      if (p.want_jac && !taylor) {
         for (int j = 0; j < nc; j++) {
           const double2* E = c.E + (size_t)j * K1S_MSZ;
           C3 m2 = K1SCtx::zero(), m4 = K1SCtx::zero(), m6 = K1SCtx::zero(), lw, lv, lu = K1SCtx::zero();
@@ -379,7 +421,7 @@ __global__ void __launch_bounds__(K1S_WPB * 32, 1) k1s_kernel(K1Params p, int S)
       }
       // ---- squarings: L <- R L + L R ; R <- R R ----
       for (int t2 = 0; t2 < sq; t2++) {
-        if (p.want_jac)
+        if (p.want_jac && !taylor)
           for (int j = 0; j < nc; j++) {
             C3 ln = K1SCtx::zero();
             c.macc(ln, c.M(sR_), c.M(K1S_FIXED + j));
@@ -411,7 +453,7 @@ __global__ void __launch_bounds__(K1S_WPB * 32, 1) k1s_kernel(K1Params p, int S)
       if (last_of_seg) k1s_store_slot(c, p.Q + (size_t)seg * slot_d, S, q3);
       {
         const int pi_q = qd == 13 ? 6 : qd == 7 ? 4 : 3;
-        const int G = p.want_jac ? (2 * pi_q + 2 * sq + 2) : 0;
+        const int G = !p.want_jac ? 0 : taylor ? (p.order == 1 ? 0 : p.order == 2 ? 2 : p.order == 3 ? 5 : 10) : (2 * pi_q + 2 * sq + 2);
         my_thirds += 3 * (pi_q + sq) + 4 + 3 * nc * G;
       }
     }

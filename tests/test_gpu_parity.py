@@ -561,3 +561,20 @@ def test_real_hamiltonian_fast_path_taylor_orders(d, nc, m, scale, monkeypatch):
         monkeypatch.delenv("QOC_NO_REALH")
         assert_parity(J, g, J2, g2)
         assert np.abs(dU - np.array(cache2.dUkdu)).max() < 1e-11 * max(1.0, np.abs(dU).max())
+
+
+@pytest.mark.parametrize("d,nt,nc,m,order", [(4, 9, 2, 4, 3), (8, 33, 2, 8, 0), (9, 40, 2, 4, 0), (9, 20, 2, 4, 4), (6, 15, 5, 2, 0)])
+def test_small_dimension_kernel_and_dmma_classes_agree(d, nt, nc, m, order, monkeypatch):
+    """d <= 9 is served by the warp-per-slice kernel k1s_kernel (nc <= 4); the DMMA shape classes it replaces stay reachable
+    (QOC_NO_K1S=1, and nc > 4).  Both against the oracle and against each other, U_k and dU_k/du_j included."""
+    cfg = o.config_synthetic(d, nt, nc=nc, m=m, seed=4000 + 13 * d + nt)
+    Jo, go, co = o.evaluate(cfg, order=order)
+    J, g, cache = gpu_eval(cfg, order)
+    assert_parity(J, g, Jo, go)
+    assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-12
+    dU = np.array(cache.dUkdu)
+    monkeypatch.setenv("QOC_NO_K1S", "1")
+    J2, g2, cache2 = gpu_eval(cfg, order)
+    assert_parity(J2, g2, Jo, go)
+    assert np.abs(cache2.Uk_vec - co["Uk"]).max() < 1e-12
+    assert np.abs(dU - np.array(cache2.dUkdu)).max() < 1e-12 * max(1.0, np.abs(dU).max())
