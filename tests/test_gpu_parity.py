@@ -578,3 +578,20 @@ def test_small_dimension_kernel_and_dmma_classes_agree(d, nt, nc, m, order, monk
     assert_parity(J2, g2, Jo, go)
     assert np.abs(cache2.Uk_vec - co["Uk"]).max() < 1e-12
     assert np.abs(dU - np.array(cache2.dUkdu)).max() < 1e-12 * max(1.0, np.abs(dU).max())
+
+
+@pytest.mark.parametrize("d,nc,m", [(7, 2, 3), (9, 4, 4), (3, 1, 1)])
+@pytest.mark.parametrize("scale", [1e-3, 0.3, 3.0, 11.0, 40.0])
+def test_small_dimension_kernel_norm_regimes(d, nc, m, scale):
+    """k1s_kernel over every Pade degree ([5/5], [7/7], [13/13]) and 0..4 squarings, exact-Frechet and Taylor-3 mode,
+    nc up to its limit of 4, ragged d (masked strips)."""
+    cfg = o.config_synthetic(d, 14, nc=nc, m=m, seed=77 + d)
+    cfg["A0"] = cfg["A0"] * scale
+    cfg["A"] = [a * scale for a in cfg["A"]]
+    for order in (0, 3):
+        Jo, go, co = o.evaluate(cfg, order=order)
+        J, g, cache = gpu_eval(cfg, order)
+        assert abs(J - Jo) <= TOL_J
+        assert np.abs(g - go).max() <= TOL_G * max(np.abs(go).max(), 1e-300)
+        assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-11
+        assert np.abs(cache.x - co["x"]).max() < 1e-11
