@@ -549,7 +549,8 @@ constexpr int K3N_CW = 7;  // contraction warps
 
 template <class C>
 // (small shape classes: 2 CTAs per SM -- the per-segment recurrence is a latency chain, co-resident segments are what
-// keeps the SM busy; d = 9 batch: 2.72 ms at one CTA per SM, 2.09 ms at two (96 registers), 2.55 ms at three (64 registers, spills))
+// keeps the SM busy; d = 9 batch: 2.72 ms at one CTA per SM, 2.09 ms at two (96 registers), 2.55 ms at three (64 registers, spills);
+// three contraction warps instead of seven at four CTAs per SM: 3.2 ms -- the contraction, not the recurrence, is what is slow at d = 9)
 __global__ void __launch_bounds__((C::NT + 1 + K3N_CW) * 32, (C::NT <= 2) ? 2 : 1) k3n_kernel(K23Params p, int seg_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int S = C::S;
