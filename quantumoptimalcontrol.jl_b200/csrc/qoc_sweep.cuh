@@ -621,6 +621,8 @@ __global__ void __launch_bounds__((C::NT + 1 + K3N_CW) * 32, (C::NT <= 2) ? 2 : 
     } else if (contract) {
       // ---------------- contraction warps ----------------
       const int cw = warp - NT - 1;
+      if (nc == 1) {
+      // a single control: one item per slice, four units in flight per lane (HBM-bound at d = 27)
       for (int item = cw; item < len * nc; item += K3N_CW) {
         const int it = item / nc, j = item - it * nc;
         const int k = k1 - 1 - it;
@@ -678,6 +680,85 @@ __global__ void __launch_bounds__((C::NT + 1 + K3N_CW) * 32, (C::NT <= 2) ? 2 : 
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0) p.dJdu[((size_t)b * p.nt + k) * nc + j] = s;
       }
+          } else {
+      // one item = (slice, pair of controls): w[r][c] = sum_l x[c][l] conj(lambda[r][l]) does not depend on the control, so
+      // it is formed once per unit and contracted with both Jacobians of the pair
+      const int npair = (nc + 1) / 2;
+      for (int item = cw; item < len * npair; item += K3N_CW) {
+        const int it = item / npair, j0 = 2 * (item - it * npair);
+        const bool two = (j0 + 1 < nc);
+        const int k = k1 - 1 - it;
+        const double* Lp0 = p.L + ((sl0 + (len - 1 - it)) * nc + j0) * slot_d;
+        const double* Lp1 = Lp0 + slot_d;   // read only when the pair is complete
+        // Re tr(lambda' dU x) = sum_{r,c} Re( dU[r][c] * w[r][c] )   (:217-223)
+        // the Jacobian loads do not depend on lambda: issue the first batch before waiting for the recurrence
+        constexpr int UB = 2;   // units in flight per lane and control
+        double2 fre[2][UB], fim[2][UB];
+#pragma unroll
+        for (int i = 0; i < UB; i++) { fre[1][i] = make_double2(0.0, 0.0); fim[1][i] = fre[1][i]; fre[0][i] = fre[1][i]; fim[0][i] = fre[1][i]; }
+#pragma unroll
+        for (int i = 0; i < UB; i++) {
+          const int u = lane + i * 32;
+          if (u < units) {
+            fre[0][i] = __ldg(reinterpret_cast<const double2*>(Lp0) + u);
+            fim[0][i] = __ldg(reinterpret_cast<const double2*>(Lp0 + d * S) + u);
+            if (two) {
+              fre[1][i] = __ldg(reinterpret_cast<const double2*>(Lp1) + u);
+              fim[1][i] = __ldg(reinterpret_cast<const double2*>(Lp1 + d * S) + u);
+            }
+          }
+        }
+        while (*ready < it) __nanosleep(64);
+        __threadfence_block();
+        const double* lr = ls + (size_t)it * sb;              // lambda_{k+1}
+        const double* xk = xs + (size_t)(k - k0) * sb;        // x_k
+        double s0 = 0.0, s1 = 0.0;
+        for (int u0 = 0; u0 < units; u0 += UB * 32) {
+          double2 cre[2][UB], cim[2][UB];
+#pragma unroll
+          for (int i = 0; i < UB; i++) { cre[0][i] = fre[0][i]; cim[0][i] = fim[0][i]; cre[1][i] = fre[1][i]; cim[1][i] = fim[1][i]; }
+#pragma unroll
+          for (int i = 0; i < UB; i++) {
+            const int u = u0 + UB * 32 + lane + i * 32;
+            if (u < units) {
+              fre[0][i] = __ldg(reinterpret_cast<const double2*>(Lp0) + u);
+              fim[0][i] = __ldg(reinterpret_cast<const double2*>(Lp0 + d * S) + u);
+              if (two) {
+                fre[1][i] = __ldg(reinterpret_cast<const double2*>(Lp1) + u);
+                fim[1][i] = __ldg(reinterpret_cast<const double2*>(Lp1 + d * S) + u);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < UB; i++) {
+            const int u = u0 + lane + i * 32;
+            if (u < units) {
+              const int r = u / (S / 2), c0 = 2 * (u - r * (S / 2));
+              const double* lrow = lr + r * W;
+              const double* x0p = xk + c0 * W;
+              double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
+              for (int l = 0; l < m; l++) {
+                const double2 lam = *reinterpret_cast<const double2*>(lrow + 2 * l);
+                const double2 xa_ = *reinterpret_cast<const double2*>(x0p + 2 * l);
+                const double2 xb_ = *reinterpret_cast<const double2*>(x0p + W + 2 * l);
+                w0r = fma(xa_.x, lam.x, fma(xa_.y, lam.y, w0r)); w0i = fma(xa_.y, lam.x, fma(-xa_.x, lam.y, w0i));
+                w1r = fma(xb_.x, lam.x, fma(xb_.y, lam.y, w1r)); w1i = fma(xb_.y, lam.x, fma(-xb_.x, lam.y, w1i));
+              }
+              s0 = fma(cre[0][i].x, w0r, fma(-cim[0][i].x, w0i, s0));
+              s0 = fma(cre[0][i].y, w1r, fma(-cim[0][i].y, w1i, s0));
+              s1 = fma(cre[1][i].x, w0r, fma(-cim[1][i].x, w0i, s1));
+              s1 = fma(cre[1][i].y, w1r, fma(-cim[1][i].y, w1i, s1));
+            }
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off); }
+        if (lane == 0) {
+          p.dJdu[((size_t)b * p.nt + k) * nc + j0] = s0;
+          if (two) p.dJdu[((size_t)b * p.nt + k) * nc + j0 + 1] = s1;
+        }
+      }
+          }
     }
     __syncthreads();
     // states / costates of the segment to global memory (debug getters, time-sharding hand-over)
