@@ -159,8 +159,15 @@ class TimeShardedEvaluator:
             self._S_all = torch.empty((self.world, eng.d, eng.d), dtype=torch.complex128, device=self.device)
             self._g_all = torch.zeros((self.world, self._nmax, nc), dtype=torch.float64, device=self.device)
             self._g_pad = torch.zeros((self._nmax, nc), dtype=torch.float64, device=self.device)
+            # pinned staging: u goes up and (gradient segments, J) come down with asynchronous copies and ONE synchronise
+            self._u_pin = torch.zeros((self.hi - self.lo, nc), dtype=torch.float64).pin_memory()
+            self._u_dev = torch.zeros((self.hi - self.lo, nc), dtype=torch.float64, device=self.device)
+            self._g_host = torch.zeros((self.world, self._nmax, nc), dtype=torch.float64).pin_memory()
+            self._J_host = torch.zeros(1, dtype=torch.float64).pin_memory()
             self._dev_ready = True
-        u_dev = torch.from_numpy(np.ascontiguousarray(u_full[:, self.lo:self.hi].T)).to(self.device, non_blocking=True)
+        self._u_pin.copy_(torch.from_numpy(u_full[:, self.lo:self.hi].T))
+        self._u_dev.copy_(self._u_pin, non_blocking=True)
+        u_dev = self._u_dev
         S = eng.phase1_cm(u_dev)
         if self.world > 1:
             dist.all_gather_into_tensor(self._S_all, S, group=self.group)
@@ -172,12 +179,15 @@ class TimeShardedEvaluator:
             dist.all_gather_into_tensor(self._g_all, self._g_pad, group=self.group)
         else:
             self._g_all[0].copy_(self._g_pad)
-        gh = self._g_all.cpu().numpy()
+        self._g_host.copy_(self._g_all, non_blocking=True)
+        self._J_host.copy_(J[:1], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        gh = self._g_host.numpy()
         g = np.zeros((nc, self.nt_total))
         for r in range(self.world):
             lo, hi = time_partition(self.nt_total, self.world, r)
             g[:, lo:hi] = gh[r, : hi - lo].T
-        return float(J.cpu()[0]), g
+        return float(self._J_host[0]), g
 
     def evaluate(self, u_full):
         """u_full: (nc, Nt) on every rank (only the local columns are used).  -> (J, dJdu (nc, Nt) numpy)."""
