@@ -64,3 +64,26 @@ def test_config_generators():
     assert np.allclose(s["T"].conj().T @ s["T"], np.eye(4))
     b = configs.config_zz_batch(3)
     assert b["u_batch"].shape == (3, 2, 100) and np.abs(b["u_batch"]).max() <= 2 * np.pi * 0.06 + 1e-12
+
+
+def test_bench_l2_note_and_ncu_summary_tool(tmp_path):
+    """bench.py states how the timed steps relate to the L2 for every workload; tools/ncu_summary.py condenses an
+    `ncu --page raw --csv` export into the JSON kept under profiles/."""
+    import importlib.util, json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert "exceeds the 126 MB L2" in bench.l2_note(27, 10000, 1, 1)          # C2: 242 MB of U_k / dU_k per step
+    assert "242 MB" in bench.l2_note(27, 10000, 1, 1)
+    assert "stays in" in bench.l2_note(24, 550, 1, 2)                          # C3: 17.7 MB
+    raw = tmp_path / "raw.csv"
+    cols = ["ID", "Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
+    raw.write_text(",".join('"%s"' % c for c in cols) + "\n" + '"","","ms","Mbyte","Kbyte","inst"\n'
+                   + '"0","k1_kernel","1.25","0.5","1,500.0","2.5"\n')
+    out = tmp_path / "out.json"
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), str(raw), str(out), "src", "wl"])
+    k = json.load(open(out))["kernels"][0]
+    assert k["name"] == "k1_kernel" and k["gpu__time_duration.sum"]["value"] == 1.25
+    assert abs(k["traffic_bytes_per_launch"] - (0.5e6 + 1500.0e3)) < 1e-6
