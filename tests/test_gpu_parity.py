@@ -595,3 +595,20 @@ def test_small_dimension_kernel_norm_regimes(d, nc, m, scale):
         assert np.abs(g - go).max() <= TOL_G * max(np.abs(go).max(), 1e-300)
         assert np.abs(cache.Uk_vec - co["Uk"]).max() < 1e-11
         assert np.abs(cache.x - co["x"]).max() < 1e-11
+
+
+def test_propagators_and_jacobians_against_binary128_ground_truth():
+    """U_k and the exact dU_k/du_j of the CUDA path against exp / Frechet derivative computed in binary128
+    (oracle/qoc_quad.c), for the three K1 forms: k1s_kernel (zz, d = 9), the real-symmetric instantiation (bus, d = 27),
+    the general complex low-degree instantiation (cavity, d = 24)."""
+    import qoc_quad
+    for cfg in (o.config_zz(), o.config_bus(Nt=40, tgate=1.4), o.config_cavity(12, Nt=30)):
+        J, g, cache = gpu_eval(cfg, 0)
+        Uk, dU = np.array(cache.Uk_vec), np.array(cache.dUkdu)
+        nt = cfg["u"].shape[1]
+        for k in (0, nt // 2, nt - 1):
+            X = o.generator(cfg["A0"], cfg["A"], cfg["u"][:, k])
+            for j, Aj in enumerate(cfg["A"]):
+                U, L = qoc_quad.expm_quad(X, Aj)
+                assert np.abs(Uk[k] - U).max() < 1e-13
+                assert np.abs(dU[k, j] - L).max() < 1e-13 * max(1.0, np.abs(L).max())

@@ -238,3 +238,26 @@ def test_f_alg_worked_values():
     assert o.f_alg(24, 2, 2, 7, 0, 0) == pytest.approx(2.84e6, rel=3e-3)
     assert o.f_alg(256, 4, 2, 13, 0, 0) == pytest.approx(4.74e9, rel=3e-3)
     assert o.f_alg(9, 4, 2, 7, 0, 3) == pytest.approx(100e3, rel=2e-2)
+
+
+def test_expm_restatements_against_binary128_ground_truth():
+    """SURVEY 8c oracle stack: the reference's expm lives in an un-vendored dependency, so the oracle's own Higham-2005 and
+    Al-Mohy-Higham (Frechet) restatements are pinned against an independent binary128 computation (oracle/qoc_quad.c:
+    Taylor series + squaring in __float128, central difference with step 2^-40 for the derivative) on slices of every
+    named model, on a non-normal generator, and over the norm regimes that select every Pade degree."""
+    import qoc_quad
+    cases = []
+    for cfg in (o.config_zz(), o.config_bus(Nt=40, tgate=1.4), o.config_cavity(12, Nt=30)):
+        for k in (0, cfg["u"].shape[1] // 2, cfg["u"].shape[1] - 1):
+            cases.append((o.generator(cfg["A0"], cfg["A"], cfg["u"][:, k]), cfg["A"][0]))
+    rng = np.random.default_rng(11)
+    for d, scale in ((6, 0.05), (6, 0.5), (8, 3.0), (5, 12.0), (7, 45.0)):
+        cases.append((scale * rng.standard_normal((d, d)) / d + 0j, rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))))
+    for X, E in cases:
+        U, L = qoc_quad.expm_quad(X, E)
+        sU, sL = max(1.0, np.abs(U).max()), max(1.0, np.abs(L).max())
+        assert np.abs(o.expm_higham2005(X) - U).max() < 5e-14 * sU
+        Us, Ls = o.expm_frechet_sps(X, E)
+        assert np.abs(Us - U).max() < 5e-14 * sU
+        assert np.abs(Ls - L).max() < 2e-13 * sL
+        assert np.abs(o.expm_frechet_blocktri(X, E)[1] - L).max() < 2e-13 * sL
