@@ -171,7 +171,15 @@ def cpu_port_run(cfg, u, batch, order, nthreads, reps):
     """Times oracle/qoc_ref.c on `reps` full evaluations of (a bounded sample of) the workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import qoc_ref
-    nth = qoc_ref.max_threads() if nthreads <= 0 else nthreads
+    # all the host cores this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every
+    # rank, which would silently turn the CPU arm into a single-thread run (the C port sets num_threads explicitly)
+    if nthreads <= 0:
+        try:
+            nth = len(os.sched_getaffinity(0))
+        except AttributeError:
+            nth = os.cpu_count() or qoc_ref.max_threads()
+    else:
+        nth = nthreads
     if batch == 1:
         pulses = [u]
     else:  # bounded sample of the batch
