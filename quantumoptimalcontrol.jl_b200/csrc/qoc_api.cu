@@ -187,7 +187,7 @@ extern "C" const char* qoc_status_string(int s) {
 }
 extern "C" const char* qoc_last_error(const qoc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 extern "C" int qoc_last_launch_count(const qoc_handle* h) { return h ? h->launches : 0; }
-extern "C" int qoc_version(void) { return 100; }
+extern "C" int qoc_version(void) { return 101; }   // 101: + qoc_last_exec_flops
 extern "C" int qoc_set_profiling(qoc_handle* h, int on) {
   if (!h) return QOC_ERR_INVALID;
   h->profiling = on != 0;
