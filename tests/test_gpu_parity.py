@@ -612,3 +612,32 @@ def test_propagators_and_jacobians_against_binary128_ground_truth():
                 U, L = qoc_quad.expm_quad(X, Aj)
                 assert np.abs(Uk[k] - U).max() < 1e-13
                 assert np.abs(dU[k, j] - L).max() < 1e-13 * max(1.0, np.abs(L).max())
+
+
+@pytest.mark.parametrize("order", [0, 3])
+def test_time_sharding_small_dimension_kernel_virtual_ranks(order):
+    """Time-segment sharding with k1s_kernel feeding the phase API (d = 9, m = 4, nc = 2, uneven segments, both gradient modes):
+    one-call phase 2 over the gathered rank propagators, P virtual ranks on one GPU."""
+    import torch
+    from qoc_b200 import sharding
+    cfg = o.config_synthetic(9, 301, nc=2, m=4, seed=123)
+    P = 3
+    Jo, go, co = o.evaluate(cfg, order=order)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"])[1]
+    dev = torch.device("cuda", 0)
+    S_all = torch.empty((P, 9, 9), dtype=torch.complex128, device=dev)
+    engines = []
+    for r in range(P):
+        lo, hi = sharding.time_partition(301, P, r)
+        e = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, cfg["x0"].shape[1], 0, order=order)
+        e.set_builtin_cost(cost, cfg["x0"])
+        u_dev = torch.from_numpy(np.ascontiguousarray(cfg["u"][:, lo:hi].T)).to(dev)
+        S_all[r].copy_(e.phase1_cm(u_dev))
+        engines.append(e)
+    g = np.zeros_like(go)
+    for r in range(P):
+        lo, hi = sharding.time_partition(301, P, r)
+        J, gl = engines[r].phase2(S_all, P, r)
+        assert abs(float(J.cpu()[0]) - Jo) <= TOL_J
+        g[:, lo:hi] = gl.cpu().numpy().T
+    assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
