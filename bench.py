@@ -402,7 +402,12 @@ def main():
     sweep = (8.0 * cfg["A0"].shape[0] ** 2 * cfg["x0"].shape[1] * (2 + nc) + 4.0 * nc * cfg["A0"].shape[0] ** 2) * nt * batch
     k1_flops = alg_flops_total - sweep
     k1_tflops = k1_flops / (stage[0] * 1e-3) * 1e-12
-    roofline = {"bound": "tensor", "kernel": "k1_kernel (expm + Jacobians + segment scan)",
+    dd = cfg["A0"].shape[0]
+    k1_name = ("k1s_kernel (warp-per-slice small-dimension form: expm + Jacobians + segment scan; scalar DFMA, the peak is still the "
+               "measured FP64 tensor-pipe figure)" if (dd <= 9 and nc <= 4 and os.environ.get("QOC_NO_K1S") != "1")
+               else "general-path batched DMMA GEMM chain (expm + Jacobians + segment products)" if dd > 28
+               else "k1_kernel (expm + Jacobians + segment scan)")
+    roofline = {"bound": "tensor", "kernel": k1_name,
                 "achieved": k1_tflops, "peak": peak, "unit": "TFLOP/s", "frac": k1_tflops / peak,
                 "traffic": ncu_traffic_bytes("k1_kernel", args.workload),
                 "peak_source": peak_src, "k1_ms": float(stage[0]), "k2_ms": float(stage[1]), "k3_ms": float(stage[2]),
