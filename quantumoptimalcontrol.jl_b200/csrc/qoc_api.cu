@@ -55,6 +55,7 @@ struct qoc_handle {
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
   bool gs2 = false;
+  bool k1_skewh = false;      // A0 and every A_j skew-Hermitian (bitwise): k1s_kernel forms A E + E A, A2 M2 + M2 A2, X E as P + P^dagger
   bool k1s_ok = false;        // d <= 9, nc <= 4: the warp-per-slice small-dimension kernel
   bool k1_sym = false;        // ... with symmetric H0, H_j: Pade denominator inverted through the real SPD matrix N N^dagger
   bool k1_realh = false;      // K1 real-Hamiltonian fast path (Re A0 = Re A_j = 0, Frechet mode, [13/13] instantiation)
@@ -454,6 +455,21 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
           }
         }
       h->k1_sym = sy;
+      // skew-Hermitian generators (every physical problem: X = -i H dt with H Hermitian), checked bitwise
+      const char* offs = getenv("QOC_NO_SKEWH");
+      bool sk = !(offs && offs[0] == '1');
+      auto skew = [&](const double* M) {
+        for (int r = 0; r < p.d; r++)
+          for (int cc = 0; cc <= r; cc++) {
+            const double ar = M[2 * (r + (size_t)p.d * cc)], ai = M[2 * (r + (size_t)p.d * cc) + 1];
+            const double br = M[2 * (cc + (size_t)p.d * r)], bi = M[2 * (cc + (size_t)p.d * r) + 1];
+            if (!(ar == -br && ai == bi)) return false;
+          }
+        return true;
+      };
+      sk = sk && skew(A0);
+      for (int j = 0; j < p.nc && sk; j++) sk = skew(A + (size_t)j * 2 * p.d * p.d);
+      h->k1_skewh = sk;
     }
   }
   if (h->gpath) {
@@ -798,7 +814,7 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   const qoc_problem& p = h->prob;
   K1Params k;
   k.d = p.d; k.nc = p.nc; k.nt = p.nt; k.batch = p.batch; k.order = p.order;
-  k.nseg = h->nseg; k.seg_per_pulse = h->spp; k.want_jac = want_jac ? 1 : 0; k.sym = h->k1_sym ? 1 : 0;
+  k.nseg = h->nseg; k.seg_per_pulse = h->spp; k.want_jac = want_jac ? 1 : 0; k.sym = h->k1_sym ? 1 : 0; k.skewh = h->k1_skewh ? 1 : 0;
   k.A0p = h->dA0p; k.Ap = h->dAp; k.u = d_u; k.U = h->dU; k.L = h->dL; k.Q = h->dQ;
   k.flops = h->dflops; k.status = h->dstatus;
   k.theta13 = (p.order == QOC_ORDER_FRECHET) ? 4.74 : 5.4;

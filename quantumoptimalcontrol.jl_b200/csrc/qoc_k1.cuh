@@ -28,6 +28,7 @@ struct K1Params {
   int d, nc, nt, batch, order;
   int nseg, seg_per_pulse;
   int want_jac;            // 0: expm only (propagate without gradient)
+  int skewh;               // k1s_kernel only: A0 and every A_j are skew-Hermitian (X_k = -i H_k dt, H_k Hermitian)
   int sym;                 // real-Hamiltonian path only: H0 and every H_j symmetric (X_k skew-Hermitian): N^-1 = N^dagger (N N^dagger)^-1
   const double* A0p;       // planar slot
   const double* Ap;        // nc planar slots
