@@ -276,6 +276,21 @@ struct K1Ctx {
     *reinterpret_cast<double2*>(plane + o) = make_double2(v0, last ? 0.0 : v1);
   }
   static __device__ __forceinline__ double2 rld(const double* plane, int o) { return *reinterpret_cast<const double2*>(plane + o); }
+  // M = P + P^dagger on this warp's tiles (skew-Hermitian generators: A E + E A and A2 M2 + M2 A2 from one product)
+  __device__ __forceinline__ void herm_add(Mat M, Mat P) const {
+    const int row = mi * 8 + (lane >> 2);
+#pragma unroll
+    for (int n = 0; n < C::BN; n++) {
+      const int col = (nj0 + n) * 8 + 2 * (lane & 3);
+      if (row < d && col < d) {
+        const int o = row * C::S + col, ot = col * C::S + row;
+        const bool last = col + 1 >= d;
+        const double2 pr = rld(P.re, o), pi = rld(P.im, o);
+        rst(M.re, o, pr.x + P.re[ot], pr.y + P.re[ot + C::S], last);
+        rst(M.im, o, pi.x - P.im[ot], pi.y - P.im[ot + C::S], last);
+      }
+    }
+  }
   // L = P + P^T on this warp's tiles (complex-symmetric squaring step of the real-symmetric-Hamiltonian path)
   __device__ __forceinline__ void sym_add(Mat L, Mat P) const {
     const int row = mi * 8 + (lane >> 2);
@@ -758,10 +773,13 @@ __device__ __forceinline__ void pade_low_build_N(K1Ctx<C>& c, Mat U, Mat N, int 
 
 // Frechet derivative of the [5/5] / [7/7] Pade approximant (Al-Mohy & Higham 2009, eq. (6.3) ff.): Lw and Lv are pure
 // linear combinations of M2, M4 (, M6), so the whole part 1 is 3 (4) two-product phases.
+// skewh (A0 and every A_j skew-Hermitian, bitwise): A E + E A = P + P^dagger, A2 M2 + M2 A2 = P + P^dagger with one product P
+// (scratch: role sT), the adjoint added in a short elementwise phase.
 template <class C>
-__device__ __forceinline__ void frechet_low_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat Sst, int q) {
+__device__ __forceinline__ void frechet_low_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat Sst, int q, bool skewh) {
   Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), W = c.S(sW), M2 = c.S(sM2), M4 = c.S(sM4), M6 = c.S(sM6), Lw = c.S(sLw);
-  c.mm2(M2, A, E, E, A, NoEpi());
+  if (skewh) { c.mm1(c.S(sT), A, E, NoEpi()); c.herm_add(M2, c.S(sT)); c.cbar(); }
+  else c.mm2(M2, A, E, E, A, NoEpi());
   DiffSumLinEpi<C::S> ds;
   ds.sdst = Sst; ds.d = c.d;
   if (q == 5) {
@@ -773,7 +791,8 @@ __device__ __forceinline__ void frechet_low_part1(K1Ctx<C>& c, Mat E, Mat Dst, M
     ds.m1 = M4; ds.m2 = M2; ds.m3 = M2; ds.c1 = b[4]; ds.c2 = b[2]; ds.c3 = 0.0;
   } else {
     const double* b = c_b7;
-    c.mm2(M4, A2, M2, M2, A2, NoEpi());
+    if (skewh) { c.mm1(c.S(sT), A2, M2, NoEpi()); c.herm_add(M4, c.S(sT)); c.cbar(); }
+    else c.mm2(M4, A2, M2, M2, A2, NoEpi());
     DualEpi<C::S> e;   // M6 = A4 M2 + M4 A2 ; Lw = b7 M6 + b5 M4 + b3 M2
     e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
     e.dst2 = Lw; e.n1 = M4; e.n2 = M2; e.n3 = M2; e.k0 = b[7]; e.k1 = b[5]; e.k2 = b[3]; e.k3 = 0.0; e.kI = 0.0; e.d = c.d;
@@ -789,12 +808,17 @@ __device__ __forceinline__ void frechet_low_part1(K1Ctx<C>& c, Mat E, Mat Dst, M
 // (L is linear in E; the factor 2^-s is applied to the result).  part 1: everything that does not need N^-1.
 // On exit: Dst = Lu - Lv, Sst = Lu + Lv   (Sst doubles as the Lv workspace).
 template <class C>
-__device__ __forceinline__ void frechet13_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat Sst) {
+__device__ __forceinline__ void frechet13_part1(K1Ctx<C>& c, Mat E, Mat Dst, Mat Sst, bool skewh) {
   const double* b = c_b13;
   Mat A = c.S(sA), A2 = c.S(sA2), A4 = c.S(sA4), A6 = c.S(sA6), WZ = c.S(sWZ), W = c.S(sW), M2 = c.S(sM2),
       M4 = c.S(sM4), M6 = c.S(sM6), T = c.S(sT), Lw = c.S(sLw), Lv = Sst;
-  c.mm2(M2, A, E, E, A, NoEpi());
-  c.mm2(M4, A2, M2, M2, A2, NoEpi());
+  if (skewh) {
+    c.mm1(T, A, E, NoEpi()); c.herm_add(M2, T); c.cbar();
+    c.mm1(T, A2, M2, NoEpi()); c.herm_add(M4, T); c.cbar();
+  } else {
+    c.mm2(M2, A, E, E, A, NoEpi());
+    c.mm2(M4, A2, M2, M2, A2, NoEpi());
+  }
   {  // M6 = A4 M2 + M4 A2 ; T = Lw1 = b13 M6 + b11 M4 + b9 M2 from the same epilogue
     DualEpi<C::S> e;
     e.base = c.epi(1.0, 0.0, A2, 0.0, A2, 0.0, A2, 0.0);
@@ -1190,8 +1214,10 @@ __global__ void __launch_bounds__(C::NTHREADS + NSW * 32, C::MINB) k1_kernel(K1P
         // control 0 last: its (D, S) stay in (sM2, sLv), which the other controls' part1 uses as workspace (sM2)
         for (int j = nc - 1; j >= 0; j--)
           if (REALH) frechet13_part1_realh<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)));
-          else if (!LOW || q_cur == 13) frechet13_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)));
-          else frechet_low_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)), q_cur);
+          // (the P + P^dagger form pays only where a product costs more than a barrier phase: measured +6 % at d = 24,
+          //  -1 % at d = 16, so the two small tile classes keep the two-product form)
+          else if (!LOW || q_cur == 13) frechet13_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)), C::NT >= 3 && p.skewh != 0);
+          else frechet_low_part1<C>(c, c.E(j), c.S(k1_role_D(j)), c.S(k1_role_S(j)), q_cur, C::NT >= 3 && p.skewh != 0);
       }
     }
     QOC_STAMP(1);
