@@ -2,26 +2,36 @@
 """bench.py -- GRAPE fidelity+gradient throughput (slices*pulses/s) of the B200-native path, per BASELINE.json.
 
 A "step" is one full fidelity + gradient evaluation (qoc_eval: K1 expm + Jacobians + segment scan, K2G two-level
-boundary scan + cost, K3N sweeps + gradient contraction) of the workload.  Workload at N = 1: BASELINE.json configs[1], the
-two_qubit_tunable_bus model (d = 27, m = 1, nc = 1) with 1e4 time slices, single pulse.  At N > 1 every rank
-evaluates its own pulse of that shape (multistart axis, no data-path collective) -> "scaling": "weak".
+boundary scan + cost, K3N sweeps + gradient contraction) of the workload.  Headline workload at N = 1: BASELINE.json
+configs[1], the two_qubit_tunable_bus model (d = 27, m = 1, nc = 1) with 1e4 time slices, single pulse, exact-Frechet
+mode (the north star's block-triangular derivative); the same workload in the reference's default Taylor-3 mode rides
+along as `taylor3`.  At N > 1 every rank evaluates its own pulse of that shape (multistart axis, no data-path
+collective) -> "scaling": "weak".
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode frechet|taylor3] [--workload bus|zz_batch|cavity]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode frechet|taylor3] [--workload bus|zz_batch|cavity...]
   python bench.py --impl reference ...      # the CPU restatement of the reference (oracle/qoc_ref.c), all host threads
 
-value  : device-resident inputs (u already in HBM), CUDA events on the launching stream, max over ranks.
-e2e    : same metric through the host-buffer C-ABI call qoc_eval (pinned host u in, J and dJdu out, copies inside
-         the timed region).
-roofline: K1 (the dominant kernel): algorithmic FP64 flops (SURVEY.md 8d F_alg, Pade degree/squarings as executed)
-         / K1's CUDA-event duration, against the FP64 tensor-core (DMMA) peak measured on this pool's B200 by
-         tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl; MEASURED_PEAKS.json has no FP64 figure).
-cpu_baseline: oracle/qoc_ref.c ("port": the Julia reference cannot run here) on the box's host cores, bounded sample.
+One JSON line.  Besides the base contract it carries
+  roofline      K1 (the dominant kernel) of the headline: algorithmic FP64 flops (SURVEY.md 8d F_alg, Pade degree /
+                squarings as executed) / K1's CUDA-event duration, against the FP64 tensor-core (DMMA) peak measured on
+                this pool's B200 (tools/fp64_peak.cu, profiles/r01_fp64_peak.jsonl; MEASURED_PEAKS.json has no FP64 figure)
+  cpu_baseline  oracle/qoc_ref.c ("port": the Julia reference cannot run here) on the box's host cores, both modes
+  taylor3       the headline workload in the reference's default gradient mode (dUkdp_order = 3)
+  sustained     the headline step repeated back to back for >= 2 s, with its own clock record
+  configs       (N = 1) every other BASELINE.json config -- C1 zz, C3 cavity N = 12 / 20 / 40 at Nt = 550, C4 4096-pulse
+                batch, C5 d = 16 ... 128 at Nt = 1e5 -- in both modes: value, e2e, roofline.frac
+                (N > 1) C4 with its 4096 pulses block-partitioned over the ranks (no collective)
+  strong        (N > 1) ONE pulse time-segment sharded over the N ranks (C2 bus and C5 d = 64, Nt = 1e5): NCCL all-gather
+                of the d x d rank propagators + all-gather of the gradient segments, max-over-ranks device time, and an
+                in-bench parity assertion against the single-GPU evaluation of the same pulse
+                (|dJ| <= 1e-10 max(1,|J|), |dg| <= 1e-8 max|g|)
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -37,6 +47,7 @@ sys.path.insert(0, ROOT)
 METRIC = "GRAPE fidelity+gradient evals/s (slices*pulses/s)"
 UNIT = "slices*pulses/s"
 FP64_PEAK_FALLBACK_TFLOPS = 37.1  # measured DMMA m8n8k4 on this pool (profiles/r01_fp64_peak.jsonl)
+TOL_J, TOL_G = 1e-10, 1e-8        # north star: relative 1e-10 on (in)fidelity, 1e-8 on each gradient component
 
 
 def fp64_peak_tflops():
@@ -62,16 +73,18 @@ def fp64_peak_tflops():
 
 def ncu_traffic_bytes(kernel_prefix, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed `ncu --set full`
-    capture (profiles/r01f_ncu_full_summary.json; captured on the bus workload only)."""
-    if workload != "bus":
+    capture of that workload (profiles/*_ncu_full_summary*.json), newest round first."""
+    tag = {"bus": "", "zz_batch": "_zz_batch"}.get(workload)
+    if tag is None:
         return None
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01f_ncu_full_summary.json")))
-        for k in prof["kernels"]:
-            if kernel_prefix in k["name"]:
-                return k["traffic_bytes_per_launch"]
-    except Exception:
-        pass
+    for rnd in ("r02", "r01f"):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", f"{rnd}_ncu_full_summary{tag}.json")))
+            for k in prof["kernels"]:
+                if kernel_prefix in k["name"]:
+                    return k["traffic_bytes_per_launch"]
+        except Exception:
+            continue
     return None
 
 
@@ -90,7 +103,7 @@ def l2_note(d, nt, batch, nc):
             "buffers); no flush between steps" % (ws, 8 * nc * nt * batch))
 
 
-def build_workload(name, rank, mode):
+def build_workload(name, rank, mode, batch_override=None):
     from qoc_b200 import configs
     if name == "bus":
         cfg = configs.config_bus(Nt=10000)
@@ -98,10 +111,14 @@ def build_workload(name, rank, mode):
             cfg["u"] = cfg["u"] + 1e-3 * np.random.default_rng(rank).standard_normal(cfg["u"].shape)
         desc = "C2 two_qubit_tunable_bus d=27 m=1 nc=1 Nt=10000, single pulse per GPU"
         batch, u = 1, cfg["u"]
+    elif name == "zz":
+        cfg = configs.config_zz()
+        desc = "C1 zz_coupling d=9 m=4 nc=2 Nt=100, single pulse per GPU"
+        batch, u = 1, cfg["u"]
     elif name == "zz_batch":
-        nb = 4096
+        nb = batch_override or 4096
         cfg = configs.config_zz_batch(nb, seed0=1 + rank * nb)
-        desc = "C4 zz_coupling d=9 m=4 nc=2 Nt=100, 4096 pulses per GPU"
+        desc = f"C4 zz_coupling d=9 m=4 nc=2 Nt=100, {nb} pulses per GPU"
         batch, u = nb, cfg["u_batch"]
     elif name == "cavity":
         cfg = configs.config_cavity(12, Nt=550)
@@ -152,38 +169,40 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the C restatement of the reference (oracle/qoc_ref.c) -- cpu_baseline and --impl reference only
+# ----------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    # all the host cores this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every
+    # rank, which would silently turn the CPU arm into a single-thread run (the C port sets num_threads explicitly)
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def cpu_port_run(cfg, u, batch, order, nthreads, reps):
     """Times oracle/qoc_ref.c on `reps` full evaluations of (a bounded sample of) the workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import qoc_ref
-    # all the host cores this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every
-    # rank, which would silently turn the CPU arm into a single-thread run (the C port sets num_threads explicitly)
-    if nthreads <= 0:
-        try:
-            nth = len(os.sched_getaffinity(0))
-        except AttributeError:
-            nth = os.cpu_count() or qoc_ref.max_threads()
-    else:
-        nth = nthreads
-    if batch == 1:
-        pulses = [u]
-    else:  # bounded sample of the batch
-        pulses = [u[b] for b in range(min(batch, 64))]
+    nth = nthreads if nthreads > 0 else host_threads()
+    pulses = [u] if batch == 1 else [u[b] for b in range(min(batch, 64))]   # bounded sample of the batch
     qoc_ref.ref_eval(cfg, order=order, nthreads=nth, u=pulses[0])  # warm-up (page in, spin up the OpenMP team)
     times, slices = [], 0
     for _ in range(reps):
@@ -195,80 +214,325 @@ def cpu_port_run(cfg, u, batch, order, nthreads, reps):
     return slices, times, nth, len(pulses)
 
 
+REF_NOTE = ("C restatement of the Julia reference (oracle/qoc_ref.c), not Julia: no julia toolchain in the image; OpenMP over the "
+            "per-slice expm loop as Threads.@threads in the reference (src/gradient_computations.jl:17), serial sweeps and serial "
+            "Jacobian loop (:65-74); hand-written loops, no MKL")
+
+
+def headline_config(desc, mode, world, extra=None):
+    """The `config` object both arms print (same keys, same values for the same run => the driver's same_config holds)."""
+    cfg = {"workload": desc, "mode": mode, "parallelism": f"pulse-sharded x{world}, no collective"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    order = 0 if args.mode == "frechet" else 3
-    cfg, u, batch, desc = build_workload(args.workload, 0, args.mode)
-    slices, times, nth, npulse = cpu_port_run(cfg, u, batch, order, 0, args.warmup + args.steps)
-    times = times[args.warmup:]
-    sec = sum(times)
-    val = slices * len(times) / sec
-    sample = f"{npulse} pulse(s) x {u.shape[-1]} slices of the workload per step, {len(times)} steps"
-    out = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(times), "higher_is_better": True, "scaling": "weak",
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    res = {}
+    for mode in ([args.mode] + [m for m in ("frechet", "taylor3") if m != args.mode]):
+        order = 0 if mode == "frechet" else 3
+        cfg, u, batch, desc = build_workload(args.workload, 0, mode)
+        reps = args.warmup + args.steps if mode == args.mode else 1 + min(3, args.steps)
+        slices, times, nth, npulse = cpu_port_run(cfg, u, batch, order, 0, reps)
+        times = times[args.warmup:] if mode == args.mode else times[1:]
+        sec = sum(times)
+        res[mode] = dict(val=slices * len(times) / sec, ms=1e3 * sec / len(times), nth=nth, npulse=npulse, n=len(times),
+                         nt=u.shape[-1], desc=desc, l2=l2_note(cfg["A0"].shape[0], u.shape[-1], batch, u.shape[-2]))
+    r = res[args.mode]
+    sample = f"{r['npulse']} pulse(s) x {r['nt']} slices of the workload per step, {r['n']} steps"
+    other = "taylor3" if args.mode == "frechet" else "frechet"
+    out = {"metric": METRIC, "value": r["val"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": desc, "mode": args.mode,
-                      "note": "C restatement of the Julia reference (oracle/qoc_ref.c), not Julia: no julia toolchain in the image; "
-                              "OpenMP over the per-slice expm loop as Threads.@threads in the reference, serial sweeps"},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample},
-           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "config": headline_config(r["desc"], args.mode, world, {"l2": r["l2"]}),   # same keys and values as the GPU arm
+           "reference_note": REF_NOTE + ("; mode 'frechet' = the exact Frechet derivative (Al-Mohy-Higham), which the reference "
+                                         "does not have: the like-for-like reference-as-shipped number is the `taylor3` entry "
+                                         "(dUkdp_order = 3, src/gradient_computations.jl:35)"),
+           "cpu_baseline": {"value": r["val"], "unit": UNIT, "cores": r["nth"], "kind": "port", "sample": sample},
+           "e2e": {"value": r["val"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           other: {"value": res[other]["val"], "unit": UNIT, "ms_per_step": res[other]["ms"], "mode": other,
+                   "steps": res[other]["n"], "e2e": {"value": res[other]["val"], "unit": UNIT}},
            "gpu_launches": 0}
     print(json.dumps(out))
     return 0
 
 
-def run_time_sharded(args, rank, world, local_rank, order):
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """Per-process bench context (device, ranks, library)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import qoc_b200 as q
+        from qoc_b200 import _lib
+        self.torch, self.dist, self.q = torch, dist, q
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _lib.load()
+        self.peak, self.peak_src = fp64_peak_tflops()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+
+def k1_name(d, nc):
+    if d <= 9 and nc <= 4 and os.environ.get("QOC_NO_K1S") != "1":
+        return ("k1s_kernel (warp-level small-dimension form: expm + Jacobians + segment scan; scalar DFMA, the peak is still the "
+                "measured FP64 tensor-pipe figure)")
+    if d > 28:
+        return "general-path batched DMMA GEMM chain (expm + Jacobians + segment products)"
+    return "k1_kernel (expm + Jacobians + segment scan)"
+
+
+def measure(cx, name, mode, steps, warmup, *, clocks=False, pageable=False, sustained_s=0.0, batch_override=None,
+            budget_s=None):
+    """One workload, one mode, on this rank's GPU (every rank runs it; times are max over ranks).
+    budget_s: cap on the timed device region (heavy configs run fewer, never fewer than 2, steps)."""
+    torch, q, lib = cx.torch, cx.q, cx.lib
+    order = 0 if mode == "frechet" else 3
+    cfg, u, batch, desc = build_workload(name, cx.rank, mode, batch_override)
+    nc, nt = u.shape[-2], u.shape[-1]
+    d, m = cfg["A0"].shape[0], cfg["x0"].shape[1]
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (nc, nt), batch=batch, device=cx.local_rank, dUkdp_order=order,
+                                store_costates=False)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"]) if cfg["cost"] == 0 else q.setup_infidelity_abs_trace(cfg["T"])
+    # two host-API evaluations: the first creates the handle and uploads the constants, the second is timed to size the run;
+    # both are full steps of the same kernels on the same data and count as warm-up steps
+    J0, g0 = q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], cost[1], dUkdp_order=order)
+    t0 = time.perf_counter()
+    J0, g0 = q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], cost[1], dUkdp_order=order)
+    t_est = time.perf_counter() - t0
+    h = cache.handle
+    launches_per_step = cache.launch_count()
+    alg_flops_total = cache.alg_flops()
+    exec_flops_k1 = cache.exec_flops()
+    if budget_s is not None:
+        steps = int(max(2, min(steps, math.floor(budget_s / max(t_est, 1e-6)))))
+        steps = int(cx.max_over_ranks(-steps)[0] * -1)   # every rank the same count (the smallest)
+    dev_warm = max(1, warmup - 2)
+
+    from qoc_b200.grape import _u_arr
+    u_host = _u_arr(u, cache)
+    # a ring of input buffers resident in HBM (the step's working set is its own U_k / dU_k slots: see config.l2)
+    d_us = [torch.from_numpy(u_host).to(cx.dev) for _ in range(4)]
+    d_J = torch.zeros(batch, dtype=torch.float64, device=cx.dev)
+    d_g = torch.zeros(u_host.shape, dtype=torch.float64, device=cx.dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device(i):
+        rc = lib.qoc_eval_device(h, C.c_void_p(d_us[i % 4].data_ptr()), C.c_void_p(d_J.data_ptr()),
+                                 C.c_void_p(d_g.data_ptr()), C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(lib.qoc_last_error(h).decode())
+
+    for i in range(dev_warm):
+        step_device(i)
+    cx.barrier()
+    sampler = None
+    if clocks:
+        sampler = ClockSampler(cx.local_rank)
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.barrier()
+    e0.record(stream)
+    for i in range(steps):
+        step_device(i)
+    e1.record(stream)
+    cx.barrier()
+    ms = e0.elapsed_time(e1)
+    # sanity: the device path reproduces the host-API numbers
+    Jd = d_J.cpu().numpy()
+    assert np.allclose(Jd, np.atleast_1d(J0), atol=1e-12), "device-resident path disagrees with the host-API path"
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    dp = C.POINTER(C.c_double)
+    u_pin = torch.from_numpy(u_host).pin_memory()
+    J_pin = torch.zeros(batch, dtype=torch.float64).pin_memory()
+    g_pin = torch.zeros(u_host.shape, dtype=torch.float64).pin_memory()
+
+    def e2e_loop(pu, pJ, pg, n):
+        for _ in range(1 if budget_s is not None else 3):
+            rc = lib.qoc_eval(h, pu, pJ, pg)
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            rc = lib.qoc_eval(h, pu, pJ, pg)
+            if rc != 0:
+                raise RuntimeError(lib.qoc_last_error(h).decode())
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    e2e_steps = steps if budget_s is None else max(1, steps // 2)
+    e2e_s = e2e_loop(C.cast(u_pin.data_ptr(), dp), C.cast(J_pin.data_ptr(), dp), C.cast(g_pin.data_ptr(), dp), e2e_steps)
+    assert np.allclose(J_pin.numpy(), np.atleast_1d(J0), atol=1e-12)
+    e2e_page_s = None
+    if pageable:   # what a Julia Matrix{Float64} is: ordinary pageable host memory
+        u_pg, J_pg, g_pg = np.array(u_host, copy=True), np.zeros(batch), np.zeros(u_host.shape)
+        e2e_page_s = e2e_loop(u_pg.ctypes.data_as(dp), J_pg.ctypes.data_as(dp), g_pg.ctypes.data_as(dp), e2e_steps)
+    clk = sampler.stop() if sampler else None
+
+    # ---- per-stage device times (CUDA events inside the library, on the launching stream) ----
+    cache.set_profiling(True)
+    stage = np.zeros(3)
+    nprof = max(1, min(10, steps)) if budget_s is None else 1
+    for i in range(nprof):
+        step_device(i)
+        torch.cuda.synchronize()
+        stage += np.array(cache.stage_ms())
+    stage /= nprof
+    cache.set_profiling(False)
+
+    sus = None
+    if sustained_s > 0:   # the same step back to back for >= sustained_s seconds, with its own clock record
+        n_sus = int(math.ceil(sustained_s / (ms / steps * 1e-3)))
+        cx.barrier()
+        s2 = ClockSampler(cx.local_rank)
+        s2.start()
+        e0.record(stream)
+        for i in range(n_sus):
+            step_device(i)
+        e1.record(stream)
+        cx.barrier()
+        sms = e0.elapsed_time(e1)
+        sus = {"steps": n_sus, "seconds": sms * 1e-3, "ms_per_step": sms / n_sus, "clocks": s2.stop()}
+
+    ms, e2e_s = cx.max_over_ranks(ms, e2e_s)
+    if e2e_page_s is not None:
+        e2e_page_s = cx.max_over_ranks(e2e_page_s)[0]
+    units = nt * batch * cx.world
+    value = units * steps / (ms * 1e-3)
+    sweep = (8.0 * d * d * m * (2 + nc) + 4.0 * nc * d * d) * nt * batch
+    k1_flops = alg_flops_total - sweep
+    k1_tflops = k1_flops / (stage[0] * 1e-3) * 1e-12
+    roofline = {"bound": "tensor", "kernel": k1_name(d, nc), "achieved": k1_tflops, "peak": cx.peak, "unit": "TFLOP/s",
+                "frac": k1_tflops / cx.peak, "traffic": ncu_traffic_bytes("k1", name), "peak_source": cx.peak_src,
+                "k1_ms": float(stage[0]), "k2_ms": float(stage[1]), "k3_ms": float(stage[2]),
+                "alg_flops_per_step": alg_flops_total, "k1_share_of_step": float(stage[0] / stage.sum()),
+                # what the FP64 tensor pipe actually ran (zero-padded DMMA tiles, 3M or real-plane products): on the
+                # real-Hamiltonian path of K1 most complex products collapse to one real product, so the algorithmic
+                # figure above is not a pipe-occupancy figure -- this one is
+                "k1_executed_dmma_tflops": exec_flops_k1 / (stage[0] * 1e-3) * 1e-12 if exec_flops_k1 > 0 else None,
+                "k1_executed_frac": exec_flops_k1 / (stage[0] * 1e-3) * 1e-12 / cx.peak if exec_flops_k1 > 0 else None,
+                "whole_step_tflops": alg_flops_total * steps / (ms * 1e-3) * 1e-12,
+                "whole_step_frac": alg_flops_total * steps / (ms * 1e-3) * 1e-12 / cx.peak}
+    e2e = {"value": units * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(u_host.nbytes),
+           "d2h_bytes_per_step": int(J_pin.numel() * 8 + g_pin.numel() * 8), "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "host_buffers": "pinned"}
+    if e2e_page_s is not None:
+        e2e["pageable"] = {"value": units * e2e_steps / e2e_page_s, "ms_per_step": 1e3 * e2e_page_s / e2e_steps,
+                           "note": "same call with ordinary pageable host arrays (what a Julia Matrix{Float64} is)"}
+    res = {"workload": desc, "mode": mode, "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "warmup": f"{dev_warm} device-resident + 2 host-API evaluations of the same step",
+           "e2e": e2e, "roofline": roofline, "gpu_launches": int(launches_per_step * steps * cx.world),
+           "launches_per_step": int(launches_per_step), "l2": l2_note(d, nt, batch, nc), "J": float(np.atleast_1d(J0)[0])}
+    if clk is not None:
+        res["clocks"] = clk
+    if sus is not None:
+        sus["value"] = units / (sus["ms_per_step"] * 1e-3)
+        res["sustained"] = sus
+    cache.close()
+    del d_us, d_J, d_g
+    torch.cuda.empty_cache()
+    return res, cfg, u, batch
+
+
+def brief(r):
+    """The per-config record kept in `configs`."""
+    rf = r["roofline"]
+    return {"workload": r["workload"], "mode": r["mode"], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+            "steps": r["steps"], "e2e": {k: r["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+            "roofline": {"frac": rf["frac"], "achieved_tflops": rf["achieved"], "k1_ms": rf["k1_ms"], "k2_ms": rf["k2_ms"],
+                         "k3_ms": rf["k3_ms"], "whole_step_frac": rf["whole_step_frac"], "kernel": rf["kernel"].split(" (")[0]},
+            "launches_per_step": r["launches_per_step"], "J": r["J"]}
+
+
+def run_time_sharded(cx, name, mode, steps, warmup):
     """ONE pulse of the workload split into `world` contiguous time segments: per step, phase 1 on the
     local slices, NCCL all-gather of the d x d rank propagators, redundant boundary algebra, local sweeps, all-gather of
-    the gradient segments.  Strong scaling: total work is fixed."""
-    import torch
-    import torch.distributed as dist
-    import qoc_b200 as q
+    the gradient segments.  Strong scaling: total work is fixed.  Returns the record and asserts parity with the
+    single-GPU evaluation of the same pulse (computed on rank 0, broadcast)."""
+    torch, dist, q = cx.torch, cx.dist, cx.q
     from qoc_b200 import sharding
-    cfg, u, batch, desc = build_workload(args.workload, 0, args.mode)
-    if batch != 1:
-        raise SystemExit("--shard time needs a single-pulse workload")
-    nt = u.shape[1]
-    lo, hi = sharding.time_partition(nt, world, rank)
-    eng = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, cfg["x0"].shape[1], local_rank, order=order)
-    cost = q.setup_infidelity(cfg["T"], cfg["n"])[1] if cfg["cost"] == 0 else q.setup_infidelity_abs_trace(cfg["T"])[1]
-    ev = sharding.TimeShardedEvaluator(eng, cfg["x0"], cost, nt)
-    for _ in range(args.warmup):
+    order = 0 if mode == "frechet" else 3
+    cfg, u, batch, desc = build_workload(name, 0, mode)
+    nt, nc = u.shape[1], u.shape[0]
+    lo, hi = sharding.time_partition(nt, cx.world, cx.rank)
+    eng = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, cfg["x0"].shape[1], cx.local_rank, order=order)
+    costp = q.setup_infidelity(cfg["T"], cfg["n"]) if cfg["cost"] == 0 else q.setup_infidelity_abs_trace(cfg["T"])
+    ev = sharding.TimeShardedEvaluator(eng, cfg["x0"], costp[1], nt)
+    for _ in range(warmup):
         J, g = ev.evaluate(u)
-    dist.barrier(); torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank); sampler.start()
+    cx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier(); torch.cuda.synchronize()
+    cx.barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         J, g = ev.evaluate(u)
     e1.record()
-    dist.barrier(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
-    value = nt * args.steps / (ms * 1e-3)
-    if rank == 0:
-        d = cfg["A0"].shape[0]
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc.replace("per GPU", "time-sharded over all GPUs"), "mode": args.mode,
-                       "parallelism": f"time-segment sharded x{world}: all-gather of {world} rank propagators "
-                                      f"({16 * d * d} B each) + all-gather of gradient segments per step"},
-            "clocks": clocks,
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(8 * u[:, lo:hi].size),
-                    "d2h_bytes_per_step": int(8 * u.size + 8),
-                    "note": "the sharded evaluator is host-driven: u enters from host memory and J, dJdu return to it every step"},
-            # per rank and step: K1, K2G (rank propagator), boundary kernel, K2G (local scan), K3N
-            "gpu_launches": int(5 * args.steps * world), "J": J}))
-    dist.destroy_process_group()
-    return 0
+    cx.barrier()
+    ms = cx.max_over_ranks(e0.elapsed_time(e1))[0]
+    # ---- parity on REAL ranks: the single-GPU evaluation of the same pulse, on rank 0, broadcast to everybody ----
+    ref = torch.zeros(1 + nc * nt, dtype=torch.float64, device=cx.dev)
+    ms1 = 0.0
+    if cx.rank == 0:
+        cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (nc, nt), device=cx.local_rank, dUkdp_order=order, store_costates=False)
+        J1, g1 = q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], costp[1], dUkdp_order=order)
+        t0 = time.perf_counter()
+        J1, g1 = q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], costp[1], dUkdp_order=order)
+        ms1 = 1e3 * (time.perf_counter() - t0)
+        ref[0] = J1
+        ref[1:] = torch.from_numpy(np.ascontiguousarray(g1).reshape(-1)).to(cx.dev)
+        cache.close()
+    dist.broadcast(ref, 0)
+    refh = ref.cpu().numpy()
+    J1, g1 = float(refh[0]), refh[1:].reshape(nc, nt)
+    dJ = abs(J - J1)
+    dg = float(np.abs(g - g1).max() / np.abs(g1).max())
+    ok = dJ <= TOL_J * max(1.0, abs(J1)) and dg <= TOL_G
+    okall = cx.max_over_ranks(0.0 if ok else 1.0)[0] == 0.0
+    d = cfg["A0"].shape[0]
+    rec = {"workload": desc.replace("single pulse per GPU", f"ONE pulse time-segment sharded over {cx.world} GPUs"), "mode": mode,
+           "value": nt * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "scaling": "strong",
+           "collectives": f"all-gather of {cx.world} rank propagators ({16 * d * d} B each) + all-gather of the gradient segments "
+                          f"({8 * nc * (hi - lo)} B each) per step, NCCL",
+           "single_gpu_ms_per_step_host_api": ms1 if cx.rank == 0 else None,
+           "parity": {"vs": "single-GPU evaluation of the same pulse (rank 0)", "abs_dJ": dJ, "rel_dg_max": dg,
+                      "tol_J": TOL_J, "tol_g": TOL_G, "ok_all_ranks": bool(okall)},
+           "J": J, "gpu_launches": int(5 * steps * cx.world)}
+    assert okall, f"time-sharded result disagrees with the single-GPU evaluation: |dJ|={dJ:.3e} rel|dg|={dg:.3e} ({name}, {mode})"
+    del ev, eng
+    torch.cuda.empty_cache()
+    return rec
+
+
+# every other BASELINE.json config: (workload, per-mode device-time budget in seconds)
+CONFIGS_N1 = [("zz", None), ("cavity", None), ("cavity20", None), ("cavity40", None), ("zz_batch", None),
+              ("synth16x100000", 3.0), ("synth32x100000", 3.0), ("synth64x100000", 4.0), ("synth128x100000", 8.0)]
 
 
 def main():
@@ -279,165 +543,94 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="frechet", choices=["frechet", "taylor3"])
     ap.add_argument("--workload", default="bus",
-                    help="bus (default, BASELINE configs[1]) | zz_batch | cavity | cavity<N_cavity> | synth<d>x<Nt>")
+                    help="bus (default, BASELINE configs[1]) | zz | zz_batch | cavity | cavity<N_cavity> | synth<d>x<Nt>")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline only (skip the configs / strong blocks)")
+    ap.add_argument("--configs", default=None, help="comma-separated workloads for the configs block (default: all of BASELINE.json)")
     ap.add_argument("--shard", default="batch", choices=["batch", "time"],
-                    help="N>1: 'batch' = one pulse per rank, no collective (weak scaling, default); "
-                         "'time' = ONE pulse split into time segments, NCCL all-gather of rank propagators (strong scaling)")
+                    help="N>1: 'batch' = one pulse per rank, no collective (weak scaling, default; the `strong` block still reports "
+                         "the time-sharded pulse); 'time' = the headline itself is ONE pulse split into time segments")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
-    import qoc_b200 as q
-    from qoc_b200 import _lib
+    cx = Ctx()
+    other = "taylor3" if args.mode == "frechet" else "frechet"
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.shard == "time" and cx.world > 1:
+        rec = run_time_sharded(cx, args.workload, args.mode, args.steps, args.warmup)
+        if cx.rank == 0:
+            out = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": cx.world, "steps": args.steps,
+                   "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                   "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                   "config": {"workload": rec["workload"], "mode": args.mode, "parallelism": rec["collectives"]},
+                   "e2e": {"value": rec["value"], "unit": UNIT, "note": "the sharded evaluator is host-driven: u enters from host "
+                           "memory and J, dJdu return to it every step"},
+                   "parity": rec["parity"], "gpu_launches": rec["gpu_launches"], "J": rec["J"]}
+            print(json.dumps(out))
+        cx.dist.destroy_process_group()
+        return 0
 
-    order = 0 if args.mode == "frechet" else 3
-    if args.shard == "time" and world > 1:
-        return run_time_sharded(args, rank, world, local_rank, order)
-    cfg, u, batch, desc = build_workload(args.workload, rank, args.mode)
-    nc, nt = u.shape[-2], u.shape[-1]
-    lib = _lib.load()
-    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (nc, nt), batch=batch, device=local_rank, dUkdp_order=order,
-                                store_costates=False)
-    cost = q.setup_infidelity(cfg["T"], cfg["n"]) if cfg["cost"] == 0 else q.setup_infidelity_abs_trace(cfg["T"])
-    # one host-API evaluation creates the handle, uploads constants and gives the numbers to sanity-check
-    J0, g0 = q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], cost[1], dUkdp_order=order)
-    h = cache.handle
-    launches_per_step = cache.launch_count()
-    alg_flops_total = cache.alg_flops()
-    exec_flops_k1 = cache.exec_flops()
-
-    from qoc_b200.grape import _u_arr
-    u_host = _u_arr(u, cache)
-    dev = torch.device("cuda", local_rank)
-    # a ring of input buffers resident in HBM; each step's working set (U_k + dU_k/du_j slots) is far larger than L2
-    d_us = [torch.from_numpy(u_host).to(dev) for _ in range(4)]
-    d_J = torch.zeros(batch, dtype=torch.float64, device=dev)
-    d_g = torch.zeros(u_host.shape, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
-
-    def step_device(i):
-        rc = lib.qoc_eval_device(h, C.c_void_p(d_us[i % 4].data_ptr()), C.c_void_p(d_J.data_ptr()),
-                                 C.c_void_p(d_g.data_ptr()), C.c_void_p(stream.cuda_stream))
-        if rc != 0:
-            raise RuntimeError(lib.qoc_last_error(h).decode())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        step_device(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for i in range(args.steps):
-        step_device(i)
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # sanity: the device path reproduces the host-API numbers
-    Jd = d_J.cpu().numpy()
-    assert np.allclose(Jd, np.atleast_1d(J0), atol=1e-12), "device-resident path disagrees with the host-API path"
-
-    # ---- e2e: host buffers through the C ABI (pinned), copies inside the timed region ----
-    u_pin = torch.from_numpy(u_host).pin_memory()
-    J_pin = torch.zeros(batch, dtype=torch.float64).pin_memory()
-    g_pin = torch.zeros(u_host.shape, dtype=torch.float64).pin_memory()
-    dp = C.POINTER(C.c_double)
-
-    def step_host():
-        rc = lib.qoc_eval(h, C.cast(u_pin.data_ptr(), dp), C.cast(J_pin.data_ptr(), dp), C.cast(g_pin.data_ptr(), dp))
-        if rc != 0:
-            raise RuntimeError(lib.qoc_last_error(h).decode())
-
-    for _ in range(3):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
-
-    # ---- per-stage device times of the dominant kernels (CUDA events inside the library, launching stream) ----
-    cache.set_profiling(True)
-    stage = np.zeros(3)
-    nprof = max(3, min(10, args.steps))
-    for i in range(nprof):
-        step_device(i)
-        torch.cuda.synchronize()
-        stage += np.array(cache.stage_ms())
-    stage /= nprof
-    cache.set_profiling(False)
-
-    if world > 1:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
-
-    units_per_step = nt * batch * world
-    value = units_per_step * args.steps / (ms * 1e-3)
-    e2e_value = units_per_step * args.steps / e2e_s
-    peak, peak_src = fp64_peak_tflops()
-    sweep = (8.0 * cfg["A0"].shape[0] ** 2 * cfg["x0"].shape[1] * (2 + nc) + 4.0 * nc * cfg["A0"].shape[0] ** 2) * nt * batch
-    k1_flops = alg_flops_total - sweep
-    k1_tflops = k1_flops / (stage[0] * 1e-3) * 1e-12
-    dd = cfg["A0"].shape[0]
-    k1_name = ("k1s_kernel (warp-per-slice small-dimension form: expm + Jacobians + segment scan; scalar DFMA, the peak is still the "
-               "measured FP64 tensor-pipe figure)" if (dd <= 9 and nc <= 4 and os.environ.get("QOC_NO_K1S") != "1")
-               else "general-path batched DMMA GEMM chain (expm + Jacobians + segment products)" if dd > 28
-               else "k1_kernel (expm + Jacobians + segment scan)")
-    roofline = {"bound": "tensor", "kernel": k1_name,
-                "achieved": k1_tflops, "peak": peak, "unit": "TFLOP/s", "frac": k1_tflops / peak,
-                "traffic": ncu_traffic_bytes("k1_kernel", args.workload),
-                "peak_source": peak_src, "k1_ms": float(stage[0]), "k2_ms": float(stage[1]), "k3_ms": float(stage[2]),
-                "alg_flops_per_step": alg_flops_total, "k1_share_of_step": float(stage[0] / stage.sum()),
-                # what the FP64 tensor pipe actually ran (zero-padded DMMA tiles, 3M or real-plane products): on the
-                # real-Hamiltonian path of K1 most complex products collapse to one real product, so the algorithmic
-                # figure above is no longer a pipe-occupancy figure -- this one is
-                "k1_executed_dmma_tflops": exec_flops_k1 / (stage[0] * 1e-3) * 1e-12 if exec_flops_k1 > 0 else None,
-                "k1_executed_frac": exec_flops_k1 / (stage[0] * 1e-3) * 1e-12 / peak if exec_flops_k1 > 0 else None,
-                "whole_step_tflops": alg_flops_total * args.steps / (ms * 1e-3) * 1e-12 / world * world}
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    # ---- headline ----
+    head, cfg, u, batch = measure(cx, args.workload, args.mode, args.steps, args.warmup, clocks=True, pageable=True,
+                                  sustained_s=2.0)
+    out = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": cx.world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": desc, "mode": args.mode, "parallelism": f"pulse-sharded x{world}, no collective",
-                      "l2": l2_note(cfg["A0"].shape[0], nt, batch, nc)},
-           "clocks": clocks,
-           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(u_host.nbytes),
-                   "d2h_bytes_per_step": int(J_pin.numel() * 8 + g_pin.numel() * 8), "ms_per_step": 1e3 * e2e_s / args.steps},
-           "gpu_launches": int(launches_per_step * args.steps * world),
-           "roofline": roofline}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        slices, times, nth, npulse = cpu_port_run(cfg, u, batch, order, 0, 3)
-        best = min(times)
-        out["cpu_baseline"] = {"value": slices / best, "unit": UNIT, "cores": nth, "kind": "port",
-                               "sample": f"{npulse} pulse(s) x {nt} slices, best of 3, oracle/qoc_ref.c (C restatement of the Julia "
-                                         f"reference, OpenMP over the expm loop), mode {args.mode}"}
-    if rank == 0:
+           "config": headline_config(head["workload"], args.mode, cx.world, {"l2": head["l2"]}),
+           "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+           "sustained": head["sustained"]}
+    # the same workload in the other gradient mode (taylor3 = the reference's default dUkdp_order, the only mode with a
+    # reference-defined 1e-8 bar)
+    oth, _, _, _ = measure(cx, args.workload, other, args.steps, args.warmup)
+    out[other] = brief(oth)
+
+    if cx.rank == 0 and cx.world == 1 and not args.no_cpu_baseline:
+        cb = {}
+        for mode in (args.mode, other):
+            slices, times, nth, npulse = cpu_port_run(cfg, u, batch, 0 if mode == "frechet" else 3, 0, 3)
+            cb[mode] = {"value": slices / min(times), "unit": UNIT, "cores": nth, "kind": "port",
+                        "sample": f"{npulse} pulse(s) x {u.shape[-1]} slices, best of 3, oracle/qoc_ref.c (C restatement of the "
+                                  f"Julia reference, OpenMP over the expm loop), mode {mode}"}
+        out["cpu_baseline"] = cb[args.mode]
+        out["cpu_baseline"][other] = {k: cb[other][k] for k in ("value", "sample")}
+
+    if not args.no_configs:
+        if cx.world == 1:
+            todo = CONFIGS_N1 if args.configs is None else [(w, 4.0 if w.startswith("synth") else None) for w in args.configs.split(",") if w]
+            recs = []
+            for wl, budget in todo:
+                if wl == args.workload:
+                    continue
+                for mode in ("frechet", "taylor3"):
+                    try:
+                        r, _, _, _ = measure(cx, wl, mode, args.steps, args.warmup, budget_s=budget)
+                        recs.append(brief(r))
+                    except Exception as e:  # a config that cannot run is reported, not hidden
+                        recs.append({"workload": wl, "mode": mode, "error": f"{type(e).__name__}: {e}"})
+            out["configs"] = recs
+        else:
+            # C4 as BASELINE.json words it: 4096 pulses block-partitioned over the ranks, no communication
+            recs = []
+            per = 4096 // cx.world
+            for mode in ("frechet", "taylor3"):
+                r, _, _, _ = measure(cx, "zz_batch", mode, args.steps, args.warmup, batch_override=per)
+                b = brief(r)
+                b["workload"] = f"C4 zz_coupling d=9 m=4 nc=2 Nt=100, 4096 pulses block-partitioned over {cx.world} GPUs ({per} each), no collective"
+                b["scaling"] = "strong"
+                recs.append(b)
+            out["configs"] = recs
+            strong = []
+            for wl, st in (("bus", args.steps), ("synth64x100000", 3)):
+                for mode in ("frechet", "taylor3"):
+                    strong.append(run_time_sharded(cx, wl, mode, st, 3))
+            out["strong"] = strong
+    if cx.rank == 0:
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
     return 0
 
 

@@ -50,8 +50,13 @@ typedef enum {
 typedef enum {
   QOC_COST_INFIDELITY = 0, /* J = 1 - |tr(T'x)|^2/n^2, dJ_dx = (-2 Omega/n^2) T   src/penalty_fcns.jl:15-24         */
   QOC_COST_ABS_TRACE = 1,  /* J = 1 - |tr(T'x)|,       dJ_dx = -(Omega/|Omega|) T  test/test_gradient_computation.jl:24-25 */
-  QOC_COST_NONE = 2        /* no built-in cost: caller evaluates Jfinal / dJfinal_dx (arbitrary closures) on the
+  QOC_COST_NONE = 2,       /* no built-in cost: caller evaluates Jfinal / dJfinal_dx (arbitrary closures) on the
                               host from x_final and passes lambda_final to qoc_gradient                         */
+  QOC_COST_ZCAL = 3        /* setup_infidelity_zcalibrated (src/penalty_fcns.jl:27-42): m = diag(T'x), four columns,
+                              J = 1 - F^2/16 with F = abs_sum_phase_calibrated(m) maximised over the virtual-Z phase by
+                              the reference's golden-section search (src/fidelities.jl:81-137, tolerance 1e-9),
+                              dJ_dx = (-2F/16) T Diagonal(dF_dm) from its rrule (:48-56).  Evaluated per pulse on the
+                              device: x_final never crosses the bus.  m != 4 -> QOC_ERR_DIMENSION (:28-30).   */
 } qoc_cost;
 
 typedef struct {
@@ -91,6 +96,12 @@ int qoc_destroy(qoc_handle* h);
  * from the cached u); changing the cost does not touch the cached propagation.                               */
 int qoc_set_order(qoc_handle* h, int order);
 int qoc_set_cost(qoc_handle* h, int cost, const double* T, int n);
+/* The reference's propagate computes the matrix exponentials only (src/gradient_computations.jl:17-25) and
+ * grape_sensitivity adds the Jacobians (:65-74).  Default (on = 0): the same split -- qoc_propagate runs K1 without
+ * Jacobians (an f-only call, e.g. a line search, costs about a third of an evaluation) and qoc_gradient re-runs K1 with them
+ * on the cached u.  on != 0: qoc_propagate produces them together with U_k (they share the Pade powers), which is
+ * cheaper when f_grad always follows f.  qoc_eval always does both in one pass.                                  */
+int qoc_set_eager_jacobians(qoc_handle* h, int on);
 
 /* ---- the hot path, host buffers in / host buffers out ------------------------------------------------------ */
 

@@ -83,3 +83,34 @@ int qoc_quad_expm(int d, const double* X, const double* E, double* U, double* L)
   free(w);
   return 0;
 }
+
+/* Serial propagation x <- U_k x, k = 0..nt-1, accumulated in binary128 (the U_k themselves are given in double):
+ * the ground truth against which the REASSOCIATION error of the parallel scans (segment products, two-level boundary
+ * walk, time sharding) is bounded -- SURVEY.md F7.  U: nt matrices, d x d row-major interleaved complex doubles;
+ * x0, x_out: d x m row-major interleaved complex doubles. */
+int qoc_quad_chain(int d, int m, int nt, const double* U, const double* x0, double* x_out) {
+  const int n = d * m;
+  q* w = malloc(sizeof(q) * n * 4);
+  if (!w) return 1;
+  q *xr = w, *xi = xr + n, *yr = xi + n, *yi = yr + n;
+  for (int e = 0; e < n; e++) { xr[e] = x0[2 * e]; xi[e] = x0[2 * e + 1]; }
+  for (int k = 0; k < nt; k++) {
+    const double* Uk = U + (size_t)k * 2 * d * d;
+    for (int i = 0; i < d; i++)
+      for (int c = 0; c < m; c++) {
+        q sr = 0, si = 0;
+        for (int j = 0; j < d; j++) {
+          const q ur = Uk[2 * (i * d + j)], ui = Uk[2 * (i * d + j) + 1];
+          sr += ur * xr[j * m + c] - ui * xi[j * m + c];
+          si += ur * xi[j * m + c] + ui * xr[j * m + c];
+        }
+        yr[i * m + c] = sr;
+        yi[i * m + c] = si;
+      }
+    q* t = xr; xr = yr; yr = t;
+    t = xi; xi = yi; yi = t;
+  }
+  for (int e = 0; e < n; e++) { x_out[2 * e] = (double)xr[e]; x_out[2 * e + 1] = (double)xi[e]; }
+  free(w);
+  return 0;
+}

@@ -44,3 +44,21 @@ def expm_quad(X, E=None):
     rc = _lib.qoc_quad_expm(d, X.ctypes.data_as(dp), E.ctypes.data_as(dp), U.ctypes.data_as(dp), L.ctypes.data_as(dp))
     assert rc == 0
     return U, L
+
+
+def chain_quad(U, x0):
+    """x_N = U_{N-1} ... U_0 x0 with the products accumulated in binary128 (U_k given in double) -> complex128."""
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.qoc_quad_expm.restype = C.c_int
+    U = np.ascontiguousarray(U, dtype=np.complex128)
+    x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.complex128).reshape(U.shape[1], -1))
+    nt, d, m = U.shape[0], U.shape[1], x0.shape[1]
+    out = np.zeros((d, m), dtype=np.complex128)
+    dp = C.POINTER(C.c_double)
+    _lib.qoc_quad_chain.restype = C.c_int
+    rc = _lib.qoc_quad_chain(d, m, nt, U.ctypes.data_as(dp), x0.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert rc == 0
+    return out

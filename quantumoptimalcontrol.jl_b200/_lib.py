@@ -10,7 +10,7 @@ from . import build as _build
 OK, ERR_INVALID, ERR_DIMENSION, ERR_STALE_CACHE, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_FINITE, \
     ERR_SINGULAR = range(9)
 ORDER_FRECHET = 0
-COST_INFIDELITY, COST_ABS_TRACE, COST_NONE = 0, 1, 2
+COST_INFIDELITY, COST_ABS_TRACE, COST_NONE, COST_ZCAL = 0, 1, 2, 3
 
 
 class Problem(C.Structure):
@@ -30,6 +30,7 @@ SYMBOLS = {
     "qoc_destroy": (C.c_int, [_vp]),
     "qoc_set_order": (C.c_int, [_vp, C.c_int]),
     "qoc_set_cost": (C.c_int, [_vp, C.c_int, _dp, C.c_int]),
+    "qoc_set_eager_jacobians": (C.c_int, [_vp, C.c_int]),
     "qoc_propagate": (C.c_int, [_vp, _dp, _dp, _dp]),
     "qoc_gradient": (C.c_int, [_vp, _dp, _dp, _dp]),
     "qoc_eval": (C.c_int, [_vp, _dp, _dp, _dp]),
@@ -67,9 +68,9 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
+    if _build.needs_build():   # missing, or built from other sources than the ones in the tree (content hash)
         if not build_if_missing:
-            raise FileNotFoundError(path + " missing: run `python __graft_entry__.py build`")
+            raise FileNotFoundError(path + " missing or stale: run `python __graft_entry__.py build`")
         _build.build()
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():

@@ -17,11 +17,26 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "--cudart", "static"]
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over the sources and the flags: content, not mtimes (the gpurun snapshot does not promise to keep mtimes, and N
+    ranks of one torchrun must agree on whether the shipped binary is current)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + sorted(HEADERS):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -29,12 +44,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, LIB)   # atomic: a concurrent loader sees the old or the new library, never a torn one
+    with open(STAMP + f".tmp{os.getpid()}", "w") as fh:
+        fh.write(source_hash())
+    os.replace(STAMP + f".tmp{os.getpid()}", STAMP)
     return LIB
 
 

@@ -231,8 +231,8 @@ def config_cavity(N_cavity=12, Nt=550, csv_path=None):
     """C3: test/test_gradient_computation.jl:7-35 set-up (Tc/2, two state columns, J = 1-|tr(T'x)|)."""
     H0, Tc, _x0, theta = model_cavity_qubit(N_cavity)
     if csv_path is None:
-        csv_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden",
-                                "cavity_qubit_pulse.txt")
+        # the reference's shipped pulse (examples/cavity_qubit_pulse_marina.csv), kept as package data
+        csv_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "cavity_qubit_pulse.txt")
     u = load_pulse_csv(csv_path)[:, :Nt]
     A0, A1, A2 = setup_bilinear_matrices(H0, Tc / 2, 1.0)
     nrm = lambda v: v / np.linalg.norm(v)

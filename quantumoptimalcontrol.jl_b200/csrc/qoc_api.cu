@@ -49,6 +49,7 @@ struct qoc_handle {
   int gchunk = 0, gnw = 0;
   double* gW = nullptr;       // workspace: gnw slots x gchunk slices
   double* dumax = nullptr;    // max_k |u_jk| per control
+  int* dpiv = nullptr;        // pivot rows of the blocked Gauss-Jordan inverse: gchunk x d
   double* dbnd = nullptr;     // time sharding: x_start and lambda_end of the local segment (2 x d x m c128)
   double *dB = nullptr, *dc = nullptr, *ddc = nullptr;   // spline basis, coefficients, dJ/dc (qoc_set_basis / qoc_eval_coeffs)
   int ns = 0;
@@ -73,6 +74,8 @@ struct qoc_handle {
   std::vector<double> last_u;
   bool have_u = false;       // a propagate() happened (cache valid)
   bool have_jac = false;
+  bool eager_jac = false;    // qoc_propagate also produces dU_k/du_j (qoc_set_eager_jacobians); default: like the reference's
+                             // propagate (:17-29), expm only -- qoc_gradient / qoc_get_jacobians add them on demand
   bool states_valid = false, costates_valid = false;
   int launches = 0;
   bool profiling = false;
@@ -188,7 +191,7 @@ extern "C" const char* qoc_status_string(int s) {
 }
 extern "C" const char* qoc_last_error(const qoc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 extern "C" int qoc_last_launch_count(const qoc_handle* h) { return h ? h->launches : 0; }
-extern "C" int qoc_version(void) { return 101; }   // 101: + qoc_last_exec_flops
+extern "C" int qoc_version(void) { return 200; }   // 200: round 2 (lazy Jacobians, z-calibrated cost, in-library sharding)
 extern "C" int qoc_set_profiling(qoc_handle* h, int on) {
   if (!h) return QOC_ERR_INVALID;
   h->profiling = on != 0;
@@ -210,6 +213,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->dstatus) cudaFree(h->dstatus);
   if (h->h_mail) cudaFreeHost(h->h_mail);
   if (h->dsync) cudaFree(h->dsync);
+  if (h->dpiv) cudaFree(h->dpiv);
   if (h->dpen_rows) cudaFree(h->dpen_rows);
   if (h->dpen_cols) cudaFree(h->dpen_cols);
   for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
@@ -226,7 +230,11 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   const qoc_problem& p = *prob;
   if (p.d <= 0 || p.m <= 0 || p.nc <= 0 || p.nt <= 0 || p.batch <= 0) { g_create_error = "non-positive size"; return QOC_ERR_DIMENSION; }
   if (p.order < 0 || p.order > 4) { g_create_error = "order must be 0 (Frechet) or 1..4"; return QOC_ERR_INVALID; }
-  if (p.cost < 0 || p.cost > 2) { g_create_error = "unknown cost kind"; return QOC_ERR_INVALID; }
+  if (p.cost < 0 || p.cost > 3) { g_create_error = "unknown cost kind"; return QOC_ERR_INVALID; }
+  if (p.cost == QOC_COST_ZCAL && p.m != 4) {   // src/penalty_fcns.jl:28-30
+    g_create_error = "Only works for two-qubit gates, x_target must have four columns";
+    return QOC_ERR_DIMENSION;
+  }
   if (p.cost != QOC_COST_NONE && !T) { g_create_error = "built-in cost needs a target T"; return QOC_ERR_INVALID; }
   if (p.m > 8) { g_create_error = "m > 8 state columns not supported yet"; return QOC_ERR_UNSUPPORTED; }
   if (p.nc > 8) { g_create_error = "nc > 8 controls not supported yet"; return QOC_ERR_UNSUPPORTED; }
@@ -254,7 +262,17 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     const size_t need = with_cfg(cfg, [&](auto c) -> size_t { typedef decltype(c) C; return k1_smem_bytes(p.d, p.nc, C::S, k1_pad_rows<C>(p.d)); });
     if (need > (size_t)dp.sharedMemPerBlockOptin) use_gpath = true;
   }
-  if (use_gpath) cfg = 5;
+  if (use_gpath) {
+    cfg = 5;
+    // dynamic shared memory of the general-path sweep kernels (gs_scan / gs_seg: two interleaved states; gs_contract: x_k and
+    // lambda_{k+1}; g_sweep: three planar states; shard_boundary: two column-major states): rejected here, not at launch
+    const size_t need = (size_t)6 * (p.d + 8) * p.m * 8 > (size_t)(2 * p.d + 8) * 2 * p.m * 8 ? (size_t)6 * (p.d + 8) * p.m * 8
+                                                                                          : (size_t)(2 * p.d + 8) * 2 * p.m * 8;
+    if (need > (size_t)dp.sharedMemPerBlockOptin) {
+      g_create_error = "d x m state working set of the general-path sweeps exceeds shared memory";
+      return QOC_ERR_UNSUPPORTED;
+    }
+  }
   qoc_handle* h = new qoc_handle();
   h->prob = p;
   if (h->prob.n <= 0) h->prob.n = p.m;
@@ -295,10 +313,12 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
       }
     }
     h->k1_smem = h->k2_smem = h->k3_smem = 0;
-    h->gnw = 24 + p.nc;
+    h->gnw = 25 + p.nc;
     const size_t slotBg = (size_t)h->slot_d * 8;
-    size_t chunk = (size_t)(1536ull << 20) / ((size_t)h->gnw * slotBg);   // ~1.5 GB of workspace
-    if (chunk < 1) chunk = 1;
+    // workspace: up to ~8 GB (an HBM3e part has 180), at least two slices per SM so that the one-CTA-per-slice kernels
+    // (Gauss-Jordan panels) fill the chip; d = 256: 296 slices = 8.2 GB, d = 64: 2048 slices = 3.7 GB
+    size_t chunk = (size_t)(8192ull << 20) / ((size_t)h->gnw * slotBg);
+    if (chunk < (size_t)2 * dp.multiProcessorCount) chunk = (size_t)2 * dp.multiProcessorCount;
     if (chunk > 2048) chunk = 2048;
     if (chunk > (size_t)p.batch * p.nt) chunk = (size_t)p.batch * p.nt;
     h->gchunk = (int)chunk;
@@ -476,6 +496,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     CR(cudaSetDevice(p.device));
     CR(cudaMalloc(&h->gW, (size_t)h->gnw * h->gchunk * slotB));
     CR(cudaMalloc(&h->dumax, 8 * 8));
+    CR(cudaMalloc(&h->dpiv, (size_t)h->gchunk * p.d * 4));
   }
   if (h->new_k2) {
     CR(cudaMalloc(&h->dPg, (size_t)p.batch * h->G * slotB));
@@ -508,9 +529,18 @@ extern "C" int qoc_set_order(qoc_handle* h, int order) {
   if (order != h->prob.order) { h->prob.order = order; h->have_jac = false; }
   return QOC_OK;
 }
+extern "C" int qoc_set_eager_jacobians(qoc_handle* h, int on) {
+  if (!h) return QOC_ERR_INVALID;
+  h->eager_jac = on != 0;
+  return QOC_OK;
+}
 extern "C" int qoc_set_cost(qoc_handle* h, int cost, const double* T, int n) {
   if (!h) return QOC_ERR_INVALID;
-  if (cost < 0 || cost > 2) { h->err = "unknown cost kind"; return QOC_ERR_INVALID; }
+  if (cost < 0 || cost > 3) { h->err = "unknown cost kind"; return QOC_ERR_INVALID; }
+  if (cost == QOC_COST_ZCAL && h->prob.m != 4) {   // src/penalty_fcns.jl:28-30
+    h->err = "Only works for two-qubit gates, x_target must have four columns";
+    return QOC_ERR_DIMENSION;
+  }
   if (cost != QOC_COST_NONE && !T) { h->err = "built-in cost needs a target T"; return QOC_ERR_INVALID; }
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
   if (T) QOC_CUDA(h, cudaMemcpy(h->dT, T, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyHostToDevice));
@@ -619,6 +649,10 @@ static int gpath_sweep2(qoc_handle* h, int mode, bool skip_bwd, bool want_grad, 
   g.xs_start = h->dxs; g.lam_end = h->dle; g.X = h->dX; g.LAM = h->dLAM; g.x_final = h->dxf; g.lam_start = h->dlam0;
   g.J = d_J ? d_J : h->dJ; g.dJdu = d_dJdu ? d_dJdu : h->dg;
   const size_t st_smem = (size_t)2 * ((p.d + 7) / 8 * 8) * 2 * p.m * 8;
+  if (st_smem > 40 * 1024) {   // qoc_create checked it against sharedMemPerBlockOptin
+    QOC_CUDA(h, cudaFuncSetAttribute(gs_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
+    QOC_CUDA(h, cudaFuncSetAttribute(gs_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
+  }
   gs_scan_kernel<<<p.batch, GS_NW * 32, st_smem, st>>>(g);
   h->launches++;
   const int grid = h->nseg < h->nsm * 4 ? h->nseg : h->nsm * 4;
@@ -671,7 +705,7 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
   }
   const double pi_q = q == 13 ? 6.0 : q == 7 ? 4.0 : 3.0;
   const double* b = q == 13 ? kB13 : q == 7 ? kB7 : kB5;
-  enum { A = 0, X, A2, A4, A6, W1, Z1, Wm, V, U, R, M2, M4, M6, T1, T2, Lw, Lv, Dd, Ss, RH, TMP, TMPR, L0 };
+  enum { A = 0, X, A2, A4, A6, W1, Z1, Wm, V, U, R, M2, M4, M6, T1, T2, Lw, Lv, Dd, Ss, RH, TMP, TMPR, NI, L0 };
   GRun g{h, st, 0, (d + 31) / 32};
   const GOp A0op{h->dA0p, 0};
   for (size_t c0 = 0; c0 < nsl; c0 += h->gchunk) {
@@ -698,11 +732,11 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
     }
     g.mm1(U, g.W(A), g.W(Wm));
     { GOp D[2] = {g.W(V), g.W(U)}; double be[2] = {1.0, -1.0}; g.lin(V, 2, D, be); }   // N = V - U (in place: elementwise)
-    g_inverse_kernel<<<nb, 256, (size_t)d * 36, st>>>(d, h->S, g.Wp(V), h->slot_d, h->dstatus);
-    h->launches++;
+    // N^-1: blocked Gauss-Jordan (panels in shared memory, rank-32 DMMA updates), V and NI as the two buffers
+    const GOp Ninv{g_inverse_blocked(d, h->S, h->slot_d, nb, g.Wp(V), g.Wp(NI), h->dpiv, h->dstatus, st, &h->launches), (long long)h->slot_d};
     // R = I + 2 N^-1 U
     double* Rout = (sq == 0) ? h->dU + c0 * h->slot_d : g.Wp(R);
-    { GOp a1 = g.W(V), b1 = g.W(U); g.gemm(Rout, h->slot_d, 1, &a1, &b1, 2.0, 0, nullptr, nullptr, 1.0); }
+    { GOp a1 = Ninv, b1 = g.W(U); g.gemm(Rout, h->slot_d, 1, &a1, &b1, 2.0, 0, nullptr, nullptr, 1.0); }
     GOp Rop{Rout, (long long)h->slot_d};
     if (want_jac) {
       for (int j = 0; j < nc; j++) {
@@ -750,7 +784,7 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
         { GOp D[2] = {g.W(Dd), g.W(Lv)}; double be[2] = {1.0, 2.0}; g.lin(Ss, 2, D, be); }                          // S = Lu + Lv
         { GOp D[1] = {g.W(Ss)}; double be[1] = {1.0}; g.mm1(RH, g.W(Dd), Rop, 1.0, 1, D, be); }                       // rhs = S + D R
         double* Lj = (sq == 0) ? Lout : g.Wp(L0 + j);
-        { GOp a1 = g.W(V), b1 = g.W(RH); g.gemm(Lj, (sq == 0) ? lstride : (long long)h->slot_d, 1, &a1, &b1, sc, 0, nullptr, nullptr, 0.0); }
+        { GOp a1 = Ninv, b1 = g.W(RH); g.gemm(Lj, (sq == 0) ? lstride : (long long)h->slot_d, 1, &a1, &b1, sc, 0, nullptr, nullptr, 0.0); }
       }
     }
     // squaring phase: L <- R L + L R ; R <- R R
@@ -856,15 +890,21 @@ static int launch_k2(qoc_handle* h, int phase, bool no_backward, const double* d
   if (h->new_k2 && phase != 3) {
     K2GParams P;
     P.q = q; P.G = h->G; P.Pg = h->dPg; P.sync = h->dsync; P.S_out = d_S_out;
-    h->sync_epoch += 1;
-    P.sync_target = (unsigned)h->G * h->sync_epoch;
-    with_cfg(h->cfg, [&](auto c) {
+    P.sync_target = (unsigned)h->G * (h->sync_epoch + 1);
+    const cudaError_t le = with_cfg(h->cfg, [&](auto c) {
       typedef decltype(c) C;
       // cooperative launch: the CTAs of a pulse wait on one another (per-pulse barrier), so they must all be resident
       void* args[] = {&P};
-      cudaLaunchCooperativeKernel((void*)k2g_kernel<C>, dim3(h->prob.batch * h->G), dim3(C::NTHREADS + 32), args, h->k2g_smem, st);
-      return 0;
+      return cudaLaunchCooperativeKernel((void*)k2g_kernel<C>, dim3(h->prob.batch * h->G), dim3(C::NTHREADS + 32), args, h->k2g_smem, st);
     });
+    // the device counters only advance when the launch was accepted: a refused launch must not move the epoch, or every later
+    // K2G launch on this handle would spin on a target the counters can never reach
+    if (le != cudaSuccess) {
+      cudaGetLastError();
+      h->err = std::string("cooperative launch of k2g_kernel failed: ") + cudaGetErrorString(le);
+      return QOC_ERR_CUDA;
+    }
+    h->sync_epoch += 1;
   } else
   with_cfg(h->cfg, [&](auto c) {
     typedef decltype(c) C;
@@ -1039,8 +1079,10 @@ extern "C" int qoc_propagate(qoc_handle* h, const double* u, double* J_out, doub
   h->costates_valid = false;
   QOC_CUDA(h, cudaMemcpyAsync(h->du, u, nu * 8, cudaMemcpyHostToDevice, h->stream));
   int rc;
-  // the Jacobians are produced together with U_k (they share the Pade powers): f_grad normally follows f
-  if ((rc = launch_k1(h, h->du, true, h->stream)) != QOC_OK) return rc;
+  // the reference's propagate does the matrix exponentials only (src/gradient_computations.jl:17-25): an f-only call (line
+  // search) does not pay for the Jacobians; qoc_gradient re-runs K1 with them on the cached u when they are missing.
+  // qoc_set_eager_jacobians(h, 1) produces them here (they share the Pade powers) when f_grad always follows f.
+  if ((rc = launch_k1(h, h->du, h->eager_jac, h->stream)) != QOC_OK) return rc;
   const bool builtin = p.cost != QOC_COST_NONE || has_penalty(h);  // J (or its penalty part) is formed on the device
   if ((rc = run_sweeps(h, false, nullptr, nullptr, nullptr, false, h->stream)) != QOC_OK) return rc;
   if (J_out && builtin) QOC_CUDA(h, cudaMemcpyAsync(J_out, h->dJ, (size_t)p.batch * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1071,15 +1113,22 @@ extern "C" int qoc_gradient(qoc_handle* h, const double* u, const double* lambda
   QOC_CUDA(h, cudaSetDevice(p.device));
   h->launches = 0;
   int rc;
-  if (!h->have_jac) {  // order changed since the propagation: redo K1 on the cached u (h->du still holds it)
+  bool k1_rerun = false;
+  if (!h->have_jac) {  // propagate ran without Jacobians, or the order changed since: K1 on the cached u (h->du still holds it)
     if ((rc = launch_k1(h, h->du, true, h->stream)) != QOC_OK) return rc;
+    k1_rerun = true;
   }
   if (lambda_final)
     QOC_CUDA(h, cudaMemcpyAsync(h->dlamf, lambda_final, (size_t)p.batch * 2 * p.d * p.m * 8, cudaMemcpyHostToDevice, h->stream));
   if ((rc = run_sweeps(h, true, lambda_final ? h->dlamf : nullptr, nullptr, nullptr, true, h->stream)) != QOC_OK) return rc;
   QOC_CUDA(h, cudaMemcpyAsync(dJdu_out, h->dg, nu * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (k1_rerun && (rc = queue_mail(h)) != QOC_OK) return rc;
   QOC_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->alg_flops += sweep_flops(p, true) - sweep_flops(p, false);
+  if (k1_rerun) {
+    if ((rc = check_status(h)) != QOC_OK) return rc;
+    if ((rc = fetch_flops(h, true)) != QOC_OK) return rc;
+  } else
+    h->alg_flops += sweep_flops(p, true) - sweep_flops(p, false);
   return QOC_OK;
 }
 
@@ -1125,7 +1174,13 @@ extern "C" int qoc_get_propagators(qoc_handle* h, double* U_out) {
 }
 extern "C" int qoc_get_jacobians(qoc_handle* h, double* dU_out) {
   if (!h || !dU_out) return QOC_ERR_INVALID;
-  if (!h->have_u || !h->have_jac) { h->err = "no Jacobians cached"; return QOC_ERR_STALE_CACHE; }
+  if (!h->have_u) { h->err = "no propagation cached"; return QOC_ERR_STALE_CACHE; }
+  if (!h->have_jac) {   // lazy: K1 with Jacobians on the cached u
+    QOC_CUDA(h, cudaSetDevice(h->prob.device));
+    const int rc = launch_k1(h, h->du, true, h->stream);
+    if (rc != QOC_OK) return rc;
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   return get_slots(h, h->dL, (size_t)h->prob.batch * h->prob.nt * h->prob.nc, dU_out);
 }
 
@@ -1165,10 +1220,22 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) kq_reduce_kernel(const double*
   }
 }
 
+// Preconditions shared by every qoc_shard_* entry point: one pulse, no running penalty (its affine costate term needs a
+// second exchange that the phase API does not carry; qoc_create_sharded / qoc_sharded_eval do), and on the general path the
+// two-level sweeps.  Never a silent fallback: anything else is QOC_ERR_UNSUPPORTED.
+static int shard_guard(qoc_handle* h) {
+  if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
+  if (has_penalty(h) || (h->row_mask64 != 0ull && h->col_mask != 0u && h->prob.mu != 0.0)) {
+    h->err = "the qoc_shard_* phase API does not carry the running state penalty (affine costate term)";
+    return QOC_ERR_UNSUPPORTED;
+  }
+  if (h->gpath && !h->gs2) { h->err = "time sharding on the general path needs the two-level sweeps (nt >= 4)"; return QOC_ERR_UNSUPPORTED; }
+  return QOC_OK;
+}
+
 extern "C" int qoc_shard_phase1_device(qoc_handle* h, const double* d_u, double* d_S_out, void* stream) {
   if (!h || !d_u || !d_S_out) return QOC_ERR_INVALID;
-  if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
-  if (h->gpath && !h->gs2) { h->err = "time sharding on the general path needs the two-level sweeps (no running penalty)"; return QOC_ERR_UNSUPPORTED; }
+  { const int gr = shard_guard(h); if (gr != QOC_OK) return gr; }
   cudaStream_t st = (cudaStream_t)stream;
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
   h->launches = 0;
@@ -1215,9 +1282,12 @@ extern "C" int qoc_shard_phase1_device(qoc_handle* h, const double* d_u, double*
 
 extern "C" int qoc_shard_forward_device(qoc_handle* h, const double* d_x_start, double* d_x_end, void* stream) {
   if (!h || !d_x_start) return QOC_ERR_INVALID;
+  { const int gr = shard_guard(h); if (gr != QOC_OK) return gr; }
   cudaStream_t st = (cudaStream_t)stream;
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
-  int rc = launch_k2(h, 1, true, nullptr, d_x_start, nullptr, st);
+  // general path: boundary walk + segment sweeps of the two-level form, forward only from the external state
+  int rc = h->gpath ? gpath_sweep2(h, 1, true, false, nullptr, d_x_start, nullptr, nullptr, st)
+                    : launch_k2(h, 1, true, nullptr, d_x_start, nullptr, st);
   if (rc != QOC_OK) return rc;
   if (d_x_end)
     QOC_CUDA(h, cudaMemcpyAsync(d_x_end, h->dxf, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyDeviceToDevice, st));
@@ -1227,11 +1297,19 @@ extern "C" int qoc_shard_forward_device(qoc_handle* h, const double* d_x_start, 
 extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_end, double* d_dJdu, double* d_lambda_start,
                                          void* stream) {
   if (!h || !d_lambda_end) return QOC_ERR_INVALID;
+  { const int gr = shard_guard(h); if (gr != QOC_OK) return gr; }
   cudaStream_t st = (cudaStream_t)stream;
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
-  int rc = launch_k2(h, 2, false, d_lambda_end, nullptr, nullptr, st);
+  int rc;
+  if (h->gpath) {   // backward from the external costate over the states the forward call left in HBM
+    if (!h->states_valid) { h->err = "qoc_shard_backward_device needs qoc_shard_forward_device first"; return QOC_ERR_STALE_CACHE; }
+    rc = gpath_sweep2(h, 2, false, true, d_lambda_end, nullptr, nullptr, d_dJdu, st);
+  } else {
+    rc = launch_k2(h, 2, false, d_lambda_end, nullptr, nullptr, st);
+    if (rc != QOC_OK) return rc;
+    rc = launch_k3(h, true, true, d_dJdu, st);
+  }
   if (rc != QOC_OK) return rc;
-  if ((rc = launch_k3(h, true, true, d_dJdu, st)) != QOC_OK) return rc;
   if (d_lambda_start)
     QOC_CUDA(h, cudaMemcpyAsync(d_lambda_start, h->dlam0, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyDeviceToDevice, st));
   return QOC_OK;
@@ -1242,16 +1320,20 @@ extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_e
 extern "C" int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int nranks, int rank, double* d_J, double* d_dJdu,
                                        void* stream) {
   if (!h || !d_S_all || nranks <= 0 || rank < 0 || rank >= nranks) return QOC_ERR_INVALID;
-  if (h->gpath && !h->gs2) { h->err = "time sharding on the general path needs the two-level sweeps (no running penalty)"; return QOC_ERR_UNSUPPORTED; }
+  { const int gr = shard_guard(h); if (gr != QOC_OK) return gr; }
   if (h->prob.cost == QOC_COST_NONE) { h->err = "qoc_shard_phase2_device needs a built-in cost"; return QOC_ERR_INVALID; }
-  if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   const qoc_problem& p = h->prob;
   QOC_CUDA(h, cudaSetDevice(p.device));
   ShardBoundary q;
   q.d = p.d; q.m = p.m; q.nranks = nranks; q.rank = rank; q.cost = p.cost; q.n = p.n;
   q.S_all = d_S_all; q.x0 = h->dx0; q.T = h->dT; q.x_start = h->dbnd; q.lam_end = h->dbnd + (size_t)2 * p.d * p.m; q.J = d_J ? d_J : h->dJ;
-  shard_boundary_kernel<<<1, 256, (size_t)2 * p.d * p.m * 16, st>>>(q);
+  {
+    const size_t b_smem = (size_t)2 * p.d * p.m * 16;
+    if (b_smem > 40 * 1024) QOC_CUDA(h, cudaFuncSetAttribute(shard_boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
+    shard_boundary_kernel<<<1, 256, b_smem, st>>>(q);
+    QOC_CUDA(h, cudaGetLastError());
+  }
   h->launches += 1;
   int rc;
   if (h->gpath) return gpath_sweep2(h, 4, false, true, q.lam_end, q.x_start, nullptr, d_dJdu, st);
@@ -1268,6 +1350,7 @@ extern "C" int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int
 // at every hand-off between the compute warps and the service warp.  out: nslices x 16 long longs.
 extern "C" int qoc_debug_k1_timeline(qoc_handle* h, long long* out, int nslices, int want_jac) {
   if (!h || !out || nslices <= 0 || !h->have_u) return QOC_ERR_INVALID;
+  if (h->gpath || h->k1s_ok) { h->err = "qoc_debug_k1_timeline: k1_kernel only"; return QOC_ERR_UNSUPPORTED; }
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
   QOC_CUDA(h, cudaMalloc(&h->dbg, sizeof(long long) * (16 * nslices + 4096)));
   QOC_CUDA(h, cudaMemset(h->dbg, 0, sizeof(long long) * (16 * nslices + 4096)));
@@ -1287,6 +1370,7 @@ extern "C" int qoc_debug_k1_timeline(qoc_handle* h, long long* out, int nslices,
 // Developer aid: K3N once on the cached evaluation with clock64 stamps of CTA 0's recurrence warp 0 (4 per step).
 extern "C" int qoc_debug_k3_timeline(qoc_handle* h, long long* out, int nsteps) {
   if (!h || !out || nsteps <= 0 || !h->have_u) return QOC_ERR_INVALID;
+  if (h->gpath) { h->err = "qoc_debug_k3_timeline: shared-memory path only"; return QOC_ERR_UNSUPPORTED; }
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
   QOC_CUDA(h, cudaMalloc(&h->dbg, sizeof(long long) * 4 * nsteps));
   QOC_CUDA(h, cudaMemset(h->dbg, 0, sizeof(long long) * 4 * nsteps));

@@ -12,6 +12,7 @@
 // This first version favours coverage over speed (no cross-launch fusion, serial sweeps); see DESIGN.md.
 #pragma once
 #include "qoc_tiles.cuh"
+#include "qoc_cost.cuh"
 
 namespace qoc {
 
@@ -33,32 +34,53 @@ struct GGemm {
   long long cstride;
   int cinner;
   long long cstride2;
+  int gj_k0, gj_nb;   // gj_nb > 0: rank-nb update of the blocked Gauss-Jordan inverse (k range [gj_k0, gj_k0 + gj_nb), D[0] = cur)
 };
 
 #ifndef QOC_3M
 #error "qoc_gpath.cuh assumes the 3M complex product (Acc carries T1/T2/T3)"
 #endif
 
-// C = alpha (A1 B1 [+ A2 B2 ...]) + sum_q beta_q D_q + gamma I  for a batch of slices.
-// CTA tile (32 WM) x (16 WN): 8 warps as 4 x 2, each warp WM x WN tiles of 8 x 8 (WM, WN = 1, 2: 32 x 32 for small d;
-// 2, 4: 64 x 64, half the L2 -> shared traffic per flop and half the shared loads per DMMA, for d >= 64).
-// Operands are staged global -> shared per 32-wide k chunk.  8x8 tiles and k-steps that lie entirely outside the
-// d x d matrix are skipped (warp-uniform predicates; d = 40 fills 25 of the 64 tiles of its 2 x 2 CTA grid and 10 of
-// 16 k-steps), the zero padding of the staged tiles covers the partial ones.
-template <int WM, int WN>
-__global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
-  constexpr int TM = 32 * WM, TN = 16 * WN;   // CTA tile
-  constexpr int AS = 36, BS = TN + 4;         // shared row strides (= 4 mod 8: conflict-free fragment loads)
+__device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// 16-byte asynchronous global -> shared copy (SASS LDGSTS); bytes beyond src_bytes (0, 8 or 16) are zero-filled
+__device__ __forceinline__ void g_cp_async16(void* sdst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(g_smem_u32(sdst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void g_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void g_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// C = alpha (A1 B1 [+ A2 B2 ...]) + sum_q beta_q D_q + gamma I  for a batch of slices (blockIdx.z), 3M DMMA tiles.
+// CTA tile (8 WM NWM) x (8 WN NWN): NWM x NWN warps, each WM x WN tiles of 8 x 8.  The operands stream through a
+// three-stage cp.async ring in 16-wide k chunks (row strides = 4 mod 8 doubles: conflict-free fragment loads), one
+// __syncthreads per chunk; edges are zero-filled by the copy itself (src-size form), 8 x 8 tiles and k-steps that lie
+// entirely outside the d x d matrix are skipped (warp-uniform predicates).
+// Round 1's kernel staged synchronously through registers (two barriers per chunk, nothing in flight while the tile loop
+// ran): 0.41 of the FP64 peak at best.  gj_nb > 0 selects the rank-nb update of the blocked Gauss-Jordan inverse below.
+template <int WM, int WN, int NWM, int NWN>
+struct GemmShape {
+  static constexpr int NTH = 32 * NWM * NWN, TM = 8 * WM * NWM, TN = 8 * WN * NWN, KC = 16, NST = 3;
+  static constexpr int AS = KC + 4, BS = TN + 4;
+  static constexpr int A_PLANE = TM * AS, B_PLANE = KC * BS, STAGE = 2 * A_PLANE + 2 * B_PLANE;   // doubles
+  static constexpr size_t SMEM = (size_t)NST * STAGE * 8;
+};
+
+template <int WM, int WN, int NWM, int NWN>
+__global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g) {
+  typedef GemmShape<WM, WN, NWM, NWN> G;
+  constexpr int NTH = G::NTH, TM = G::TM, TN = G::TN, KC = G::KC, NST = G::NST, AS = G::AS, BS = G::BS;
   extern __shared__ __align__(16) unsigned char gsm_raw[];
-  double* smAr = reinterpret_cast<double*>(gsm_raw);
-  double* smAi = smAr + TM * AS;
-  double* smBr = smAi + TM * AS;
-  double* smBi = smBr + 32 * BS;
+  double* sm = reinterpret_cast<double*>(gsm_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;
+  const int wm = warp / NWN, wn = warp - wm * NWN;
   const int s = blockIdx.z, tm = blockIdx.y, tn = blockIdx.x;
   const int d = g.d, S = g.S, plane = d * S;
   const int gq = lane >> 2, q4 = lane & 3;
+  const bool gj = g.gj_nb > 0;
+  const int kbeg = gj ? g.gj_k0 : 0;
+  const int kend = gj ? ((g.gj_k0 + g.gj_nb < d) ? g.gj_k0 + g.gj_nb : d) : d;
+  const int nkc = (kend - kbeg + KC - 1) / KC;
+  const int total = g.npairs * nkc;
   double T1[WM][WN][2], T2[WM][WN][2], T3[WM][WN][2];
 #pragma unroll
   for (int a = 0; a < WM; a++)
@@ -69,62 +91,69 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
   for (int a = 0; a < WM; a++) rowv[a] = tm * TM + (wm * WM + a) * 8 < d;
 #pragma unroll
   for (int b = 0; b < WN; b++) colv[b] = tn * TN + (wn * WN + b) * 8 < d;
-  const int nkc = (d + 31) / 32;
-  for (int p = 0; p < g.npairs; p++) {
+
+  auto issue = [&](int c) {
+    const int p = c / nkc, kc = c - p * nkc, kb = kbeg + kc * KC;
     const double* Ag = g.A[p].p + g.A[p].off(s);
     const double* Bg = g.B[p].p + g.B[p].off(s);
-    for (int kc = 0; kc < nkc; kc++) {
-      __syncthreads();
+    double* st = sm + (size_t)(c % NST) * G::STAGE;
+    for (int e = tid; e < TM * (KC / 2); e += NTH) {          // A tile: TM rows x KC columns, both planes
+      const int r = e / (KC / 2), cc = (e - r * (KC / 2)) * 2;
+      const int gr = tm * TM + r, gc = kb + cc;
+      int bytes = (gr < d) ? (kend - gc) * 8 : 0;
+      bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+      const double* src = bytes ? Ag + (size_t)gr * S + gc : Ag;
+      g_cp_async16(st + r * AS + cc, src, bytes);
+      g_cp_async16(st + G::A_PLANE + r * AS + cc, bytes ? src + plane : Ag, bytes);
+    }
+    double* sb = st + 2 * G::A_PLANE;
+    for (int e = tid; e < KC * (TN / 2); e += NTH) {          // B tile: KC rows x TN columns, both planes
+      const int r = e / (TN / 2), cc = (e - r * (TN / 2)) * 2;
+      const int gr = kb + r, gc = tn * TN + cc;
+      const int bytes = (gr < kend && gc < S) ? 16 : 0;
+      const double* src = bytes ? Bg + (size_t)gr * S + gc : Bg;
+      g_cp_async16(sb + r * BS + cc, src, bytes);
+      g_cp_async16(sb + G::B_PLANE + r * BS + cc, bytes ? src + plane : Bg, bytes);
+    }
+  };
+
 #pragma unroll
-      for (int i = 0; i < 2 * WM; i++) {          // A tile: TM rows x 32 columns
-        const int e = tid + i * 256, r = e >> 4, c = (e & 15) * 2;
-        const int gr = tm * TM + r, gc = kc * 32 + c;
-        double2 vr = make_double2(0.0, 0.0), vi = vr;
-        if (gr < d && gc < d) {
-          vr = *reinterpret_cast<const double2*>(Ag + (size_t)gr * S + gc);
-          vi = *reinterpret_cast<const double2*>(Ag + plane + (size_t)gr * S + gc);
-        }
-        *reinterpret_cast<double2*>(&smAr[r * AS + c]) = vr;
-        *reinterpret_cast<double2*>(&smAi[r * AS + c]) = vi;
-      }
+  for (int c = 0; c < NST - 1; c++) {
+    if (c < total) issue(c);
+    g_cp_async_commit();
+  }
+  const bool work = rowv[0] && colv[0];
+  for (int it = 0; it < total; it++) {
+    g_cp_async_wait<NST - 2>();
+    __syncthreads();
+    if (it + NST - 1 < total) issue(it + NST - 1);
+    g_cp_async_commit();
+    if (work) {
+      const double* st = sm + (size_t)(it % NST) * G::STAGE;
+      const int kc = it % nkc;
+      const int kleft = kend - (kbeg + kc * KC);
+      const int ksmax = kleft >= KC ? KC / 4 : (kleft + 3) / 4;
+      const double* are = st + (wm * WM * 8 + gq) * AS + q4;
+      const double* aim = are + G::A_PLANE;
+      const double* bre = st + 2 * G::A_PLANE + q4 * BS + wn * WN * 8 + gq;
+      const double* bim = bre + G::B_PLANE;
 #pragma unroll
-      for (int i = 0; i < WN; i++) {              // B tile: 32 rows x TN columns
-        const int e = tid + i * 256, r = e / (TN / 2), c = (e % (TN / 2)) * 2;
-        const int gr = kc * 32 + r, gc = tn * TN + c;
-        double2 vr = make_double2(0.0, 0.0), vi = vr;
-        if (gr < d && gc < d) {
-          vr = *reinterpret_cast<const double2*>(Bg + (size_t)gr * S + gc);
-          vi = *reinterpret_cast<const double2*>(Bg + plane + (size_t)gr * S + gc);
-        }
-        *reinterpret_cast<double2*>(&smBr[r * BS + c]) = vr;
-        *reinterpret_cast<double2*>(&smBi[r * BS + c]) = vi;
-      }
-      __syncthreads();
-      const int kvalid = d - kc * 32;
-      const int kmax = kvalid >= 32 ? 8 : (kvalid + 3) / 4;
-      if (rowv[0] && colv[0]) {
-        const double* are = smAr + (wm * WM * 8 + gq) * AS + q4;
-        const double* aim = smAi + (wm * WM * 8 + gq) * AS + q4;
-        const double* bre = smBr + q4 * BS + wn * WN * 8 + gq;
-        const double* bim = smBi + q4 * BS + wn * WN * 8 + gq;
+      for (int ks = 0; ks < KC / 4; ks++) {
+        if (ks < ksmax) {
+          double ar[WM], ai[WM], as[WM];
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) {
-          if (ks < kmax) {
-            double ar[WM], ai[WM], as[WM];
+          for (int a = 0; a < WM; a++) { ar[a] = are[a * 8 * AS + ks * 4]; ai[a] = aim[a * 8 * AS + ks * 4]; as[a] = ar[a] + ai[a]; }
 #pragma unroll
-            for (int a = 0; a < WM; a++) { ar[a] = are[a * 8 * AS + ks * 4]; ai[a] = aim[a * 8 * AS + ks * 4]; as[a] = ar[a] + ai[a]; }
+          for (int b = 0; b < WN; b++) {
+            if (colv[b]) {
+              const double br = bre[ks * 4 * BS + b * 8], bi = bim[ks * 4 * BS + b * 8];
+              const double bs = br + bi;
 #pragma unroll
-            for (int b = 0; b < WN; b++) {
-              if (colv[b]) {
-                const double br = bre[ks * 4 * BS + b * 8], bi = bim[ks * 4 * BS + b * 8];
-                const double bs = br + bi;
-#pragma unroll
-                for (int a = 0; a < WM; a++) {
-                  if (rowv[a]) {
-                    dmma(T1[a][b][0], T1[a][b][1], ar[a], br);
-                    dmma(T2[a][b][0], T2[a][b][1], ai[a], bi);
-                    dmma(T3[a][b][0], T3[a][b][1], as[a], bs);
-                  }
+              for (int a = 0; a < WM; a++) {
+                if (rowv[a]) {
+                  dmma(T1[a][b][0], T1[a][b][1], ar[a], br);
+                  dmma(T2[a][b][0], T2[a][b][1], ai[a], bi);
+                  dmma(T3[a][b][0], T3[a][b][1], as[a], bs);
                 }
               }
             }
@@ -133,6 +162,7 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
       }
     }
   }
+  g_cp_async_wait<0>();
   double* Cg = g.C + (g.cinner > 0 ? (long long)(s / g.cinner) * g.cstride2 + (long long)(s % g.cinner) * g.cstride
                                    : (long long)s * g.cstride);
 #pragma unroll
@@ -146,14 +176,23 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
         double r0 = g.alpha * (T1[a][b][0] - T2[a][b][0]), r1 = g.alpha * (T1[a][b][1] - T2[a][b][1]);
         double i0 = g.alpha * ((T3[a][b][0] - T1[a][b][0]) - T2[a][b][0]), i1 = g.alpha * ((T3[a][b][1] - T1[a][b][1]) - T2[a][b][1]);
         const size_t o = (size_t)row * S + col;
-        for (int q = 0; q < g.nadd; q++) {
-          const double* Dg = g.D[q].p + g.D[q].off(s);
+        if (gj) {
+          // blocked Gauss-Jordan step on the panel K = [kbeg, kend): the K columns of `cur` already hold the transformation
+          // G; every other column becomes (cur with its K rows zeroed) + G cur[K, :]
+          const double* Dg = g.D[0].p + g.D[0].off(s);
           const double2 u = *reinterpret_cast<const double2*>(Dg + o), v = *reinterpret_cast<const double2*>(Dg + plane + o);
-          r0 = fma(g.beta[q], u.x, r0); r1 = fma(g.beta[q], u.y, r1);
-          i0 = fma(g.beta[q], v.x, i0); i1 = fma(g.beta[q], v.y, i1);
+          if (col >= kbeg && col < kend) { r0 = u.x; r1 = u.y; i0 = v.x; i1 = v.y; }
+          else if (!(row >= kbeg && row < kend)) { r0 += u.x; r1 += u.y; i0 += v.x; i1 += v.y; }
+        } else {
+          for (int q = 0; q < g.nadd; q++) {
+            const double* Dg = g.D[q].p + g.D[q].off(s);
+            const double2 u = *reinterpret_cast<const double2*>(Dg + o), v = *reinterpret_cast<const double2*>(Dg + plane + o);
+            r0 = fma(g.beta[q], u.x, r0); r1 = fma(g.beta[q], u.y, r1);
+            i0 = fma(g.beta[q], v.x, i0); i1 = fma(g.beta[q], v.y, i1);
+          }
+          if (row == col) r0 += g.gamma;
+          if (row == col + 1) r1 += g.gamma;
         }
-        if (row == col) r0 += g.gamma;
-        if (row == col + 1) r1 += g.gamma;
         if (col + 1 >= d) { r1 = 0.0; i1 = 0.0; }
         *reinterpret_cast<double2*>(Cg + o) = make_double2(r0, r1);
         *reinterpret_cast<double2*>(Cg + plane + o) = make_double2(i0, i1);
@@ -162,17 +201,69 @@ __global__ void __launch_bounds__(256) g_gemm_kernel(GGemm g) {
   }
 }
 
-// host-side launch helper.  Measured on B200 (synthetic d = 64 / 128 / 256, cavity d = 80): 64 x 64 tiles (WM, WN = 2, 4;
-// 168 registers, one CTA per SM) are 10-50 % SLOWER than 32 x 32 (80 registers, three CTAs per SM) because the operand
-// staging is synchronous and only co-resident CTAs hide it; 64 x 32 at two CTAs per SM is a wash.  Larger tiles need an
-// asynchronous (cp.async / TMA) double buffer first -- DESIGN.md section 7.
-// (A register double buffer -- global loads of chunk i+1 issued behind the hand-over of chunk i -- was measured too: 5-8 % SLOWER
-// at every tile shape, 90 instead of 80 registers; the kernel is not bound by the exposed load latency.)
+// C = sum_q beta_q D_q + gamma I over whole planar slots (no product): a streaming elementwise pass, 16-byte accesses
+__global__ void __launch_bounds__(256) g_lin_kernel(GGemm g) {
+  const int s = blockIdx.y;
+  const int d = g.d, S = g.S, plane = d * S, n2 = plane / 2, S2 = S / 2;
+  double* Cg = g.C + (g.cinner > 0 ? (long long)(s / g.cinner) * g.cstride2 + (long long)(s % g.cinner) * g.cstride
+                                   : (long long)s * g.cstride);
+  const double* Dp[3];
+  for (int q = 0; q < 3; q++) Dp[q] = q < g.nadd ? g.D[q].p + g.D[q].off(s) : nullptr;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += gridDim.x * blockDim.x) {
+    double2 r = make_double2(0.0, 0.0), i = r;
+    for (int q = 0; q < g.nadd; q++) {
+      const double2 u = reinterpret_cast<const double2*>(Dp[q])[e], v = reinterpret_cast<const double2*>(Dp[q] + plane)[e];
+      r.x = fma(g.beta[q], u.x, r.x); r.y = fma(g.beta[q], u.y, r.y);
+      i.x = fma(g.beta[q], v.x, i.x); i.y = fma(g.beta[q], v.y, i.y);
+    }
+    if (g.gamma != 0.0) {
+      const int row = e / S2, col = 2 * (e - row * S2);
+      if (row == col) r.x += g.gamma;
+      if (row == col + 1) r.y += g.gamma;
+    }
+    reinterpret_cast<double2*>(Cg)[e] = r;
+    reinterpret_cast<double2*>(Cg + plane)[e] = i;
+  }
+}
+
+// host-side launch helper: the CTA tile that wastes least of the d x d matrix (ties: the larger tile)
+//   32 x 32 (8 warps of 1 x 2 tiles) | 40 x 40 (5 warps of 1 x 5) | 48 x 48 (6 warps of 1 x 6) | 64 x 64 (16 warps of 2 x 2)
+template <int WM, int WN, int NWM, int NWN>
+static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
+  typedef GemmShape<WM, WN, NWM, NWN> G;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(g_gemm2_kernel<WM, WN, NWM, NWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    attr_done = true;
+  }
+  const int tm = (g.d + G::TM - 1) / G::TM, tn = (g.d + G::TN - 1) / G::TN;
+  g_gemm2_kernel<WM, WN, NWM, NWN><<<dim3(tn, tm, nb), G::NTH, G::SMEM, st>>>(g);
+}
+static inline int g_gemm_tile(int d) {
+  static const int cand[4] = {64, 48, 40, 32};
+  int best = 64, bestpad = 1 << 30;
+  for (int i = 0; i < 4; i++) {
+    const int t = cand[i], pad = (d + t - 1) / t * t;
+    if (pad < bestpad) { bestpad = pad; best = t; }
+  }
+  const char* f = getenv("QOC_GEMM_TILE");
+  if (f && atoi(f) > 0) best = atoi(f);
+  return best;
+}
 static inline void g_gemm_launch(const GGemm& g, int nb, cudaStream_t st) {
-  constexpr int WM = 1, WN = 2;
-  const size_t smem = (size_t)(2 * 32 * WM * 36 + 2 * 32 * (16 * WN + 4)) * 8;
-  const int tiles = (g.d + 31) / 32;
-  g_gemm_kernel<WM, WN><<<dim3(tiles, tiles, nb), 256, smem, st>>>(g);
+  if (g.npairs == 0 && g.gj_nb == 0) {
+    const int n2 = g.d * g.S / 2;
+    int bx = (n2 + 255) / 256;
+    if (bx > 8) bx = 8;
+    g_lin_kernel<<<dim3(bx, nb), 256, 0, st>>>(g);
+    return;
+  }
+  switch (g_gemm_tile(g.d)) {
+    case 32: g_gemm2_launch_t<1, 2, 4, 2>(g, nb, st); break;
+    case 40: g_gemm2_launch_t<1, 5, 5, 1>(g, nb, st); break;
+    case 48: g_gemm2_launch_t<1, 6, 6, 1>(g, nb, st); break;
+    default: g_gemm2_launch_t<2, 2, 4, 4>(g, nb, st); break;
+  }
 }
 
 // X[s] = (A0 + sum_j u[s][j] A_j) * scale ;  optionally the unscaled generator too (Taylor mode)
@@ -217,26 +308,44 @@ __global__ void g_umax_kernel(const double* u, int nc, long long n, double* out)
   }
 }
 
-// In-place Gauss-Jordan inverse with partial (row) pivoting, one CTA per slice, matrix in global memory (L2).
-__global__ void __launch_bounds__(256) g_inverse_kernel(int d, int S, double* N, long long stride, int* status) {
+// ---- blocked Gauss-Jordan inverse with partial (row) pivoting -------------------------------------------------------------
+// Replaces round 1's g_inverse_kernel (whole matrix eliminated in L2, d steps of d^2 work behind four barriers each: 23 % of
+// the step at d = 64, 74 % at d = 256).  The matrix is processed in column panels K of nb <= 32 columns:
+//   g_gj_panel_kernel  one CTA per slice: the d x nb panel in shared memory, nb pivot searches / eliminations on the panel
+//                      only; leaves the transformation G in the K columns and applies the panel's row interchanges to the
+//                      other columns.  O(d nb^2) work per panel, latency-bound, negligible.
+//   g_gemm2_kernel     (gj_nb > 0) every other column block: (cur with its K rows zeroed) + G cur[K, :] -- a rank-nb DMMA
+//                      update, out of place (cur -> oth); all d^3 flops of the inversion are here.
+//   g_gj_perm_kernel   undoes the row interchanges as one column gather (A^-1 = (P A)^-1 P).
+// With d <= 32 the single panel is the whole matrix and no update is needed.
+__global__ void __launch_bounds__(256) g_gj_panel_kernel(int d, int S, int k0, int nb, double* M, long long stride, int* piv, int* status) {
   extern __shared__ __align__(16) unsigned char gsm[];
-  double2* rowbuf = reinterpret_cast<double2*>(gsm);   // d
-  double2* colbuf = rowbuf + d;                        // d
-  int* piv = reinterpret_cast<int*>(colbuf + d);       // d
+  const int NBP = nb <= 8 ? 8 : (nb <= 16 ? 16 : 32);   // lanes per panel row
+  double2* pan = reinterpret_cast<double2*>(gsm);       // [d][NBP]
+  double2* prow = pan + (size_t)d * NBP;                // old pivot row      [NBP]
+  double2* krow = prow + 32;                            // old row k          [NBP]
   __shared__ double red_v[8];
   __shared__ int red_i[8];
-  __shared__ int sh_p;
+  __shared__ int sh_piv[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* re = N + (long long)blockIdx.x * stride;
+  double* re = M + (long long)blockIdx.x * stride;
   double* im = re + (size_t)d * S;
+  int* pv = piv + (size_t)blockIdx.x * d;
+  const int rpw = 32 / NBP;                 // panel rows per warp pass
+  const int c = lane % NBP, rsub = lane / NBP;
+  // load the panel (columns k0 .. k0+nb-1 of every row)
+  for (int i = warp * rpw + rsub; i < d; i += 8 * rpw)
+    pan[(size_t)i * NBP + c] = (c < nb) ? make_double2(re[(size_t)i * S + k0 + c], im[(size_t)i * S + k0 + c]) : make_double2(0.0, 0.0);
+  __syncthreads();
   bool ok = true;
-  for (int k = 0; k < d; k++) {
-    // pivot search over rows i >= k
+  for (int kk = 0; kk < nb; kk++) {
+    const int k = k0 + kk;
+    // pivot search over the rows that have not pivoted yet (i >= k)
     double best = -1.0;
     int bi = k;
     for (int i = k + tid; i < d; i += 256) {
-      const double x = re[(size_t)i * S + k], y = im[(size_t)i * S + k];
-      const double m = x * x + y * y;
+      const double2 v = pan[(size_t)i * NBP + kk];
+      const double m = v.x * v.x + v.y * v.y;
       if (m > best) { best = m; bi = i; }
     }
     for (int off = 16; off > 0; off >>= 1) {
@@ -246,67 +355,124 @@ __global__ void __launch_bounds__(256) g_inverse_kernel(int d, int S, double* N,
     }
     if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
     __syncthreads();
-    if (tid == 0) {
-      double b = red_v[0];
-      int p = red_i[0];
-      for (int w = 1; w < 8; w++)
-        if (red_v[w] > b || (red_v[w] == b && red_i[w] < p)) { b = red_v[w]; p = red_i[w]; }
-      sh_p = (b > 0.0) ? p : -1 - p;
-      piv[k] = p;
-    }
+    double b = red_v[0];
+    int p = red_i[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++)
+      if (red_v[w] > b || (red_v[w] == b && red_i[w] < p)) { b = red_v[w]; p = red_i[w]; }
+    if (!(b > 0.0)) ok = false;
+    // stage the two rows that trade places (old values), then update in place
+    if (warp == 0 && lane < NBP) prow[lane] = pan[(size_t)p * NBP + lane];
+    if (warp == 1 && lane < NBP) krow[lane] = pan[(size_t)k * NBP + lane];
+    if (tid == 64) sh_piv[kk] = p;
     __syncthreads();
-    int p = sh_p;
-    if (p < 0) { ok = false; p = -1 - p; }
-    // stage the pivot row (old row p), the displaced row goes to row p; multipliers = column k after the swap
-    for (int c = tid; c < d; c += 256) {
-      const double2 rp = make_double2(re[(size_t)p * S + c], im[(size_t)p * S + c]);
-      if (p != k) {
-        re[(size_t)p * S + c] = re[(size_t)k * S + c];
-        im[(size_t)p * S + c] = im[(size_t)k * S + c];
-      }
-      rowbuf[c] = rp;
-    }
-    __syncthreads();
-    for (int i = tid; i < d; i += 256) colbuf[i] = make_double2(re[(size_t)i * S + k], im[(size_t)i * S + k]);  // row k entry unused
-    __syncthreads();
-    const double2 pv = rowbuf[k];
-    const double den = 1.0 / (pv.x * pv.x + pv.y * pv.y);
-    const double pir = pv.x * den, pii = -pv.y * den;
-    for (int e = tid; e < d * d; e += 256) {
-      const int i = e / d, c = e - i * d;
-      double vr, vi;
-      if (i == k) {
-        if (c == k) { vr = pir; vi = pii; }
-        else { const double2 r = rowbuf[c]; vr = r.x * pir - r.y * pii; vi = r.x * pii + r.y * pir; }
+    const double2 pvv = prow[kk];
+    const double den = 1.0 / (pvv.x * pvv.x + pvv.y * pvv.y);
+    const double pir = pvv.x * den, pii = -pvv.y * den;   // 1 / pivot
+    const double2 pr = prow[c];
+    for (int i0 = warp * rpw; i0 < d; i0 += 8 * rpw) {   // warp-uniform trip count (__syncwarp inside)
+      const int i = (i0 + rsub < d) ? i0 + rsub : d - 1;
+      const bool live = (i0 + rsub < d) && c < nb;
+      double2 x = pan[(size_t)i * NBP + c];
+      if (i == p) x = krow[c];                 // the displaced row k lands in row p
+      double2 val;
+      if (i == k) {                            // pivot row: scaled
+        if (c == kk) val = make_double2(pir, pii);
+        else val = make_double2(pr.x * pir - pr.y * pii, pr.x * pii + pr.y * pir);
       } else {
-        const double2 f = colbuf[i];
-        const double gr = f.x * pir - f.y * pii, gi = f.x * pii + f.y * pir;  // f / pivot
-        if (c == k) { vr = -gr; vi = -gi; }
-        else {
-          const double2 r = rowbuf[c];
-          vr = re[(size_t)i * S + c] - (gr * r.x - gi * r.y);
-          vi = im[(size_t)i * S + c] - (gr * r.y + gi * r.x);
-        }
+        const double2 f = (i == p) ? krow[kk] : pan[(size_t)i * NBP + kk];   // multiplier: this row's entry in column kk
+        const double gr = f.x * pir - f.y * pii, gi = f.x * pii + f.y * pir;
+        if (c == kk) val = make_double2(-gr, -gi);
+        else val = make_double2(x.x - (gr * pr.x - gi * pr.y), x.y - (gr * pr.y + gi * pr.x));
       }
-      re[(size_t)i * S + c] = vr;
-      im[(size_t)i * S + c] = vi;
+      // every lane of the row group has read column kk of its row before anybody overwrites it
+      __syncwarp();
+      if (live) pan[(size_t)i * NBP + c] = val;
     }
     __syncthreads();
   }
-  // undo the row interchanges as column interchanges in reverse order
-  for (int k = d - 1; k >= 0; k--) {
-    const int p = piv[k];
-    if (p != k) {
-      for (int i = tid; i < d; i += 256) {
-        const size_t a = (size_t)i * S + k, b = (size_t)i * S + p;
+  // panel back to the K columns; pivots of this panel to the list
+  for (int i = warp * rpw + rsub; i < d; i += 8 * rpw)
+    if (c < nb) { const double2 v = pan[(size_t)i * NBP + c]; re[(size_t)i * S + k0 + c] = v.x; im[(size_t)i * S + k0 + c] = v.y; }
+  if (tid < nb) pv[k0 + tid] = sh_piv[tid];
+  // the panel's row interchanges on every other column: columns are independent, each thread replays the nb swaps on its own
+  for (int col = tid; col < d; col += 256) {
+    if (col >= k0 && col < k0 + nb) continue;
+    for (int kk = 0; kk < nb; kk++) {
+      const int p = sh_piv[kk], k = k0 + kk;
+      if (p != k) {
+        const size_t a = (size_t)k * S + col, b2 = (size_t)p * S + col;
         const double tr = re[a], ti = im[a];
-        re[a] = re[b]; im[a] = im[b];
-        re[b] = tr; im[b] = ti;
+        re[a] = re[b2]; im[a] = im[b2];
+        re[b2] = tr; im[b2] = ti;
       }
     }
-    __syncthreads();
   }
   if (tid == 0 && !ok) atomicExch(status, 8);
+}
+
+// dst[:, c] = src[:, idx[c]] with idx = the column interchanges k <-> piv[k], k = d-1 .. 0, composed
+__global__ void __launch_bounds__(256) g_gj_perm_kernel(int d, int S, const double* src, double* dst, long long stride, const int* piv) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  int* idx = reinterpret_cast<int*>(gsm);
+  const int tid = threadIdx.x;
+  const int* pv = piv + (size_t)blockIdx.x * d;
+  for (int i = tid; i < d; i += 256) idx[i] = i;
+  __syncthreads();
+  if (tid == 0)
+    for (int k = d - 1; k >= 0; k--) {
+      const int p = pv[k];
+      if (p != k) { const int t = idx[k]; idx[k] = idx[p]; idx[p] = t; }
+    }
+  __syncthreads();
+  const double* sre = src + (long long)blockIdx.x * stride;
+  const double* sim = sre + (size_t)d * S;
+  double* dre = dst + (long long)blockIdx.x * stride;
+  double* dim_ = dre + (size_t)d * S;
+  for (int e = tid; e < d * S; e += 256) {
+    const int r = e / S, col = e - r * S;
+    double vr = 0.0, vi = 0.0;
+    if (col < d) { vr = sre[(size_t)r * S + idx[col]]; vi = sim[(size_t)r * S + idx[col]]; }
+    dre[e] = vr; dim_[e] = vi;
+  }
+}
+
+static inline int g_gj_panel_width(int d) { return d <= 384 ? 32 : 16; }
+static inline size_t g_gj_panel_smem(int d) {
+  const int nb = g_gj_panel_width(d) < d ? g_gj_panel_width(d) : d;
+  const int NBP = nb <= 8 ? 8 : (nb <= 16 ? 16 : 32);
+  return ((size_t)d * NBP + 64) * 16;
+}
+
+// N^-1 for `nsl` slices: cur (holds N, destroyed) and oth are two workspace slots; returns the buffer that holds the inverse.
+static inline double* g_inverse_blocked(int d, int S, long long slot_d, int nsl, double* cur, double* oth, int* piv, int* status,
+                                        cudaStream_t st, int* launches) {
+  const int nbw = g_gj_panel_width(d);
+  const size_t psm = g_gj_panel_smem(d);
+  static size_t attr_set = 0;
+  if (psm > 40 * 1024 && psm > attr_set) {
+    cudaFuncSetAttribute(g_gj_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+    attr_set = psm;
+  }
+  for (int k0 = 0; k0 < d; k0 += nbw) {
+    const int nb = (d - k0 < nbw) ? d - k0 : nbw;
+    g_gj_panel_kernel<<<nsl, 256, psm, st>>>(d, S, k0, nb, cur, slot_d, piv, status);
+    (*launches)++;
+    if (d > nbw) {
+      GGemm g;
+      memset(&g, 0, sizeof g);
+      g.d = d; g.S = S; g.nb = nsl; g.npairs = 1; g.nadd = 1; g.alpha = 1.0;
+      g.A[0] = GOp{cur, slot_d, 0, 0}; g.B[0] = g.A[0]; g.D[0] = g.A[0]; g.beta[0] = 1.0;
+      g.C = oth; g.cstride = slot_d;
+      g.gj_k0 = k0; g.gj_nb = nb;
+      g_gemm_launch(g, nsl, st);
+      (*launches)++;
+      double* t = cur; cur = oth; oth = t;
+    }
+  }
+  g_gj_perm_kernel<<<nsl, 256, (size_t)d * 4, st>>>(d, S, cur, oth, slot_d, piv);
+  (*launches)++;
+  return oth;
 }
 
 struct GSweep {
@@ -368,6 +534,7 @@ __global__ void __launch_bounds__(256) g_sweep_kernel(GSweep g) {
   double* buf = reinterpret_cast<double*>(gsm);   // 3 state buffers x (re, im): x / lambda ping-pong + y
   double* b0 = buf; double* b1 = buf + 2 * dm; double* b2 = buf + 4 * dm;
   __shared__ double red[4];
+  __shared__ double ov[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const size_t plane = (size_t)d * g.S;
@@ -402,31 +569,19 @@ __global__ void __launch_bounds__(256) g_sweep_kernel(GSweep g) {
   // ---- terminal cost / costate: x_N in cur, lambda_N -> nxt ----
   const bool builtin = (g.phase != 2) && g.cost != 2;
   if (tid < 4) red[tid] = 0.0;
+  if (tid < 16) ov[tid] = 0.0;
   __syncthreads();
-  double J = 0.0, cr_ = 0.0, ci_ = 0.0;
-  if (builtin) {
-    double orr = 0.0, oii = 0.0;
-    for (int e = tid; e < dm; e += 256) {
-      const int c = e / d, r = e - c * d;
-      const double tr = g.T[2 * e], ti = g.T[2 * e + 1];
-      const double xr = cur[r * m + c], xi = cur[dm + r * m + c];
-      orr += tr * xr + ti * xi;
-      oii += tr * xi - ti * xr;
-    }
-    for (int off = 16; off > 0; off >>= 1) { orr += __shfl_xor_sync(0xffffffffu, orr, off); oii += __shfl_xor_sync(0xffffffffu, oii, off); }
-    if (lane == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
-  }
+  double J = 0.0;
+  CostCoef cc;
+  if (builtin)
+    cost_overlaps_accumulate(g.T, d, m, [&](int r, int c) { return make_double2(cur[r * m + c], cur[dm + r * m + c]); }, ov, tid, 256, lane);
   if (pen && g.phase != 2) {
     double ps = Jpen;
     for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
     if (lane == 0) atomicAdd(&red[2], ps);
   }
   __syncthreads();
-  if (builtin) {
-    const double Or = red[0], Oi = red[1], nn = (double)g.n * (double)g.n;
-    if (g.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
-    else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
-  }
+  if (builtin) { cost_from_overlaps(g.cost, g.n, m, ov, cc); J = cc.J; }
   if (pen && g.phase != 2) J += g.mu * red[2];
   if (tid == 0 && g.J && (builtin || (pen && g.phase != 2))) g.J[b] = J;
   if (g.phase == 1 || !g.want_grad) return;
@@ -434,7 +589,15 @@ __global__ void __launch_bounds__(256) g_sweep_kernel(GSweep g) {
     const int c = e / d, r = e - c * d;
     double lr = 0.0, li = 0.0;
     if (g.lam_final) { lr = g.lam_final[(size_t)b * 2 * dm + 2 * e]; li = g.lam_final[(size_t)b * 2 * dm + 2 * e + 1]; }
-    else if (builtin) { const double tr = g.T[2 * e], ti = g.T[2 * e + 1]; lr = cr_ * tr - ci_ * ti; li = cr_ * ti + ci_ * tr; }
+    else if (builtin) {
+      const double tr = g.T[2 * e], ti = g.T[2 * e + 1];
+      double kr = cc.cr[0], ki = cc.ci[0];
+      if (g.cost == QOC_COST_ZCAL_) {
+#pragma unroll
+        for (int q = 1; q < 4; q++) if (c == q) { kr = cc.cr[q]; ki = cc.ci[q]; }
+      }
+      lr = kr * tr - ki * ti; li = kr * ti + ki * tr;
+    }
     if (penalised(r, c)) { lr = fma(2.0 * g.mu, cur[r * m + c], lr); li = fma(2.0 * g.mu, cur[dm + r * m + c], li); }
     nxt[r * m + c] = lr; nxt[dm + r * m + c] = li;
   }
@@ -586,7 +749,7 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
   const int rows_pad = (d + 7) / 8 * 8;
   double* b0 = reinterpret_cast<double*>(gsm);
   double* b1 = b0 + rows_pad * W;
-  __shared__ double red[4];
+  __shared__ double ov[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nth = blockDim.x;
   const int b = blockIdx.x;
   for (int e = tid; e < 2 * rows_pad * W; e += nth) b0[e] = 0.0;
@@ -607,26 +770,15 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
   }
   if (g.mode == 1) return;
   const bool builtin = do_fwd && g.cost != 2 && g.mode != 4;
-  if (tid < 4) red[tid] = 0.0;
+  if (tid < 16) ov[tid] = 0.0;
   __syncthreads();
-  double cr_ = 0.0, ci_ = 0.0;
+  CostCoef cc;
   if (builtin) {
-    double orr = 0.0, oii = 0.0;
-    for (int c = 0; c < m; c++)
-      for (int r = tid; r < d; r += nth) {
-        const double2 t = reinterpret_cast<const double2*>(g.T)[r + (size_t)d * c];
-        const double2 x = *reinterpret_cast<const double2*>(cur + r * W + 2 * c);
-        orr += t.x * x.x + t.y * x.y;
-        oii += t.x * x.y - t.y * x.x;
-      }
-    for (int off = 16; off > 0; off >>= 1) { orr += __shfl_xor_sync(0xffffffffu, orr, off); oii += __shfl_xor_sync(0xffffffffu, oii, off); }
-    if (lane == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
+    cost_overlaps_accumulate(g.T, d, m, [&](int r, int c) { return *reinterpret_cast<const double2*>(cur + r * W + 2 * c); },
+                             ov, tid, nth, lane);
     __syncthreads();
-    const double Or = red[0], Oi = red[1], nn = (double)g.n * (double)g.n;
-    double J;
-    if (g.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
-    else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
-    if (tid == 0 && g.J) g.J[b] = J;
+    cost_from_overlaps(g.cost, g.n, m, ov, cc);
+    if (tid == 0 && g.J) g.J[b] = cc.J;
   }
   if (!do_bwd) return;
   for (int c = 0; c < m; c++)
@@ -635,7 +787,12 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
       if (g.lam_final) l = reinterpret_cast<const double2*>(g.lam_final + (size_t)b * 2 * dm)[r + (size_t)d * c];
       else if (builtin) {
         const double2 t = reinterpret_cast<const double2*>(g.T)[r + (size_t)d * c];
-        l = make_double2(cr_ * t.x - ci_ * t.y, cr_ * t.y + ci_ * t.x);
+        double kr = cc.cr[0], ki = cc.ci[0];
+        if (g.cost == QOC_COST_ZCAL_) {
+#pragma unroll
+          for (int q = 1; q < 4; q++) if (c == q) { kr = cc.cr[q]; ki = cc.ci[q]; }
+        }
+        l = make_double2(kr * t.x - ki * t.y, kr * t.y + ki * t.x);
       }
       *reinterpret_cast<double2*>(nxt + r * W + 2 * c) = l;
     }

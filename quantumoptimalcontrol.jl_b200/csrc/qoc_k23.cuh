@@ -12,6 +12,7 @@
 // States are d x m with m <= 8: one 8-wide DMMA column tile; the d x d operand (U_k, U_k^dagger via the
 // transposed fragment pattern, dU_k/du_j, Q_seg) is staged HBM -> shared memory through a cp.async ring.
 #pragma once
+#include "qoc_cost.cuh"
 #include "qoc_tiles.cuh"
 
 namespace qoc {
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(C::NT * 32, 1) k2_kernel(K23Params p) {
   double* tail = ring + (size_t)K2_NST * slot_d;  // 8*S zero pad
   double* xbuf = tail + 8 * S;                    // 2 buffers x (re, im) x d*m
   double* red = xbuf + 4 * d * m;                 // 4 doubles
+  __shared__ double ov[16];                       // per-column overlaps diag(T' x_N)
   {
     double2* z = reinterpret_cast<double2*>(ring);
     const int total2 = (K2_NST * slot_d + 8 * S) / 2;
@@ -227,26 +229,14 @@ __global__ void __launch_bounds__(C::NT * 32, 1) k2_kernel(K23Params p) {
     const bool have_x = (p.k2_phase != 2);                 // phase 2 has no forward pass in this launch
     const bool builtin = have_x && p.cost != 2;
     if (tid < 4) red[tid] = 0.0;
+    if (tid < 16) ov[tid] = 0.0;
     if (!have_x && pen) state_from_global(XR(cur), XI(cur), p.x_final + (size_t)b * 2 * dm, d, m, tid, NTH);
     __syncthreads();
-    double J = 0.0, cr_ = 0.0, ci_ = 0.0;
-    if (builtin) {
-      // Omega = tr(T' x) = sum conj(T) .* x      src/penalty_fcns.jl:16,20
-      double orr = 0.0, oii = 0.0;
-      for (int e = tid; e < dm; e += NTH) {
-        const int c = e / d, r = e - c * d;
-        double2 t = reinterpret_cast<const double2*>(p.T)[e];
-        const double xr = XR(cur)[r * m + c], xi = XI(cur)[r * m + c];
-        orr += t.x * xr + t.y * xi;
-        oii += t.x * xi - t.y * xr;
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        orr += __shfl_xor_sync(0xffffffffu, orr, off);
-        oii += __shfl_xor_sync(0xffffffffu, oii, off);
-      }
-      if (lane == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
-    }
+    double J = 0.0;
+    CostCoef cc;
+    if (builtin)   // per-column overlaps m_c = sum_r conj(T[r][c]) x_N[r][c]      src/penalty_fcns.jl:16,20,32
+      cost_overlaps_accumulate(p.T, d, m, [&](int r, int c) { return make_double2(XR(cur)[r * m + c], XI(cur)[r * m + c]); },
+                               ov, tid, NTH, lane);
     if (pen && p.k2_phase == 3) {
       double ps = penalty_partial(XR(cur), XI(cur), d, m, p.row_mask, p.col_mask, tid, NTH);
 #pragma unroll
@@ -254,12 +244,7 @@ __global__ void __launch_bounds__(C::NT * 32, 1) k2_kernel(K23Params p) {
       if (lane == 0) atomicAdd(&red[2], ps);
     }
     __syncthreads();
-    if (builtin) {
-      const double Or = red[0], Oi = red[1];
-      const double nn = (double)p.n * (double)p.n;
-      if (p.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
-      else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
-    }
+    if (builtin) { cost_from_overlaps(p.cost, p.n, m, ov, cc); J = cc.J; }
     if (pen && p.k2_phase == 3) J += p.mu * red[2] + p.Jpen[b];
     if (tid == 0 && p.J && (builtin || (pen && p.k2_phase == 3))) p.J[b] = J;
     // terminal costate
@@ -270,7 +255,12 @@ __global__ void __launch_bounds__(C::NT * 32, 1) k2_kernel(K23Params p) {
       if (p.lam_final) { lr = XR(cur ^ 1)[r * m + c]; li = XI(cur ^ 1)[r * m + c]; }   // same thread wrote it above
       else if (builtin) {
         double2 t = reinterpret_cast<const double2*>(p.T)[e];
-        lr = cr_ * t.x - ci_ * t.y; li = cr_ * t.y + ci_ * t.x;
+        double kr = cc.cr[0], ki = cc.ci[0];   // lambda_N[:, c] = coef_c T[:, c]; only the z-calibrated cost has per-column coefficients
+        if (p.cost == QOC_COST_ZCAL_) {
+#pragma unroll
+          for (int q = 1; q < 4; q++) if (c == q) { kr = cc.cr[q]; ki = cc.ci[q]; }
+        }
+        lr = kr * t.x - ki * t.y; li = kr * t.y + ki * t.x;
       }
       if (pen && ((p.row_mask >> r) & 1u) && ((p.col_mask >> c) & 1u)) {
         lr = fma(2.0 * p.mu, XR(cur)[r * m + c], lr);

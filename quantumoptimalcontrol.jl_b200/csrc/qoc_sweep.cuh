@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(C::NTHREADS + 64, 1) k2g_kernel(K2GParams P) {
   double* sbuf = pad + pad_rows * S;                      // 4 state buffers: xa, xb, save_x, save_l
   const int sb = RP * W;
   double* red = sbuf + 4 * sb;                            // 4 doubles
+  __shared__ double ov[16];                               // per-column overlaps diag(T' x_N)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(red + 4);
   TmaRing ring;
   ring.slots = ringp; ring.full = bars; ring.empty = bars + SW_NST; ring.slot_d = slot_d; ring.bytes = (unsigned)slot_d * 8u;
@@ -394,33 +395,16 @@ __global__ void __launch_bounds__(C::NTHREADS + 64, 1) k2g_kernel(K2GParams P) {
   if (mode == 0 || mode == 2 || mode == 4) {
     // terminal cost and costate:  lambda_N = dJfinal_dx(x_N)     src/gradient_computations.jl:46, penalty_fcns.jl:15-24
     const bool builtin = do_fwd && p.cost != 2 && mode != 4;
-    if (tid < 4) red[tid] = 0.0;
+    if (tid < 16) ov[tid] = 0.0;
     bar_rec(NT * 32);
-    double cr_ = 0.0, ci_ = 0.0;
+    CostCoef cc;
     if (builtin) {
-      if (rec) {
-        double orr = 0.0, oii = 0.0;   // Omega = tr(T' x) = sum conj(T) .* x
-        for (int c = 0; c < m; c++)
-          for (int r = tid; r < d; r += RT) {
-            const double2 t = reinterpret_cast<const double2*>(p.T)[r + d * c];
-            const double2 x = *reinterpret_cast<const double2*>(cur + r * W + 2 * c);
-            orr += t.x * x.x + t.y * x.y;
-            oii += t.x * x.y - t.y * x.x;
-          }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          orr += __shfl_xor_sync(0xffffffffu, orr, off);
-          oii += __shfl_xor_sync(0xffffffffu, oii, off);
-        }
-        if (lane == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
-      }
+      // per-column overlaps m_c = sum_r conj(T[r][c]) x_N[r][c] (Omega = tr(T'x) is their sum)
+      cost_overlaps_accumulate(p.T, d, m, [&](int r, int c) { return *reinterpret_cast<const double2*>(cur + r * W + 2 * c); },
+                               ov, tid, RT, lane);
       bar_rec(NT * 32);
-      const double Or = red[0], Oi = red[1];
-      const double nn = (double)p.n * (double)p.n;
-      double J;
-      if (p.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
-      else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
-      if (tid == 0 && g == 0 && p.J) p.J[b] = J;
+      cost_from_overlaps(p.cost, p.n, m, ov, cc);
+      if (tid == 0 && g == 0 && p.J) p.J[b] = cc.J;
     }
     if (do_bwd) {
       if (rec)
@@ -430,7 +414,12 @@ __global__ void __launch_bounds__(C::NTHREADS + 64, 1) k2g_kernel(K2GParams P) {
             if (p.lam_final) l = reinterpret_cast<const double2*>(p.lam_final + (size_t)b * 2 * dm)[r + d * c];
             else if (builtin) {
               const double2 t = reinterpret_cast<const double2*>(p.T)[r + d * c];
-              l = make_double2(cr_ * t.x - ci_ * t.y, cr_ * t.y + ci_ * t.x);
+              double kr = cc.cr[0], ki = cc.ci[0];   // per-column coefficients only for the z-calibrated cost
+              if (p.cost == QOC_COST_ZCAL_) {
+#pragma unroll
+                for (int q = 1; q < 4; q++) if (c == q) { kr = cc.cr[q]; ki = cc.ci[q]; }
+              }
+              l = make_double2(kr * t.x - ki * t.y, kr * t.y + ki * t.x);
             }
             *reinterpret_cast<double2*>(nxt + r * W + 2 * c) = l;
           }
@@ -483,7 +472,7 @@ __global__ void __launch_bounds__(256) shard_boundary_kernel(ShardBoundary q) {
   const int d = q.d, m = q.m, dm = d * m, tid = threadIdx.x;
   double2* xa = reinterpret_cast<double2*>(smem_raw);   // column-major d x m, like the ABI
   double2* xb = xa + dm;
-  __shared__ double red[2];
+  __shared__ double ov[16];
   for (int e = tid; e < dm; e += 256) xa[e] = reinterpret_cast<const double2*>(q.x0)[e];
   __syncthreads();
   auto matvec = [&](const double* Sp, bool adj, const double2* in, double2* out) {
@@ -508,26 +497,22 @@ __global__ void __launch_bounds__(256) shard_boundary_kernel(ShardBoundary q) {
     double2* t = cur; cur = nxt; nxt = t;
   }
   // cost and terminal costate (src/penalty_fcns.jl:15-24, test/test_gradient_computation.jl:24-25)
-  if (tid < 2) red[tid] = 0.0;
+  if (tid < 16) ov[tid] = 0.0;
   __syncthreads();
-  double orr = 0.0, oii = 0.0;
+  cost_overlaps_accumulate(q.T, d, m, [&](int r, int c) { return cur[r + d * c]; }, ov, tid, 256, tid & 31);
+  __syncthreads();
+  CostCoef cc;
+  cost_from_overlaps(q.cost, q.n, m, ov, cc);
+  if (tid == 0 && q.J) *q.J = cc.J;
   for (int e = tid; e < dm; e += 256) {
     const double2 t = reinterpret_cast<const double2*>(q.T)[e];
-    const double2 x = cur[e];
-    orr += t.x * x.x + t.y * x.y;
-    oii += t.x * x.y - t.y * x.x;
-  }
-  for (int off = 16; off > 0; off >>= 1) { orr += __shfl_xor_sync(0xffffffffu, orr, off); oii += __shfl_xor_sync(0xffffffffu, oii, off); }
-  if ((tid & 31) == 0) { atomicAdd(&red[0], orr); atomicAdd(&red[1], oii); }
-  __syncthreads();
-  const double Or = red[0], Oi = red[1], nn = (double)q.n * (double)q.n;
-  double J, cr_, ci_;
-  if (q.cost == 0) { J = 1.0 - (Or * Or + Oi * Oi) / nn; cr_ = -2.0 * Or / nn; ci_ = -2.0 * Oi / nn; }
-  else { const double a = sqrt(Or * Or + Oi * Oi); J = 1.0 - a; cr_ = -Or / a; ci_ = -Oi / a; }
-  if (tid == 0 && q.J) *q.J = J;
-  for (int e = tid; e < dm; e += 256) {
-    const double2 t = reinterpret_cast<const double2*>(q.T)[e];
-    nxt[e] = make_double2(cr_ * t.x - ci_ * t.y, cr_ * t.y + ci_ * t.x);
+    const int c = e / d;
+    double kr = cc.cr[0], ki = cc.ci[0];
+    if (q.cost == QOC_COST_ZCAL_) {
+#pragma unroll
+      for (int k = 1; k < 4; k++) if (c == k) { kr = cc.cr[k]; ki = cc.ci[k]; }
+    }
+    nxt[e] = make_double2(kr * t.x - ki * t.y, kr * t.y + ki * t.x);
   }
   __syncthreads();
   { double2* t = cur; cur = nxt; nxt = t; }

@@ -169,13 +169,7 @@ def infidelity(U_target, Uf, calibration="lms_phase"):
     return 1 - abs_trace_phase_calibrated(U_target.conj().T @ np.asarray(Uf), calibration) / 4
 
 
-def setup_infidelity_zcalibrated(x_target):
-    """src/penalty_fcns.jl:27-42 -> (J, dJ_dx) host closures on d x 4 states (or batches (..., d, 4)); pass dJ_dx to
-    grape_sensitivity like any other closure: only x[end] and the terminal costate cross PCIe."""
-    T = np.asarray(x_target, dtype=np.complex128)
-    if T.ndim != 2 or T.shape[1] != 4:
-        raise ValueError("Only works for two-qubit gates, x_target must have four columns")
-
+def _zcal_host(T):
     def J(x):
         m = np.sum(T.conj() * np.asarray(x), axis=-2)  # diag(T' x)
         return 1 - abs_sum_phase_calibrated(m) ** 2 / 16
@@ -186,3 +180,35 @@ def setup_infidelity_zcalibrated(x_target):
         return (-2 * np.asarray(F)[..., None, None] / 16) * T * dF[..., None, :]
 
     return J, dJ_dx
+
+
+def setup_infidelity_zcalibrated(x_target, device=True):
+    """src/penalty_fcns.jl:27-42 -> (J, dJ_dx) on d x 4 states (or batches (..., d, 4)).
+
+    device=True (default): the returned callables are built-in costs (QOC_COST_ZCAL): handed to propagate / grape_sensitivity /
+    evaluate they make the library reduce m = diag(T'x), run the golden-section search and the rrule, and form J and
+    lambda_N per pulse on the device -- x[end] never crosses the bus.  Called directly on numpy arrays they evaluate the same
+    formulas on the host (vectorised over a batch).  device=False: plain host closures, the reference's own route
+    (x[end] down, terminal costate up)."""
+    T = np.asarray(x_target, dtype=np.complex128)
+    if T.ndim != 2 or T.shape[1] != 4:
+        raise ValueError("Only works for two-qubit gates, x_target must have four columns")
+    Jh, dJh = _zcal_host(T)
+    if not device:
+        return Jh, dJh
+    from .grape import _BuiltinCost
+    from ._lib import COST_ZCAL
+
+    class _ZcalJ(_BuiltinCost):
+        kind = COST_ZCAL
+
+        def __call__(self, x):
+            return Jh(x)
+
+    class _ZcalGrad(_BuiltinCost):
+        kind = COST_ZCAL
+
+        def __call__(self, x):
+            return dJh(x)
+
+    return _ZcalJ(T, 4), _ZcalGrad(T, 4)

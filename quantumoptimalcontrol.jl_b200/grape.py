@@ -20,11 +20,11 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (COST_ABS_TRACE, COST_INFIDELITY, COST_NONE, ORDER_FRECHET)  # noqa: F401
+from ._lib import (COST_ABS_TRACE, COST_INFIDELITY, COST_NONE, COST_ZCAL, ORDER_FRECHET)  # noqa: F401
 
 __all__ = ["QOCError", "GrapeCache", "setup_grape_cache", "propagate", "grape_sensitivity", "evaluate",
            "setup_infidelity", "setup_infidelity_abs_trace", "setup_state_penalty", "setup_bilinear_matrices",
-           "ORDER_FRECHET", "COST_INFIDELITY", "COST_ABS_TRACE", "COST_NONE"]
+           "ORDER_FRECHET", "COST_INFIDELITY", "COST_ABS_TRACE", "COST_NONE", "COST_ZCAL"]
 
 
 class QOCError(RuntimeError):
@@ -152,6 +152,7 @@ class GrapeCache:
         self._cost_key = None
         self._penalty = None
         self.J = None
+        self.x_final = None   # set by propagate(); closure costs in grape_sensitivity read it
 
     # -- handle management --
     def _ensure(self, A0, A, x0, penalty=None):
@@ -292,8 +293,10 @@ def _u_arr(u, cache):
     return np.ascontiguousarray(np.transpose(u, (0, 2, 1)))  # (b, k, j): j fastest
 
 
-def propagate(A0, A, u, x0, cache=None, Jfinal=None, penalty=None):
+def propagate(A0, A, u, x0, cache=None, Jfinal=None, penalty=None, eager_jacobians=False):
     """src/gradient_computations.jl:2-32.  Returns the cache (cache.x are the states; the reference returns x).
+    Like the reference's propagate this computes the exponentials only; grape_sensitivity adds the Jacobians on the cached u
+    (eager_jacobians=True produces them here, in the same kernel pass, when a gradient always follows).
     Jfinal: optional built-in cost from setup_infidelity*: J = Jfinal(x[end]) (+ sum(L, x)) is then formed on the
     device and left in cache.J (examples/ipopt_callbacks_exp.jl:18).  penalty = (L, dL_dx) from setup_state_penalty."""
     u = np.asarray(u, dtype=np.float64)
@@ -305,6 +308,7 @@ def propagate(A0, A, u, x0, cache=None, Jfinal=None, penalty=None):
     if Jfinal is not None:
         cache._set_cost(Jfinal)
     lib = _lib.load()
+    cache._check(lib.qoc_set_eager_jacobians(cache._h, 1 if eager_jacobians else 0))
     uu = _u_arr(u, cache)
     J = np.zeros(cache.batch)
     xf = np.zeros((cache.d, cache.m, cache.batch), dtype=np.complex128, order="F")
@@ -331,6 +335,8 @@ def grape_sensitivity(A0, A, dJfinal_dx, u, x0, cache, dUkdp_order=3, dL_dx=None
         cache._check(lib.qoc_gradient(cache._h, _dptr(uu), None, _dptr(g)))
     else:
         xf = cache.x_final
+        if xf is None:  # evaluate() alone does not bring x[end] to the host
+            raise QOCError(_lib.ERR_STALE_CACHE, "a host-closure dJfinal_dx needs propagate() on this cache first")
         if cache.batch == 1:
             lam = _c128(dJfinal_dx(xf)).reshape(cache.d, cache.m, 1, order="F")
         else:
@@ -353,6 +359,7 @@ def evaluate(cache, A0, A, u, x0, cost, dUkdp_order=None, penalty=None):
     J = np.zeros(cache.batch)
     g = np.zeros(uu.shape)
     cache._check(lib.qoc_eval(cache._h, _dptr(uu), _dptr(J), _dptr(g)))
+    cache.x_final = None   # belongs to an earlier propagate(), not to this u
     if cache.batch == 1:
         return float(J[0]), g.T.copy()
     return J, np.transpose(g, (0, 2, 1)).copy()

