@@ -179,6 +179,7 @@ def _zcal_host(T):
         F, dF = abs_sum_phase_calibrated_rrule(m)
         return (-2 * np.asarray(F)[..., None, None] / 16) * T * dF[..., None, :]
 
+    J.batched = dJ_dx.batched = True   # both accept (..., d, 4) stacks (grape_sensitivity hands a batch over in one call)
     return J, dJ_dx
 
 
@@ -201,12 +202,14 @@ def setup_infidelity_zcalibrated(x_target, device=True):
 
     class _ZcalJ(_BuiltinCost):
         kind = COST_ZCAL
+        host_J, host_grad = staticmethod(Jh), staticmethod(dJh)
 
         def __call__(self, x):
             return Jh(x)
 
     class _ZcalGrad(_BuiltinCost):
         kind = COST_ZCAL
+        host_J, host_grad = staticmethod(Jh), staticmethod(dJh)
 
         def __call__(self, x):
             return dJh(x)

@@ -339,6 +339,8 @@ def grape_sensitivity(A0, A, dJfinal_dx, u, x0, cache, dUkdp_order=3, dL_dx=None
             raise QOCError(_lib.ERR_STALE_CACHE, "a host-closure dJfinal_dx needs propagate() on this cache first")
         if cache.batch == 1:
             lam = _c128(dJfinal_dx(xf)).reshape(cache.d, cache.m, 1, order="F")
+        elif getattr(dJfinal_dx, "batched", False):   # a closure that takes the whole (batch, d, m) stack at once
+            lam = np.transpose(np.asarray(dJfinal_dx(xf), dtype=np.complex128), (1, 2, 0))
         else:
             lam = np.asfortranarray(np.stack([_c128(dJfinal_dx(xf[b])) for b in range(cache.batch)], axis=2))
         lam = np.asfortranarray(lam)

@@ -127,7 +127,7 @@ def _builtin_cost_torch(cost, x):
         return float(1 - a), -(om / a) * T
     if cost.kind == COST_ZCAL:        # src/penalty_fcns.jl:27-42 (scalar tail on four numbers: host formulas)
         xh = x.cpu().numpy()
-        return float(type(cost).__call__.__globals__["np"].real(1.0)) * _zcal_J(cost, xh), torch.as_tensor(np.asarray(cost(xh)), device=x.device)
+        return float(cost.host_J(xh)), torch.as_tensor(np.asarray(cost.host_grad(xh), dtype=np.complex128), device=x.device)
     raise ValueError("unknown built-in cost")
 
 
