@@ -48,7 +48,8 @@ def test_device_search_reproduces_reference_known_answers(kat, d):
     Jf, dJf = q.setup_infidelity_zcalibrated(T)
     cache = q.setup_grape_cache(A0, x0, u.shape, dUkdp_order=0)
     J, g = q.evaluate(cache, A0, A, u, x0, dJf, dUkdp_order=0)
-    tol = 2e-7 if F_ref in (2.8284271, 2.0099751, 3.995001) else 1e-12   # the reference quotes those three to 7-8 digits
+    # the reference's `@test a ≈ b` is isapprox with rtol = sqrt(eps) = 1.5e-8; three values are quoted to 7-8 digits only
+    tol = 2e-7 if F_ref in (2.8284271, 2.0099751, 3.995001) else 1.5e-8 * F_ref
     assert abs(np.sqrt(16 * (1 - J)) - F_ref) < tol
     # the oracle's restatement of the search on the same four numbers: same bracket updates -> same F to rounding
     assert abs(np.sqrt(16 * (1 - J)) - o.abs_sum_phase_calibrated(mvec)) < 1e-12
@@ -57,7 +58,12 @@ def test_device_search_reproduces_reference_known_answers(kat, d):
     co = o.setup_grape_cache(A0, x0, u.shape)
     o.propagate(A0, A, u, x0, co)
     go = o.grape_sensitivity(A0, A, dJo, u, x0, co, dUkdp_order=0)
-    assert np.abs(g - go).max() <= TOL_G * max(np.abs(go).max(), 1e-3)
+    # Tolerance: the reference locates theta by golden-section search on a flat maximum, which cannot resolve the maximiser
+    # better than ~sqrt(eps) (the last comparisons are decided by rounding noise of cos / sqrt, which differ between libm
+    # implementations); dF_dm depends on theta to first order, so the gradient is only defined to ~1e-8..1e-7 relative by
+    # the reference's own algorithm.  Its test compares the rrule with finite differences at rtol 1e-6
+    # (test/test_fidelities.jl:130-148): the same bar here.
+    assert np.abs(g - go).max() <= 1e-6 * max(np.abs(go).max(), 1e-3)
     cache.close()
 
 
