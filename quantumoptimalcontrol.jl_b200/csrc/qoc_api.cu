@@ -57,7 +57,8 @@ struct qoc_handle {
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
   bool gs2 = false;
   bool k1_skewh = false;      // A0 and every A_j skew-Hermitian (bitwise): k1s_kernel forms A E + E A, A2 M2 + M2 A2, X E as P + P^dagger
-  bool k1s_ok = false;        // d <= 9, nc <= 4: the warp-per-slice small-dimension kernel
+  bool k1s_ok = false;        // d <= 9, nc <= 4: the small-dimension kernel (nine lanes per slice, three slices per warp)
+  int k1s_wpb = 0;            // its warps per CTA (what fits shared memory)
   bool k1_sym = false;        // ... with symmetric H0, H_j: Pade denominator inverted through the real SPD matrix N N^dagger
   bool k1_realh = false;      // K1 real-Hamiltonian fast path (Re A0 = Re A_j = 0, Frechet mode, [13/13] instantiation)
   bool k1_low = true;         // K1 instantiation with the low-degree Pade forms (false when ||A0||_1 alone is far above theta7)           // second-generation general-path sweeps (no running penalty)
@@ -341,23 +342,26 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     QOC_CUDA(h, cudaFuncSetAttribute(k2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k2_smem));
     {
       const char* off = getenv("QOC_NO_K1S");
-      h->k1s_ok = p.d <= K1S_DMAX && p.nc <= K1S_MAXNC && C::S == 12 && !(off && off[0] == '1') &&
-                  k1s_smem_bytes(p.nc) <= (size_t)dp.sharedMemPerBlockOptin;
+      h->k1s_wpb = k1s_warps_per_block(p.nc, (size_t)dp.sharedMemPerBlockOptin);
+      { const char* w = getenv("QOC_K1S_WPB"); if (w && atoi(w) > 0 && atoi(w) < h->k1s_wpb) h->k1s_wpb = atoi(w); }
+      h->k1s_ok = p.d <= K1S_DMAX && p.nc <= K1S_MAXNC && C::S == 12 && !(off && off[0] == '1') && h->k1s_wpb >= 1;
       if (h->k1s_ok)
-        QOC_CUDA(h, cudaFuncSetAttribute(k1s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1s_smem_bytes(p.nc)));
+        QOC_CUDA(h, cudaFuncSetAttribute(k1s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)k1s_smem_bytes(p.nc, h->k1s_wpb)));
     }
     int occ = 1;
     QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_kernel<C, true>, C::NTHREADS + NSW * 32, h->k1_smem));
     if (occ < 1) occ = 1;
     long long target = (long long)h->nsm * occ;
-    if (h->k1s_ok && target < (long long)h->nsm * K1S_WPB) target = (long long)h->nsm * K1S_WPB;
+    const long long k1s_workers = (long long)h->nsm * h->k1s_wpb * K1S_GPW;   // lane groups on the chip
+    if (h->k1s_ok && target < k1s_workers) target = k1s_workers;
     long long spp = (target + p.batch - 1) / p.batch;
     if (spp < 1) spp = 1;
     if (spp > p.nt) spp = p.nt;
     if (h->k1s_ok && p.batch > 1) {
       // K1S workers (warps) take whole segments: pick the segment count that wastes least of the last wave
       // (4096 pulses on 1184 workers: 1 segment per pulse fills 3.46 waves, 2 fill 6.92)
-      const long long W = (long long)h->nsm * K1S_WPB;
+      const long long W = k1s_workers;
       double best = 1e30; long long bs = spp;
       for (long long s2 = spp; s2 < spp + 6 && s2 <= p.nt; s2++) {
         const long long ns = s2 * p.batch, waves = (ns + W - 1) / W;
@@ -864,8 +868,9 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
     // NW compute warps + 4 service warps
     if (h->k1s_ok) {
       // small-dimension form: one warp per segment, no CTA barriers (qoc_k1s.cuh)
-      const int ctas = (h->nseg + K1S_WPB - 1) / K1S_WPB;
-      k1s_kernel<<<ctas < h->nsm ? ctas : h->nsm, K1S_WPB * 32, k1s_smem_bytes(p.nc), st>>>(k, h->S);
+      const int per_cta = h->k1s_wpb * K1S_GPW;
+      const int ctas = (h->nseg + per_cta - 1) / per_cta;
+      k1s_kernel<<<ctas < h->nsm ? ctas : h->nsm, h->k1s_wpb * 32, k1s_smem_bytes(p.nc, h->k1s_wpb), st>>>(k, h->S);
     } else if (h->k1_realh) k1_kernel<C, false, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
     else if (h->k1_low) k1_kernel<C, true><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
     else k1_kernel<C, false><<<h->k1_grid, C::NTHREADS + NSW * 32, h->k1_smem, st>>>(k);
