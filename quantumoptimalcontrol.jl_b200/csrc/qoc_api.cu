@@ -49,6 +49,7 @@ struct qoc_handle {
   int gchunk = 0, gnw = 0;
   double* gW = nullptr;       // workspace: gnw slots x gchunk slices
   double* dumax = nullptr;    // max_k |u_jk| per control
+  double* dk1s_scr = nullptr; // k1s_kernel: per-lane-group scratch (A4, W)
   int* dpiv = nullptr;        // pivot rows of the blocked Gauss-Jordan inverse: gchunk x d
   double* dbnd = nullptr;     // time sharding: x_start and lambda_end of the local segment (2 x d x m c128)
   double *dB = nullptr, *dc = nullptr, *ddc = nullptr;   // spline basis, coefficients, dJ/dc (qoc_set_basis / qoc_eval_coeffs)
@@ -215,6 +216,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->h_mail) cudaFreeHost(h->h_mail);
   if (h->dsync) cudaFree(h->dsync);
   if (h->dpiv) cudaFree(h->dpiv);
+  if (h->dk1s_scr) cudaFree(h->dk1s_scr);
   if (h->dpen_rows) cudaFree(h->dpen_rows);
   if (h->dpen_cols) cudaFree(h->dpen_cols);
   for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
@@ -448,6 +450,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   CR(cudaMalloc(&h->dJ, (size_t)p.batch * 8));
   CR(cudaMalloc(&h->dg, nsl * p.nc * 8));
   CR(cudaMalloc(&h->dflops, 16));
+  if (h->k1s_ok) CR(cudaMalloc(&h->dk1s_scr, (size_t)h->nsm * K1S_MAXWPB * K1S_GPW * 2 * K1S_MSZ * 16));
   CR(cudaMalloc(&h->dS, slotB));
   {
     auto norm1 = [&](const double* M) {
@@ -854,7 +857,7 @@ static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream
   k.d = p.d; k.nc = p.nc; k.nt = p.nt; k.batch = p.batch; k.order = p.order;
   k.nseg = h->nseg; k.seg_per_pulse = h->spp; k.want_jac = want_jac ? 1 : 0; k.sym = h->k1_sym ? 1 : 0; k.skewh = h->k1_skewh ? 1 : 0;
   k.A0p = h->dA0p; k.Ap = h->dAp; k.u = d_u; k.U = h->dU; k.L = h->dL; k.Q = h->dQ;
-  k.flops = h->dflops; k.status = h->dstatus;
+  k.flops = h->dflops; k.status = h->dstatus; k.scr = h->dk1s_scr;
   k.theta13 = (p.order == QOC_ORDER_FRECHET) ? 4.74 : 5.4;
   // degree switch points: Higham-2005 table as rounded by the reference's dependency (Taylor mode: only expm is
   // approximated), Al-Mohy-Higham l_m for the Frechet pair.  QOC_PADE13=1 forces the [13/13] form (A/B measurements).

@@ -41,6 +41,7 @@ struct K1Params {
   double theta13;          // scaling threshold: 5.4 (Higham-2005 / reference) or 4.74 (Frechet, Al-Mohy-Higham)
   double theta5, theta7;   // ||X||_1 <= theta5: [5/5] Pade, <= theta7: [7/7], else [13/13] with scaling
                            // (0.25 / 0.95 in Taylor mode = the reference's expm table, 0.2 / 0.783 in Frechet mode)
+  double* scr;             // k1s_kernel only: per lane group, two 9 x 9 complex matrices (A4 and W of the slice in flight)
   long long* dbg;          // optional timeline of CTA 0: [slice][16] clock64 stamps (NULL in production)
   int dbg_slices;
   int dbg_flags;           // bit 0: skip the service inverse (timing experiment, results invalid)

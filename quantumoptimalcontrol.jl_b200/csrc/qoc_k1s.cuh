@@ -17,9 +17,9 @@
 // the 4096-pulse batch, 79 % of the kernel's SM cycles; FP64 pipe 29 %).  The 3 x 3 block needs 6 LDS.128 per 36 DFMA
 // -- 2.7 bytes per DFMA instead of 5.3 -- and the matrix set is trimmed to nine per slice ([5/5] and [7/7] Pade only:
 // beyond theta_7 the generator is scaled down further, which costs the same number of products as [13/13] would, see
-// below; the running segment product and, when squarings follow, the L_j pass through their global slots) so that 18
-// slices stay resident per SM: six warps.  One warp per scheduler cannot hide the FP64 issue latency (measured: 2.9
-// cycles per DFMA in the dense product loops of a lone warp).
+// below; A4, W, the running segment product and, when squarings follow, the L_j pass through L2-resident global slots)
+// so that 24 slices stay resident per SM: eight warps, two per scheduler.  One warp per scheduler cannot hide the FP64
+// issue latency (measured: 2.9 cycles per DFMA in the dense product loops of a lone warp; 4 / 6 warps: 6.67 / 5.69 ms).
 //
 // Degrees: ||X||_1 <= theta_5 -> [5/5]; otherwise [7/7] with s = ceil(log2(||X||_1 / theta_7))+ squarings.  ([13/13] buys
 // a factor 5.7 in norm for two extra products and four more per control, i.e. the price of two squarings: the same
@@ -40,9 +40,11 @@ __host__ __device__ __forceinline__ constexpr int k1s_idx(int r, int c) { return
 constexpr int K1S_GPW = 3;                  // lane groups (slices) per warp
 constexpr int K1S_MAXWPB = 8;
 constexpr int K1S_MAXNC = 4;
-// group-private matrices: nine, whatever nc.  The running segment product Q and (only when squarings follow) the L_j
-// live in their global slots, which stay in L2, and pass through a temporary when they are an operand.
-enum : int { sA_ = 0, sA2_, sA4_, sW_, sN_, sR_, sX1_, sX2_, sX3_, K1S_FIXED };
+// group-private matrices: seven, whatever nc.  Everything that is an operand only once per control passes through a
+// temporary instead of owning a slot: A4 and W (homes: sX3_ / sX1_ while the Pade approximant is formed, then a
+// per-group global scratch that stays in L2, prefetched into registers one product ahead), the running segment product Q
+// and (only when squarings follow) the L_j (their own global slots).
+enum : int { sA_ = 0, sA2_, sN_, sR_, sX1_, sX2_, sX3_, K1S_FIXED };
 __host__ __device__ constexpr int k1s_mats(int) { return K1S_FIXED; }
 // complex elements between the matrix sets of consecutive groups: (stride in 16-byte units) = 4 mod 8, so that the
 // groups that share a quarter-warp hit disjoint bank quads in the operand loads (block rows are 27 = 3 mod 8 units apart,
@@ -330,6 +332,26 @@ __device__ __forceinline__ C9 k1s_load_slot(const K1SCtx& c, bool on, const doub
   return x;
 }
 
+// per-group global scratch (block-major like shared memory: a lane's block is 144 contiguous bytes, and every lane only
+// ever re-reads the block it wrote itself)
+__device__ __forceinline__ void k1s_scr_store(const K1SCtx& c, double2* m, const C9& x) {
+  if (!c.act) return;
+  double2* q = m + 9 * (3 * c.br + c.bc);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) q[3 * i + j] = x.v[i][j];
+}
+__device__ __forceinline__ C9 k1s_scr_load(const K1SCtx& c, const double2* m) {
+  C9 x;
+  const double2* q = m + 9 * (3 * c.br + c.bc);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) x.v[i][j] = q[3 * i + j];
+  return x;
+}
+
 __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int S) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned FULL = 0xffffffffu;
@@ -359,6 +381,8 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
   }
   c.base = sm + (size_t)(warp * K1S_GPW + c.g) * gstride;
   c.E = shE;
+  double2* gA4 = reinterpret_cast<double2*>(p.scr) + (size_t)((blockIdx.x * wpb + warp) * K1S_GPW + c.g) * 2 * K1S_MSZ;
+  double2* gW = gA4 + K1S_MSZ;
   c.d = d; c.lane = lane;
   c.kd = (d + 2) / 3 * 3;
   c.act = lane < 27;
@@ -426,7 +450,6 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
       scale9(a, scl);
       c.st(c.M(sA_), a);
     }
-    if (taylor && p.want_jac && p.order >= 2) c.st(c.M(sX1_), x);   // the unscaled generator, operand of the Taylor Jacobian
     __syncwarp();
 
     // ---- Pade numerator / denominator: U = A W, N = V - U ----
@@ -436,20 +459,23 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
     c.st(c.M(sA2_), a2);
     __syncwarp();
     c.macc(a4, c.M(sA2_), c.M(sA2_));
-    c.st(c.M(sA4_), a4);
+    const bool frechet_on = p.want_jac && !taylor;
+    c.st(c.M(sX3_), a4);
+    if (frechet_on && qd == 7) k1s_scr_store(c, gA4, a4);
     __syncwarp();
     if (qd == 7) {
       C9 a6 = K1SCtx::zero();
-      c.macc(a6, c.M(sA2_), c.M(sA4_));
+      c.macc(a6, c.M(sA2_), c.M(sX3_));
       w = lin3(b[7], a6, b[5], a4, b[3], a2); c.add_eye(w, b[1]);
       nn = lin3(b[6], a6, b[4], a4, b[2], a2); c.add_eye(nn, b[0]);
     } else {
       w = lin2(b[5], a4, b[3], a2); c.add_eye(w, b[1]);
       nn = lin2(b[4], a4, b[2], a2); c.add_eye(nn, b[0]);
     }
-    c.st(c.M(sW_), w);
+    c.st(c.M(sX1_), w);
+    if (frechet_on) k1s_scr_store(c, gW, w);
     __syncwarp();
-    c.macc(uu, c.M(sA_), c.M(sW_));
+    c.macc(uu, c.M(sA_), c.M(sX1_));
     c.st(c.M(sX2_), uu);      // U lives in a temporary: it is dead once R has been formed
     axpy9(nn, -1.0, uu);
     // ---- N^-1 (registers -> sN_) and R = I + 2 N^-1 U ----
@@ -465,12 +491,18 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
 
     // ---- the reference's truncated Taylor Jacobian (src/gradient_computations.jl:177-213, dt = 1, same association
     //      order): E + (EX + XE)/2 + (EX X + XE X + X XE)/6 + (EX X2 + XE X2 + X2 EX + X2 XE)/24 ----
-    // slots: X (unscaled) in sX1_, EX in sX2_ (U is dead: R has been formed), XE in sX3_, X2 in sA2_ and scratch in sW_
-    // (the Pade operands are dead too)
+    // slots: X (unscaled) in sA_ (X = 2^s A exactly: rescaled in place, the Pade operands are dead), EX in sX2_, XE in
+    // sX3_, X2 in sA2_, scratch in sX1_
     if (p.want_jac && taylor) {
+      if (sq > 0 && p.order >= 2) {
+        C9 a = c.ld(c.M(sA_));
+        scale9(a, __hiloint2double((1023 + sq) << 20, 0));
+        c.st(c.M(sA_), a);      // (each lane rewrites the block it read)
+        __syncwarp();
+      }
       if (p.order >= 4) {
         C9 x2 = K1SCtx::zero();
-        c.macc(x2, c.M(sX1_), c.M(sX1_));
+        c.macc(x2, c.M(sA_), c.M(sA_));
         c.st(c.M(sA2_), x2);
       }
       for (int j = 0; j < nc; j++) {
@@ -478,25 +510,25 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
         C9 out = c.ld(E);
         if (p.order >= 2) {
           C9 ex = K1SCtx::zero(), xe = K1SCtx::zero();
-          c.macc(ex, E, c.M(sX1_));
+          c.macc(ex, E, c.M(sA_));
           c.st(c.M(sX2_), ex);
           if (p.skewh) {          // X, E skew-Hermitian: X E = (E X)^dagger
             __syncwarp();
             xe = c.ldH(c.M(sX2_));
-          } else c.macc(xe, c.M(sX1_), E);
+          } else c.macc(xe, c.M(sA_), E);
           c.st(c.M(sX3_), xe);
           __syncwarp();
           axpy9(out, 0.5, ex);
           axpy9(out, 0.5, xe);
           if (p.order >= 3) {
             C9 t3 = K1SCtx::zero();
-            c.macc(t3, c.M(sX2_), c.M(sX1_));
+            c.macc(t3, c.M(sX2_), c.M(sA_));
             if (p.skewh) {        // X (X E) = -((E X) X)^dagger
-              c.st(c.M(sW_), t3);
+              c.st(c.M(sX1_), t3);
               __syncwarp();
-              axpy9(t3, -1.0, c.ldH(c.M(sW_)));
-            } else c.macc(t3, c.M(sX1_), c.M(sX3_));
-            c.macc(t3, c.M(sX3_), c.M(sX1_));
+              axpy9(t3, -1.0, c.ldH(c.M(sX1_)));
+            } else c.macc(t3, c.M(sA_), c.M(sX3_));
+            c.macc(t3, c.M(sX3_), c.M(sA_));
             axpy9(out, 1.0 / 6.0, t3);
           }
           if (p.order >= 4) {
@@ -513,7 +545,7 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
       }
     }
     // ---- exact Frechet derivative per control (Al-Mohy & Higham 2009, Alg. 6.4; E unscaled, 2^-s on the result) ----
-    // temporaries: sX1_ = M2 then D, sX2_ = M4 then rhs, sX3_ = scratch of the adjoint shortcuts then Lw
+    // temporaries: sX1_ = M2 then D, sX2_ = M4 then W then rhs, sX3_ = scratch of the adjoint shortcuts then A4 then Lw
     if (p.want_jac && !taylor) {
       for (int j = 0; j < nc; j++) {
         const double2* E = c.E + (size_t)j * K1S_MSZ;
@@ -528,6 +560,8 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
         } else c.macc(m2, E, c.M(sA_));
         c.st(c.M(sX1_), m2);
         __syncwarp();
+        C9 a4g;
+        if (qd == 7) a4g = k1s_scr_load(c, gA4);   // in flight during the next product
         c.macc(m4, c.M(sA2_), c.M(sX1_));
         if (p.skewh) {
           c.st(c.M(sX3_), m4);
@@ -537,19 +571,27 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
         c.st(c.M(sX2_), m4);
         __syncwarp();
         if (qd == 7) {
+          c.st(c.M(sX3_), a4g);      // A4 back from its scratch
+          __syncwarp();
           C9 m6 = K1SCtx::zero();
-          c.macc(m6, c.M(sA4_), c.M(sX1_));
+          c.macc(m6, c.M(sX3_), c.M(sX1_));
           c.macc(m6, c.M(sX2_), c.M(sA2_));
           lw = lin3(b[7], m6, b[5], m4, b[3], m2);
           lv = lin3(b[6], m6, b[4], m4, b[2], m2);
+          __syncwarp();              // every lane has read A4
         } else {
           lw = lin2(b[5], m4, b[3], m2);
           lv = lin2(b[4], m4, b[2], m2);
         }
         c.st(c.M(sX3_), lw);
         __syncwarp();
-        c.macc(lu, c.M(sA_), c.M(sX3_));
-        c.macc(lu, E, c.M(sW_));
+        {
+          const C9 wg = k1s_scr_load(c, gW);   // in flight during A Lw
+          c.macc(lu, c.M(sA_), c.M(sX3_));
+          c.st(c.M(sX2_), wg);                 // (M4 is dead)
+        }
+        __syncwarp();
+        c.macc(lu, E, c.M(sX2_));
         // rhs = (Lu + Lv) + (Lu - Lv) R ;  L = 2^-s N^-1 rhs
         C9 dd = lu, rhs = lu;
         axpy9(dd, -1.0, lv);
