@@ -154,6 +154,29 @@ int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_end, double*
 int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int nranks, int rank, double* d_J, double* d_dJdu,
                             void* stream);
 
+/* ---- one process, several GPUs (n_gpus / shard kind) ----------------------------------------------- */
+/* The reference has no multi-device notion; its two loops over pulses (a multistart driver's) and over slices
+ * (src/gradient_computations.jl:27-29, :52-58, :65-74) are what shards.  A Julia / C host cannot run one process per GPU
+ * under torchrun, so the library drives the devices itself: one host thread enqueues, every rank has its own stream.
+ *   QOC_SHARD_BATCH: prob->batch pulses block-partitioned over the ranks (rank p: pulses [p B / P, (p+1) B / P)), no exchange.
+ *   QOC_SHARD_TIME:  ONE pulse (batch == 1, built-in cost), rank p owns the slices [p Nt / P, (p+1) Nt / P).  The rank
+ *                    propagators S_p are stored by a kernel of rank p straight into every rank's buffer through NVLink peer
+ *                    mappings (cudaMemcpyPeerAsync when a pair has none); phase 2 starts when the P events have fired; every
+ *                    rank copies its gradient segment to its slice of the caller's host buffer.  No NCCL, no MPI.
+ * devices: n_ranks CUDA ordinals (NULL = 0 .. n_ranks-1); an ordinal may repeat (several ranks on one GPU).
+ * qoc_sharded_eval: u and dJdu_out are nc x Nt x batch host arrays exactly as for qoc_eval; J_out: batch doubles.       */
+typedef struct qoc_sharded qoc_sharded;
+typedef enum { QOC_SHARD_BATCH = 0, QOC_SHARD_TIME = 1 } qoc_shard_kind;
+int qoc_create_sharded(const qoc_problem* prob, const double* A0, const double* A, const double* x0, const double* T,
+                       int n_ranks, const int* devices, int shard_kind, qoc_sharded** out);
+int qoc_sharded_destroy(qoc_sharded* s);
+int qoc_sharded_set_order(qoc_sharded* s, int order);
+int qoc_sharded_eval(qoc_sharded* s, const double* u, double* J_out, double* dJdu_out);
+int qoc_sharded_ranks(const qoc_sharded* s);
+/* device time (ms) of the slowest rank in the last qoc_sharded_eval: H2D of its inputs .. D2H of its results, CUDA events */
+double qoc_sharded_last_ms(const qoc_sharded* s);
+const char* qoc_sharded_last_error(const qoc_sharded* s); /* s may be NULL: error of the last failed qoc_create_sharded */
+
 /* ---- cache getters (the reference returns x as its result, :31; parity tests read the rest) --------------- */
 int qoc_get_states(qoc_handle* h, double* x_out);        /* c128 d x m x (Nt+1) x batch  = cache.x              */
 int qoc_get_costates(qoc_handle* h, double* lam_out);    /* c128 d x m x (Nt+1) x batch  = cache.lambda          */

@@ -31,6 +31,13 @@ SYMBOLS = {
     "qoc_set_order": (C.c_int, [_vp, C.c_int]),
     "qoc_set_cost": (C.c_int, [_vp, C.c_int, _dp, C.c_int]),
     "qoc_set_eager_jacobians": (C.c_int, [_vp, C.c_int]),
+    "qoc_create_sharded": (C.c_int, [C.POINTER(Problem), _dp, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "qoc_sharded_destroy": (C.c_int, [_vp]),
+    "qoc_sharded_set_order": (C.c_int, [_vp, C.c_int]),
+    "qoc_sharded_eval": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "qoc_sharded_ranks": (C.c_int, [_vp]),
+    "qoc_sharded_last_ms": (C.c_double, [_vp]),
+    "qoc_sharded_last_error": (C.c_char_p, [_vp]),
     "qoc_propagate": (C.c_int, [_vp, _dp, _dp, _dp]),
     "qoc_gradient": (C.c_int, [_vp, _dp, _dp, _dp]),
     "qoc_eval": (C.c_int, [_vp, _dp, _dp, _dp]),

@@ -1433,3 +1433,224 @@ extern "C" int qoc_eval_coeffs(qoc_handle* h, const double* c, double* J_out, do
       if (!std::isfinite(J_out[b])) { h->err = "J is not finite"; return QOC_ERR_NOT_FINITE; }
   return QOC_OK;
 }
+
+// =====================================================================================================================
+// One process, several GPUs (include/qoc_b200.h: qoc_create_sharded / qoc_sharded_eval).
+//
+//   QOC_SHARD_BATCH  the pulses of a batch are block-partitioned over the devices; no exchange at all.
+//   QOC_SHARD_TIME   ONE pulse, contiguous time segments (the serial loops of src/gradient_computations.jl:27-29, :52-58,
+//                    :65-74 cut into P pieces).  Per evaluation and device p:
+//                      phase 1 (local): U_k, dU_k/du_j, rank propagator S_p
+//                      publish: ONE kernel on device p stores S_p straight into slot p of every device's S_all buffer over
+//                               NVLink peer mappings (no NCCL, no host hop: the message is 16 d^2 bytes), then an event
+//                      phase 2 (local, after the P events): boundary state / cost / boundary costate from S_all, sweeps,
+//                               gradient columns of the segment
+//                      the gradient segment goes from device p straight to ITS slice of the caller's host buffer: there
+//                      is no gather step because the destination is host memory anyway.
+//                    Every device runs on its own stream; the host thread only enqueues.
+// A device may appear several times in `devices` (virtual ranks on one GPU: how the single-GPU CI exercises this code).
+// =====================================================================================================================
+struct qoc_sharded {
+  int n = 0, kind = 0;
+  qoc_problem prob;                 // the global problem
+  std::vector<qoc_handle*> h;
+  std::vector<int> dev, lo, hi;     // per rank: device, unit range (slices or pulses)
+  std::vector<cudaEvent_t> ev_pub, ev_t0, ev_t1;
+  std::vector<double*> dS_loc, dS_all, du, dJ, dg;
+  std::vector<double**> d_dst;      // per rank: device array of n pointers (slot p of every rank's S_all)
+  bool peer = true;                 // every pair of distinct devices has a peer mapping
+  float last_ms = 0.f;
+  std::string err;
+};
+
+static thread_local std::string g_sharded_error;
+
+__global__ void shard_publish_kernel(const double* S, int n2, double* const* dst) {
+  double2* o = reinterpret_cast<double2*>(dst[blockIdx.y]);
+  const double2* s = reinterpret_cast<const double2*>(S);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) o[i] = s[i];
+}
+
+extern "C" const char* qoc_sharded_last_error(const qoc_sharded* s) { return s ? s->err.c_str() : g_sharded_error.c_str(); }
+extern "C" double qoc_sharded_last_ms(const qoc_sharded* s) { return s ? (double)s->last_ms : 0.0; }
+extern "C" int qoc_sharded_ranks(const qoc_sharded* s) { return s ? s->n : 0; }
+
+extern "C" int qoc_sharded_destroy(qoc_sharded* s) {
+  if (!s) return QOC_OK;
+  for (int p = 0; p < s->n; p++) {
+    if (p < (int)s->dev.size()) cudaSetDevice(s->dev[p]);
+    if (p < (int)s->dS_loc.size() && s->dS_loc[p]) cudaFree(s->dS_loc[p]);
+    if (p < (int)s->dS_all.size() && s->dS_all[p]) cudaFree(s->dS_all[p]);
+    if (p < (int)s->du.size() && s->du[p]) cudaFree(s->du[p]);
+    if (p < (int)s->dJ.size() && s->dJ[p]) cudaFree(s->dJ[p]);
+    if (p < (int)s->dg.size() && s->dg[p]) cudaFree(s->dg[p]);
+    if (p < (int)s->d_dst.size() && s->d_dst[p]) cudaFree(s->d_dst[p]);
+    if (p < (int)s->ev_pub.size()) { cudaEventDestroy(s->ev_pub[p]); cudaEventDestroy(s->ev_t0[p]); cudaEventDestroy(s->ev_t1[p]); }
+    if (p < (int)s->h.size() && s->h[p]) qoc_destroy(s->h[p]);
+  }
+  delete s;
+  return QOC_OK;
+}
+
+#define QOC_SH(s, call)                                                                                       \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess) {                                                                                 \
+      char buf__[512];                                                                                        \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      (s)->err = buf__;                                                                                       \
+      return QOC_ERR_CUDA;                                                                                    \
+    }                                                                                                         \
+  } while (0)
+
+extern "C" int qoc_create_sharded(const qoc_problem* prob, const double* A0, const double* A, const double* x0, const double* T,
+                                  int n_ranks, const int* devices, int shard_kind, qoc_sharded** out) {
+  if (!prob || !out || n_ranks <= 0) { g_sharded_error = "null argument or n_ranks <= 0"; return QOC_ERR_INVALID; }
+  if (shard_kind != QOC_SHARD_BATCH && shard_kind != QOC_SHARD_TIME) { g_sharded_error = "unknown shard kind"; return QOC_ERR_INVALID; }
+  const long long units = shard_kind == QOC_SHARD_TIME ? prob->nt : prob->batch;
+  if (shard_kind == QOC_SHARD_TIME && prob->batch != 1) { g_sharded_error = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
+  if (shard_kind == QOC_SHARD_TIME && prob->cost == QOC_COST_NONE) { g_sharded_error = "time sharding needs a built-in cost"; return QOC_ERR_INVALID; }
+  if (units < n_ranks) { g_sharded_error = "fewer slices / pulses than ranks"; return QOC_ERR_DIMENSION; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_sharded_error = "no CUDA device"; return QOC_ERR_NO_DEVICE; }
+  qoc_sharded* s = new qoc_sharded();
+  s->n = n_ranks; s->kind = shard_kind; s->prob = *prob;
+  s->dev.resize(n_ranks); s->lo.resize(n_ranks); s->hi.resize(n_ranks);
+  s->h.assign(n_ranks, nullptr);
+  s->dS_loc.assign(n_ranks, nullptr); s->dS_all.assign(n_ranks, nullptr); s->du.assign(n_ranks, nullptr);
+  s->dJ.assign(n_ranks, nullptr); s->dg.assign(n_ranks, nullptr); s->d_dst.assign(n_ranks, nullptr);
+  auto fail = [&](int rc, const std::string& msg) { g_sharded_error = msg; qoc_sharded_destroy(s); return rc; };
+  for (int p = 0; p < n_ranks; p++) {
+    s->dev[p] = devices ? devices[p] : p;
+    if (s->dev[p] < 0 || s->dev[p] >= ndev) return fail(QOC_ERR_INVALID, "device ordinal out of range");
+    s->lo[p] = (int)((long long)p * units / n_ranks);          // the partition of sharding.py (block_partition / time_partition)
+    s->hi[p] = (int)((long long)(p + 1) * units / n_ranks);
+  }
+  // peer mappings between every pair of distinct devices (NVLink / NVSwitch); without them the exchange falls back to
+  // cudaMemcpyPeerAsync
+  for (int p = 0; p < n_ranks && shard_kind == QOC_SHARD_TIME; p++)
+    for (int q = 0; q < n_ranks; q++) {
+      if (s->dev[p] == s->dev[q]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, s->dev[p], s->dev[q]);
+      if (!can) { s->peer = false; continue; }
+      cudaSetDevice(s->dev[p]);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(s->dev[q], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) s->peer = false;
+      cudaGetLastError();
+    }
+  const size_t d2 = (size_t)2 * prob->d * prob->d;   // doubles of one c128 d x d matrix
+  for (int p = 0; p < n_ranks; p++) {
+    qoc_problem pp = *prob;
+    pp.device = s->dev[p];
+    if (shard_kind == QOC_SHARD_TIME) pp.nt = s->hi[p] - s->lo[p]; else pp.batch = s->hi[p] - s->lo[p];
+    const int rc = qoc_create(&pp, A0, A, x0, T, &s->h[p]);
+    if (rc != QOC_OK) return fail(rc, std::string("rank ") + std::to_string(p) + ": " + g_create_error);
+    if (cudaSetDevice(s->dev[p]) != cudaSuccess) return fail(QOC_ERR_CUDA, "cudaSetDevice failed");
+    const size_t nu = (size_t)prob->nc * (shard_kind == QOC_SHARD_TIME ? pp.nt : (size_t)prob->nt * pp.batch);
+    bool ok = cudaMalloc(&s->du[p], nu * 8) == cudaSuccess && cudaMalloc(&s->dg[p], nu * 8) == cudaSuccess &&
+              cudaMalloc(&s->dJ[p], (size_t)pp.batch * 8) == cudaSuccess;
+    if (shard_kind == QOC_SHARD_TIME)
+      ok = ok && cudaMalloc(&s->dS_loc[p], d2 * 8) == cudaSuccess && cudaMalloc(&s->dS_all[p], d2 * 8 * n_ranks) == cudaSuccess &&
+           cudaMalloc(&s->d_dst[p], sizeof(double*) * n_ranks) == cudaSuccess;
+    if (!ok) return fail(QOC_ERR_CUDA, "device allocation failed");
+  }
+  s->ev_pub.resize(n_ranks); s->ev_t0.resize(n_ranks); s->ev_t1.resize(n_ranks);
+  for (int p = 0; p < n_ranks; p++) {
+    cudaSetDevice(s->dev[p]);
+    cudaEventCreateWithFlags(&s->ev_pub[p], cudaEventDisableTiming);
+    cudaEventCreate(&s->ev_t0[p]);
+    cudaEventCreate(&s->ev_t1[p]);
+    if (shard_kind == QOC_SHARD_TIME) {
+      std::vector<double*> dst(n_ranks);
+      for (int q = 0; q < n_ranks; q++) dst[q] = s->dS_all[q] + (size_t)p * d2;
+      if (cudaMemcpy(s->d_dst[p], dst.data(), sizeof(double*) * n_ranks, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(QOC_ERR_CUDA, "upload of the peer table failed");
+    }
+  }
+  *out = s;
+  return QOC_OK;
+}
+
+extern "C" int qoc_sharded_set_order(qoc_sharded* s, int order) {
+  if (!s) return QOC_ERR_INVALID;
+  for (int p = 0; p < s->n; p++) {
+    const int rc = qoc_set_order(s->h[p], order);
+    if (rc != QOC_OK) { s->err = s->h[p]->err; return rc; }
+  }
+  s->prob.order = order;
+  return QOC_OK;
+}
+
+extern "C" int qoc_sharded_eval(qoc_sharded* s, const double* u, double* J_out, double* dJdu_out) {
+  if (!s || !u) return QOC_ERR_INVALID;
+  const qoc_problem& gp = s->prob;
+  const int P = s->n;
+  const size_t d2 = (size_t)2 * gp.d * gp.d;
+  auto sub = [&](int p, int rc) { if (rc != QOC_OK) s->err = std::string("rank ") + std::to_string(p) + ": " + s->h[p]->err; return rc; };
+  int rc;
+  if (s->kind == QOC_SHARD_BATCH) {
+    const size_t per = (size_t)gp.nc * gp.nt;   // doubles per pulse
+    for (int p = 0; p < P; p++) {
+      qoc_handle* h = s->h[p];
+      const size_t n = (size_t)(s->hi[p] - s->lo[p]);
+      QOC_SH(s, cudaSetDevice(s->dev[p]));
+      QOC_SH(s, cudaEventRecord(s->ev_t0[p], h->stream));
+      QOC_SH(s, cudaMemcpyAsync(s->du[p], u + (size_t)s->lo[p] * per, n * per * 8, cudaMemcpyHostToDevice, h->stream));
+      if ((rc = sub(p, qoc_eval_device(h, s->du[p], s->dJ[p], s->dg[p], h->stream))) != QOC_OK) return rc;
+      if (J_out) QOC_SH(s, cudaMemcpyAsync(J_out + s->lo[p], s->dJ[p], n * 8, cudaMemcpyDeviceToHost, h->stream));
+      if (dJdu_out) QOC_SH(s, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * per, s->dg[p], n * per * 8, cudaMemcpyDeviceToHost, h->stream));
+      QOC_SH(s, cudaEventRecord(s->ev_t1[p], h->stream));
+      if ((rc = sub(p, queue_mail(h))) != QOC_OK) return rc;
+    }
+  } else {
+    // ---- phase 1 + publish, every rank ----
+    for (int p = 0; p < P; p++) {
+      qoc_handle* h = s->h[p];
+      const size_t n = (size_t)(s->hi[p] - s->lo[p]) * gp.nc;
+      QOC_SH(s, cudaSetDevice(s->dev[p]));
+      QOC_SH(s, cudaEventRecord(s->ev_t0[p], h->stream));
+      QOC_SH(s, cudaMemcpyAsync(s->du[p], u + (size_t)s->lo[p] * gp.nc, n * 8, cudaMemcpyHostToDevice, h->stream));
+      if ((rc = sub(p, qoc_shard_phase1_device(h, s->du[p], s->dS_loc[p], h->stream))) != QOC_OK) return rc;
+      if (s->peer) {
+        int bx = (int)((d2 / 2 + 255) / 256);
+        if (bx > 16) bx = 16;
+        shard_publish_kernel<<<dim3(bx, P), 256, 0, h->stream>>>(s->dS_loc[p], (int)(d2 / 2), s->d_dst[p]);
+        QOC_SH(s, cudaGetLastError());
+      } else {
+        for (int q = 0; q < P; q++)
+          QOC_SH(s, cudaMemcpyPeerAsync(s->dS_all[q] + (size_t)p * d2, s->dev[q], s->dS_loc[p], s->dev[p], d2 * 8, h->stream));
+      }
+      QOC_SH(s, cudaEventRecord(s->ev_pub[p], h->stream));
+    }
+    // ---- phase 2 once every S_p has landed; the gradient segment goes straight to its place in the host buffer ----
+    for (int p = 0; p < P; p++) {
+      qoc_handle* h = s->h[p];
+      const size_t n = (size_t)(s->hi[p] - s->lo[p]) * gp.nc;
+      QOC_SH(s, cudaSetDevice(s->dev[p]));
+      for (int q = 0; q < P; q++)
+        if (q != p) QOC_SH(s, cudaStreamWaitEvent(h->stream, s->ev_pub[q], 0));
+      if ((rc = sub(p, qoc_shard_phase2_device(h, s->dS_all[p], P, p, s->dJ[p], s->dg[p], h->stream))) != QOC_OK) return rc;
+      if (dJdu_out) QOC_SH(s, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * gp.nc, s->dg[p], n * 8, cudaMemcpyDeviceToHost, h->stream));
+      if (p == 0 && J_out) QOC_SH(s, cudaMemcpyAsync(J_out, s->dJ[0], 8, cudaMemcpyDeviceToHost, h->stream));
+      QOC_SH(s, cudaEventRecord(s->ev_t1[p], h->stream));
+      if ((rc = sub(p, queue_mail(h))) != QOC_OK) return rc;
+    }
+  }
+  float worst = 0.f;
+  for (int p = 0; p < P; p++) {
+    qoc_handle* h = s->h[p];
+    QOC_SH(s, cudaSetDevice(s->dev[p]));
+    QOC_SH(s, cudaStreamSynchronize(h->stream));
+    if ((rc = sub(p, check_status(h))) != QOC_OK) return rc;
+    h->mail_valid = false;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev_t0[p], s->ev_t1[p]) == cudaSuccess && ms > worst) worst = ms;
+  }
+  s->last_ms = worst;   // device time of the slowest rank (H2D of its inputs to D2H of its results)
+  const int nJ = s->kind == QOC_SHARD_BATCH ? gp.batch : 1;
+  if (J_out)
+    for (int b = 0; b < nJ; b++)
+      if (!std::isfinite(J_out[b])) { s->err = "J is not finite"; return QOC_ERR_NOT_FINITE; }
+  return QOC_OK;
+}

@@ -65,140 +65,155 @@ struct GemmShape {
   static constexpr size_t SMEM = (size_t)NST * STAGE * 8;
 };
 
+// PERSISTENT: the grid is one wave of CTAs (SM count x occupancy); CTA b walks the work items b, b + grid, ... (item =
+// one CTA tile of one slice) and its cp.async ring runs straight THROUGH the item boundaries: while the last chunks of an
+// item are multiplied and its epilogue (D reads, C stores) runs, the first chunks of the next item are already in flight.
+// One-CTA-per-tile launches exposed a prologue (first chunk: an L2 / HBM round trip) and an epilogue per tile with
+// nothing to overlap them when only one CTA fits an SM (the 64 x 64 tile: 16 warps x ~100 registers): at d = 64, where a
+// tile is only four chunks long, that was half the kernel.
 template <int WM, int WN, int NWM, int NWN>
-__global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g) {
+__global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int ntm, int ntn, int nitems) {
   typedef GemmShape<WM, WN, NWM, NWN> G;
   constexpr int NTH = G::NTH, TM = G::TM, TN = G::TN, KC = G::KC, NST = G::NST, AS = G::AS, BS = G::BS;
   extern __shared__ __align__(16) unsigned char gsm_raw[];
   double* sm = reinterpret_cast<double*>(gsm_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / NWN, wn = warp - wm * NWN;
-  const int s = blockIdx.z, tm = blockIdx.y, tn = blockIdx.x;
   const int d = g.d, S = g.S, plane = d * S;
   const int gq = lane >> 2, q4 = lane & 3;
   const bool gj = g.gj_nb > 0;
   const int kbeg = gj ? g.gj_k0 : 0;
   const int kend = gj ? ((g.gj_k0 + g.gj_nb < d) ? g.gj_k0 + g.gj_nb : d) : d;
   const int nkc = (kend - kbeg + KC - 1) / KC;
-  const int total = g.npairs * nkc;
-  double T1[WM][WN][2], T2[WM][WN][2], T3[WM][WN][2];
-#pragma unroll
-  for (int a = 0; a < WM; a++)
-#pragma unroll
-    for (int b = 0; b < WN; b++) { T1[a][b][0] = T1[a][b][1] = T2[a][b][0] = T2[a][b][1] = T3[a][b][0] = T3[a][b][1] = 0.0; }
-  bool rowv[WM], colv[WN];
-#pragma unroll
-  for (int a = 0; a < WM; a++) rowv[a] = tm * TM + (wm * WM + a) * 8 < d;
-#pragma unroll
-  for (int b = 0; b < WN; b++) colv[b] = tn * TN + (wn * WN + b) * 8 < d;
+  const int total = g.npairs * nkc;   // chunks per item
+  const int tps = ntm * ntn;          // tiles per slice
 
-  auto issue = [&](int c) {
-    const int p = c / nkc, kc = c - p * nkc, kb = kbeg + kc * KC;
-    const double* Ag = g.A[p].p + g.A[p].off(s);
-    const double* Bg = g.B[p].p + g.B[p].off(s);
-    double* st = sm + (size_t)(c % NST) * G::STAGE;
-    for (int e = tid; e < TM * (KC / 2); e += NTH) {          // A tile: TM rows x KC columns, both planes
-      const int r = e / (KC / 2), cc = (e - r * (KC / 2)) * 2;
-      const int gr = tm * TM + r, gc = kb + cc;
-      int bytes = (gr < d) ? (kend - gc) * 8 : 0;
-      bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-      const double* src = bytes ? Ag + (size_t)gr * S + gc : Ag;
-      g_cp_async16(st + r * AS + cc, src, bytes);
-      g_cp_async16(st + G::A_PLANE + r * AS + cc, bytes ? src + plane : Ag, bytes);
+  // producer cursor: (item, chunk) of the next chunk to put in flight, and the ring stage it goes to
+  int pw = blockIdx.x, pc = 0, pstage = 0;
+  auto issue_next = [&]() {
+    if (pw < nitems) {
+      const int s = pw / tps, r = pw - s * tps, tm = r / ntn, tn = r - tm * ntn;
+      const int p = pc / nkc, kc = pc - p * nkc, kb = kbeg + kc * KC;
+      const double* Ag = g.A[p].p + g.A[p].off(s);
+      const double* Bg = g.B[p].p + g.B[p].off(s);
+      double* st = sm + (size_t)pstage * G::STAGE;
+      for (int e = tid; e < TM * (KC / 2); e += NTH) {          // A tile: TM rows x KC columns, both planes
+        const int rr = e / (KC / 2), cc = (e - rr * (KC / 2)) * 2;
+        const int gr = tm * TM + rr, gc = kb + cc;
+        int bytes = (gr < d) ? (kend - gc) * 8 : 0;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        const double* src = bytes ? Ag + (size_t)gr * S + gc : Ag;
+        g_cp_async16(st + rr * AS + cc, src, bytes);
+        g_cp_async16(st + G::A_PLANE + rr * AS + cc, bytes ? src + plane : Ag, bytes);
+      }
+      double* sb = st + 2 * G::A_PLANE;
+      for (int e = tid; e < KC * (TN / 2); e += NTH) {          // B tile: KC rows x TN columns, both planes
+        const int rr = e / (TN / 2), cc = (e - rr * (TN / 2)) * 2;
+        const int gr = kb + rr, gc = tn * TN + cc;
+        const int bytes = (gr < kend && gc < S) ? 16 : 0;
+        const double* src = bytes ? Bg + (size_t)gr * S + gc : Bg;
+        g_cp_async16(sb + rr * BS + cc, src, bytes);
+        g_cp_async16(sb + G::B_PLANE + rr * BS + cc, bytes ? src + plane : Bg, bytes);
+      }
+      if (++pc == total) { pc = 0; pw += gridDim.x; }
     }
-    double* sb = st + 2 * G::A_PLANE;
-    for (int e = tid; e < KC * (TN / 2); e += NTH) {          // B tile: KC rows x TN columns, both planes
-      const int r = e / (TN / 2), cc = (e - r * (TN / 2)) * 2;
-      const int gr = kb + r, gc = tn * TN + cc;
-      const int bytes = (gr < kend && gc < S) ? 16 : 0;
-      const double* src = bytes ? Bg + (size_t)gr * S + gc : Bg;
-      g_cp_async16(sb + r * BS + cc, src, bytes);
-      g_cp_async16(sb + G::B_PLANE + r * BS + cc, bytes ? src + plane : Bg, bytes);
-    }
+    pstage = (pstage + 1 == NST) ? 0 : pstage + 1;
+    g_cp_async_commit();
   };
 
 #pragma unroll
-  for (int c = 0; c < NST - 1; c++) {
-    if (c < total) issue(c);
-    g_cp_async_commit();
-  }
-  const bool work = rowv[0] && colv[0];
-  for (int it = 0; it < total; it++) {
-    g_cp_async_wait<NST - 2>();
-    __syncthreads();
-    if (it + NST - 1 < total) issue(it + NST - 1);
-    g_cp_async_commit();
-    if (work) {
-      const double* st = sm + (size_t)(it % NST) * G::STAGE;
-      const int kc = it % nkc;
-      const int kleft = kend - (kbeg + kc * KC);
-      const int ksmax = kleft >= KC ? KC / 4 : (kleft + 3) / 4;
-      const double* are = st + (wm * WM * 8 + gq) * AS + q4;
-      const double* aim = are + G::A_PLANE;
-      const double* bre = st + 2 * G::A_PLANE + q4 * BS + wn * WN * 8 + gq;
-      const double* bim = bre + G::B_PLANE;
+  for (int c = 0; c < NST - 1; c++) issue_next();
+  int cstage = 0;   // consumer stage
+  for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+    const int s = w / tps, r = w - s * tps, tm = r / ntn, tn = r - tm * ntn;
+    double T1[WM][WN][2], T2[WM][WN][2], T3[WM][WN][2];
 #pragma unroll
-      for (int ks = 0; ks < KC / 4; ks++) {
-        if (ks < ksmax) {
-          double ar[WM], ai[WM], as[WM];
+    for (int a = 0; a < WM; a++)
 #pragma unroll
-          for (int a = 0; a < WM; a++) { ar[a] = are[a * 8 * AS + ks * 4]; ai[a] = aim[a * 8 * AS + ks * 4]; as[a] = ar[a] + ai[a]; }
+      for (int b = 0; b < WN; b++) { T1[a][b][0] = T1[a][b][1] = T2[a][b][0] = T2[a][b][1] = T3[a][b][0] = T3[a][b][1] = 0.0; }
+    bool rowv[WM], colv[WN];
 #pragma unroll
-          for (int b = 0; b < WN; b++) {
-            if (colv[b]) {
-              const double br = bre[ks * 4 * BS + b * 8], bi = bim[ks * 4 * BS + b * 8];
-              const double bs = br + bi;
+    for (int a = 0; a < WM; a++) rowv[a] = tm * TM + (wm * WM + a) * 8 < d;
 #pragma unroll
-              for (int a = 0; a < WM; a++) {
-                if (rowv[a]) {
-                  dmma(T1[a][b][0], T1[a][b][1], ar[a], br);
-                  dmma(T2[a][b][0], T2[a][b][1], ai[a], bi);
-                  dmma(T3[a][b][0], T3[a][b][1], as[a], bs);
+    for (int b = 0; b < WN; b++) colv[b] = tn * TN + (wn * WN + b) * 8 < d;
+    const bool work = rowv[0] && colv[0];
+    for (int it = 0; it < total; it++) {
+      g_cp_async_wait<NST - 2>();
+      __syncthreads();
+      issue_next();
+      if (work) {
+        const double* st = sm + (size_t)cstage * G::STAGE;
+        const int kc = it % nkc;
+        const int kleft = kend - (kbeg + kc * KC);
+        const int ksmax = kleft >= KC ? KC / 4 : (kleft + 3) / 4;
+        const double* are = st + (wm * WM * 8 + gq) * AS + q4;
+        const double* aim = are + G::A_PLANE;
+        const double* bre = st + 2 * G::A_PLANE + q4 * BS + wn * WN * 8 + gq;
+        const double* bim = bre + G::B_PLANE;
+#pragma unroll
+        for (int ks = 0; ks < KC / 4; ks++) {
+          if (ks < ksmax) {
+            double ar[WM], ai[WM], as[WM];
+#pragma unroll
+            for (int a = 0; a < WM; a++) { ar[a] = are[a * 8 * AS + ks * 4]; ai[a] = aim[a * 8 * AS + ks * 4]; as[a] = ar[a] + ai[a]; }
+#pragma unroll
+            for (int b = 0; b < WN; b++) {
+              if (colv[b]) {
+                const double br = bre[ks * 4 * BS + b * 8], bi = bim[ks * 4 * BS + b * 8];
+                const double bs = br + bi;
+#pragma unroll
+                for (int a = 0; a < WM; a++) {
+                  if (rowv[a]) {
+                    dmma(T1[a][b][0], T1[a][b][1], ar[a], br);
+                    dmma(T2[a][b][0], T2[a][b][1], ai[a], bi);
+                    dmma(T3[a][b][0], T3[a][b][1], as[a], bs);
+                  }
                 }
               }
             }
           }
         }
       }
+      cstage = (cstage + 1 == NST) ? 0 : cstage + 1;
     }
-  }
-  g_cp_async_wait<0>();
-  double* Cg = g.C + (g.cinner > 0 ? (long long)(s / g.cinner) * g.cstride2 + (long long)(s % g.cinner) * g.cstride
-                                   : (long long)s * g.cstride);
+    double* Cg = g.C + (g.cinner > 0 ? (long long)(s / g.cinner) * g.cstride2 + (long long)(s % g.cinner) * g.cstride
+                                     : (long long)s * g.cstride);
 #pragma unroll
-  for (int a = 0; a < WM; a++) {
-    const int row = tm * TM + (wm * WM + a) * 8 + gq;
+    for (int a = 0; a < WM; a++) {
+      const int row = tm * TM + (wm * WM + a) * 8 + gq;
 #pragma unroll
-    for (int b = 0; b < WN; b++) {
-      const int col = tn * TN + (wn * WN + b) * 8 + 2 * q4;
-      if (row < d && col < d) {
-        // 3M: Re = T1 - T2, Im = T3 - T1 - T2
-        double r0 = g.alpha * (T1[a][b][0] - T2[a][b][0]), r1 = g.alpha * (T1[a][b][1] - T2[a][b][1]);
-        double i0 = g.alpha * ((T3[a][b][0] - T1[a][b][0]) - T2[a][b][0]), i1 = g.alpha * ((T3[a][b][1] - T1[a][b][1]) - T2[a][b][1]);
-        const size_t o = (size_t)row * S + col;
-        if (gj) {
-          // blocked Gauss-Jordan step on the panel K = [kbeg, kend): the K columns of `cur` already hold the transformation
-          // G; every other column becomes (cur with its K rows zeroed) + G cur[K, :]
-          const double* Dg = g.D[0].p + g.D[0].off(s);
-          const double2 u = *reinterpret_cast<const double2*>(Dg + o), v = *reinterpret_cast<const double2*>(Dg + plane + o);
-          if (col >= kbeg && col < kend) { r0 = u.x; r1 = u.y; i0 = v.x; i1 = v.y; }
-          else if (!(row >= kbeg && row < kend)) { r0 += u.x; r1 += u.y; i0 += v.x; i1 += v.y; }
-        } else {
-          for (int q = 0; q < g.nadd; q++) {
-            const double* Dg = g.D[q].p + g.D[q].off(s);
+      for (int b = 0; b < WN; b++) {
+        const int col = tn * TN + (wn * WN + b) * 8 + 2 * q4;
+        if (row < d && col < d) {
+          // 3M: Re = T1 - T2, Im = T3 - T1 - T2
+          double r0 = g.alpha * (T1[a][b][0] - T2[a][b][0]), r1 = g.alpha * (T1[a][b][1] - T2[a][b][1]);
+          double i0 = g.alpha * ((T3[a][b][0] - T1[a][b][0]) - T2[a][b][0]), i1 = g.alpha * ((T3[a][b][1] - T1[a][b][1]) - T2[a][b][1]);
+          const size_t o = (size_t)row * S + col;
+          if (gj) {
+            // blocked Gauss-Jordan step on the panel K = [kbeg, kend): the K columns of `cur` already hold the transformation
+            // G; every other column becomes (cur with its K rows zeroed) + G cur[K, :]
+            const double* Dg = g.D[0].p + g.D[0].off(s);
             const double2 u = *reinterpret_cast<const double2*>(Dg + o), v = *reinterpret_cast<const double2*>(Dg + plane + o);
-            r0 = fma(g.beta[q], u.x, r0); r1 = fma(g.beta[q], u.y, r1);
-            i0 = fma(g.beta[q], v.x, i0); i1 = fma(g.beta[q], v.y, i1);
+            if (col >= kbeg && col < kend) { r0 = u.x; r1 = u.y; i0 = v.x; i1 = v.y; }
+            else if (!(row >= kbeg && row < kend)) { r0 += u.x; r1 += u.y; i0 += v.x; i1 += v.y; }
+          } else {
+            for (int q = 0; q < g.nadd; q++) {
+              const double* Dg = g.D[q].p + g.D[q].off(s);
+              const double2 u = *reinterpret_cast<const double2*>(Dg + o), v = *reinterpret_cast<const double2*>(Dg + plane + o);
+              r0 = fma(g.beta[q], u.x, r0); r1 = fma(g.beta[q], u.y, r1);
+              i0 = fma(g.beta[q], v.x, i0); i1 = fma(g.beta[q], v.y, i1);
+            }
+            if (row == col) r0 += g.gamma;
+            if (row == col + 1) r1 += g.gamma;
           }
-          if (row == col) r0 += g.gamma;
-          if (row == col + 1) r1 += g.gamma;
+          if (col + 1 >= d) { r1 = 0.0; i1 = 0.0; }
+          *reinterpret_cast<double2*>(Cg + o) = make_double2(r0, r1);
+          *reinterpret_cast<double2*>(Cg + plane + o) = make_double2(i0, i1);
         }
-        if (col + 1 >= d) { r1 = 0.0; i1 = 0.0; }
-        *reinterpret_cast<double2*>(Cg + o) = make_double2(r0, r1);
-        *reinterpret_cast<double2*>(Cg + plane + o) = make_double2(i0, i1);
       }
     }
   }
+  g_cp_async_wait<0>();
 }
 
 // C = sum_q beta_q D_q + gamma I over whole planar slots (no product): a streaming elementwise pass, 16-byte accesses
@@ -231,13 +246,18 @@ __global__ void __launch_bounds__(256) g_lin_kernel(GGemm g) {
 template <int WM, int WN, int NWM, int NWN>
 static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
   typedef GemmShape<WM, WN, NWM, NWN> G;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static int wave = 0;   // CTAs in one wave of this instantiation (per process: one device model)
+  if (!wave) {
     cudaFuncSetAttribute(g_gemm2_kernel<WM, WN, NWM, NWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-    attr_done = true;
+    int dev = 0, nsm = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_gemm2_kernel<WM, WN, NWM, NWN>, G::NTH, G::SMEM);
+    wave = nsm * (occ < 1 ? 1 : occ);
   }
   const int tm = (g.d + G::TM - 1) / G::TM, tn = (g.d + G::TN - 1) / G::TN;
-  g_gemm2_kernel<WM, WN, NWM, NWN><<<dim3(tn, tm, nb), G::NTH, G::SMEM, st>>>(g);
+  const long long items = (long long)tm * tn * nb;
+  g_gemm2_kernel<WM, WN, NWM, NWN><<<(int)(items < wave ? items : wave), G::NTH, G::SMEM, st>>>(g, tm, tn, (int)items);
 }
 static inline int g_gemm_tile(int d) {
   static const int cand[4] = {64, 48, 40, 32};

@@ -30,7 +30,8 @@ import torch.distributed as dist
 from . import _lib
 from .grape import GrapeCache, QOCError, _BuiltinCost, COST_INFIDELITY, COST_ABS_TRACE, COST_ZCAL
 
-__all__ = ["block_partition", "time_partition", "CudaSegmentEngine", "TimeShardedEvaluator", "evaluate_batch_sharded"]
+__all__ = ["block_partition", "time_partition", "CudaSegmentEngine", "TimeShardedEvaluator", "evaluate_batch_sharded",
+           "InProcessSharded"]
 
 
 def block_partition(n: int, world: int, rank: int):
@@ -270,3 +271,66 @@ def evaluate_batch_sharded(eval_local, u_batch, group=None, gather=True):
         J[l:h] = outJ[r][: h - l].cpu().numpy()
         g[l:h] = outg[r][: h - l].cpu().numpy()
     return J, g, (lo, hi)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one process, several GPUs: the library drives the devices itself (qoc_create_sharded / qoc_sharded_eval)
+# ----------------------------------------------------------------------------------------------------------------------
+class InProcessSharded:
+    """The multi-GPU evaluation a host without torchrun (a Julia process, a C program) uses: ONE process, the C library
+    owns a stream per device, exchanges the rank propagators through NVLink peer stores and writes every rank's results
+    into the caller's host arrays.  kind: "batch" (pulses block-partitioned, no exchange) or "time" (one pulse, contiguous
+    time segments).  devices: CUDA ordinals, one per rank (an ordinal may repeat: virtual ranks on one GPU)."""
+
+    def __init__(self, A0, A, x0, cost, u_size, devices, kind="time", batch=1, dUkdp_order=0):
+        from .grape import _c128, _dptr
+        if not isinstance(cost, _BuiltinCost):
+            raise QOCError(_lib.ERR_INVALID, "the in-library sharded evaluation needs a built-in cost")
+        lib = _lib.load()
+        self.lib = lib
+        A0c = _c128(A0)
+        Ac = np.stack([_c128(a) for a in A], axis=0)
+        x0c = _c128(np.asarray(x0).reshape(np.asarray(x0).shape[0], -1))
+        Aflat = np.ascontiguousarray(np.stack([a.T for a in Ac], axis=0))
+        pr = _lib.Problem()
+        pr.d, pr.m, pr.nc, pr.nt, pr.batch = A0c.shape[0], x0c.shape[1], len(A), int(u_size[1]), int(batch)
+        pr.order, pr.cost, pr.n, pr.device = int(dUkdp_order), cost.kind, cost.n, 0
+        self.nc, self.nt, self.batch, self.kind = pr.nc, pr.nt, pr.batch, kind
+        devs = (C.c_int * len(devices))(*[int(x) for x in devices])
+        h = C.c_void_p()
+        rc = lib.qoc_create_sharded(C.byref(pr), _dptr(A0c), _dptr(Aflat), _dptr(x0c), _dptr(cost.T), len(devices), devs,
+                                    1 if kind == "time" else 0, C.byref(h))
+        if rc != _lib.OK:
+            raise QOCError(rc, lib.qoc_sharded_last_error(None).decode())
+        self._h = h
+
+    def evaluate(self, u):
+        """u: (nc, Nt) or (batch, nc, Nt) -> (J, dJdu) with the shapes of qoc_b200.evaluate."""
+        from .grape import _dptr
+        u = np.asarray(u, dtype=np.float64)
+        if self.batch == 1:
+            uu = np.ascontiguousarray(u.T)
+        else:
+            uu = np.ascontiguousarray(np.transpose(u, (0, 2, 1)))
+        J = np.zeros(self.batch)
+        g = np.zeros(uu.shape)
+        rc = self.lib.qoc_sharded_eval(self._h, _dptr(uu), _dptr(J), _dptr(g))
+        if rc != _lib.OK:
+            raise QOCError(rc, self.lib.qoc_sharded_last_error(self._h).decode())
+        if self.batch == 1:
+            return float(J[0]), g.T.copy()
+        return J, np.transpose(g, (0, 2, 1)).copy()
+
+    def last_ms(self):
+        return self.lib.qoc_sharded_last_ms(self._h)
+
+    def close(self):
+        if self._h is not None:
+            self.lib.qoc_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
