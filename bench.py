@@ -283,6 +283,9 @@ class Ctx:
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=self.dev)
+            # CPU-side rendezvous for the phases in which ONE process drives every GPU: a rank parked in an NCCL barrier keeps a
+            # spinning kernel on its GPU, and rank 0's work there would be time-sliced against it
+            self.cpu_group = dist.new_group(backend="gloo")
         self.lib = _lib.load()
         self.peak, self.peak_src = fp64_peak_tflops()
 
@@ -530,6 +533,56 @@ def run_time_sharded(cx, name, mode, steps, warmup):
     return rec
 
 
+def run_in_library_sharded(cx, name, mode, steps, warmup):
+    """The same ONE-pulse time-segment sharding driven by ONE process through the C ABI (qoc_create_sharded /
+    qoc_sharded_eval): rank 0 of the torchrun job drives all N GPUs (the other ranks wait at a barrier), the rank
+    propagators travel by NVLink peer stores issued from a kernel, there is no NCCL call on the path.  This is what a Julia
+    or C host gets.  Timed with CUDA events on device 0 around the whole loop (every evaluation ends with a host
+    synchronise of all N streams, so the span covers all devices); parity asserted against the single-GPU evaluation."""
+    torch, q = cx.torch, cx.q
+    from qoc_b200 import sharding
+    rec = None
+    torch.cuda.synchronize()
+    cx.dist.barrier(group=cx.cpu_group)   # every GPU idle from here on (no NCCL kernel parked on it)
+    if cx.rank == 0:
+        order = 0 if mode == "frechet" else 3
+        cfg, u, batch, desc = build_workload(name, 0, mode)
+        nc, nt = u.shape
+        costp = q.setup_infidelity(cfg["T"], cfg["n"]) if cfg["cost"] == 0 else q.setup_infidelity_abs_trace(cfg["T"])
+        cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (nc, nt), device=cx.local_rank, dUkdp_order=order, store_costates=False)
+        J1, g1 = q.evaluate(cache, cfg["A0"], cfg["A"], u, cfg["x0"], costp[1], dUkdp_order=order)
+        cache.close()
+        sh = sharding.InProcessSharded(cfg["A0"], cfg["A"], cfg["x0"], costp[1], (nc, nt), list(range(cx.world)), kind="time",
+                                       dUkdp_order=order)
+        for _ in range(warmup):
+            J, g = sh.evaluate(u)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dev_ms = []
+        for _ in range(steps):
+            J, g = sh.evaluate(u)
+            dev_ms.append(sh.last_ms())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        dJ, dg = abs(J - J1), float(np.abs(g - g1).max() / np.abs(g1).max())
+        ok = dJ <= TOL_J * max(1.0, abs(J1)) and dg <= TOL_G
+        d = cfg["A0"].shape[0]
+        rec = {"workload": desc.replace("single pulse per GPU", f"ONE pulse time-segment sharded over {cx.world} GPUs, ONE process (C ABI)"),
+               "mode": mode, "value": nt * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+               "scaling": "strong", "api": "qoc_create_sharded / qoc_sharded_eval, host buffers in and out",
+               "slowest_rank_device_ms": float(np.median(dev_ms)),
+               "collectives": f"none (NCCL-free): {cx.world} rank propagators ({16 * d * d} B each) stored into every peer's buffer by one "
+                              f"kernel per rank over NVLink peer mappings; gradient segments D2H straight into the caller's array",
+               "parity": {"vs": "single-GPU evaluation of the same pulse", "abs_dJ": dJ, "rel_dg_max": dg, "tol_J": TOL_J,
+                          "tol_g": TOL_G, "ok": bool(ok)}, "J": J}
+        sh.close()
+        assert ok, f"in-library sharded result disagrees with the single-GPU evaluation: |dJ|={dJ:.3e} rel|dg|={dg:.3e} ({name}, {mode})"
+    cx.dist.barrier(group=cx.cpu_group)
+    return rec
+
+
 # every other BASELINE.json config: (workload, per-mode device-time budget in seconds)
 CONFIGS_N1 = [("zz", None), ("cavity", None), ("cavity20", None), ("cavity40", None), ("zz_batch", None),
               ("synth16x100000", 3.0), ("synth32x100000", 3.0), ("synth64x100000", 4.0), ("synth128x100000", 8.0)]
@@ -627,6 +680,12 @@ def main():
                 for mode in ("frechet", "taylor3"):
                     strong.append(run_time_sharded(cx, wl, mode, st, 3))
             out["strong"] = strong
+            inlib = []
+            for wl, st in (("bus", args.steps), ("synth64x100000", 3)):
+                r = run_in_library_sharded(cx, wl, "frechet", st, 3)
+                if r is not None:
+                    inlib.append(r)
+            out["strong_in_library"] = inlib
     if cx.rank == 0:
         print(json.dumps(out))
     if cx.world > 1:

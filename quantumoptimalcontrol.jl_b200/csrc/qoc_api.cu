@@ -4,7 +4,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qoc_b200.h"
@@ -1461,6 +1464,17 @@ struct qoc_sharded {
   bool peer = true;                 // every pair of distinct devices has a peer mapping
   float last_ms = 0.f;
   std::string err;
+  // one host thread per rank (persistent): job hand-over and the barrier between the two halves of an evaluation
+  bool threads = true;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv;
+  unsigned long long gen = 0, arrived_gen = 0;
+  int arrived = 0, done = 0;
+  bool quit = false;
+  const double* job_u = nullptr;
+  double *job_J = nullptr, *job_g = nullptr;
+  std::vector<int> rc_rank;
 };
 
 static thread_local std::string g_sharded_error;
@@ -1477,6 +1491,11 @@ extern "C" int qoc_sharded_ranks(const qoc_sharded* s) { return s ? s->n : 0; }
 
 extern "C" int qoc_sharded_destroy(qoc_sharded* s) {
   if (!s) return QOC_OK;
+  if (!s->workers.empty()) {
+    { std::lock_guard<std::mutex> lk(s->mu); s->quit = true; }
+    s->cv.notify_all();
+    for (auto& t : s->workers) t.join();
+  }
   for (int p = 0; p < s->n; p++) {
     if (p < (int)s->dev.size()) cudaSetDevice(s->dev[p]);
     if (p < (int)s->dS_loc.size() && s->dS_loc[p]) cudaFree(s->dS_loc[p]);
@@ -1515,6 +1534,7 @@ extern "C" int qoc_create_sharded(const qoc_problem* prob, const double* A0, con
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_sharded_error = "no CUDA device"; return QOC_ERR_NO_DEVICE; }
   qoc_sharded* s = new qoc_sharded();
   s->n = n_ranks; s->kind = shard_kind; s->prob = *prob;
+  { const char* t = getenv("QOC_SHARD_THREADS"); s->threads = !(t && t[0] == '0') && n_ranks > 1; }
   s->dev.resize(n_ranks); s->lo.resize(n_ranks); s->hi.resize(n_ranks);
   s->h.assign(n_ranks, nullptr);
   s->dS_loc.assign(n_ranks, nullptr); s->dS_all.assign(n_ranks, nullptr); s->du.assign(n_ranks, nullptr);
@@ -1582,71 +1602,124 @@ extern "C" int qoc_sharded_set_order(qoc_sharded* s, int order) {
   return QOC_OK;
 }
 
+// ---- per-rank halves of an evaluation (each runs on the rank's own host thread: a stream's launch queue is finite, and one
+//      thread issuing the ~1000 launches of a long general-path phase 1 for rank 0 would not reach rank 1 before rank 0's
+//      GPU had drained most of them -- measured: 2 GPUs, d = 64, Nt = 1e5: 317 ms single-threaded vs 217 ms one process per GPU) ----
+static int sharded_rank_A(qoc_sharded* s, int p, const double* u) {
+  const qoc_problem& gp = s->prob;
+  qoc_handle* h = s->h[p];
+  auto sub = [&](int rc) { return rc; };
+  int rc;
+  QOC_CUDA(h, cudaSetDevice(s->dev[p]));
+  QOC_CUDA(h, cudaEventRecord(s->ev_t0[p], h->stream));
+  if (s->kind == QOC_SHARD_BATCH) {
+    const size_t per = (size_t)gp.nc * gp.nt, n = (size_t)(s->hi[p] - s->lo[p]);
+    QOC_CUDA(h, cudaMemcpyAsync(s->du[p], u + (size_t)s->lo[p] * per, n * per * 8, cudaMemcpyHostToDevice, h->stream));
+    return sub(qoc_eval_device(h, s->du[p], s->dJ[p], s->dg[p], h->stream));
+  }
+  const size_t d2 = (size_t)2 * gp.d * gp.d;
+  const size_t n = (size_t)(s->hi[p] - s->lo[p]) * gp.nc;
+  QOC_CUDA(h, cudaMemcpyAsync(s->du[p], u + (size_t)s->lo[p] * gp.nc, n * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = qoc_shard_phase1_device(h, s->du[p], s->dS_loc[p], h->stream)) != QOC_OK) return rc;
+  if (s->peer) {
+    int bx = (int)((d2 / 2 + 255) / 256);
+    if (bx > 16) bx = 16;
+    shard_publish_kernel<<<dim3(bx, s->n), 256, 0, h->stream>>>(s->dS_loc[p], (int)(d2 / 2), s->d_dst[p]);
+    QOC_CUDA(h, cudaGetLastError());
+  } else {
+    for (int q = 0; q < s->n; q++)
+      QOC_CUDA(h, cudaMemcpyPeerAsync(s->dS_all[q] + (size_t)p * d2, s->dev[q], s->dS_loc[p], s->dev[p], d2 * 8, h->stream));
+  }
+  QOC_CUDA(h, cudaEventRecord(s->ev_pub[p], h->stream));
+  return QOC_OK;
+}
+
+// second half: (time sharding) phase 2 once every S_q has landed; results straight to the caller's host arrays; synchronise
+static int sharded_rank_B(qoc_sharded* s, int p, double* J_out, double* dJdu_out) {
+  const qoc_problem& gp = s->prob;
+  qoc_handle* h = s->h[p];
+  int rc;
+  QOC_CUDA(h, cudaSetDevice(s->dev[p]));
+  if (s->kind == QOC_SHARD_BATCH) {
+    const size_t per = (size_t)gp.nc * gp.nt, n = (size_t)(s->hi[p] - s->lo[p]);
+    if (J_out) QOC_CUDA(h, cudaMemcpyAsync(J_out + s->lo[p], s->dJ[p], n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (dJdu_out) QOC_CUDA(h, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * per, s->dg[p], n * per * 8, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    const size_t n = (size_t)(s->hi[p] - s->lo[p]) * gp.nc;
+    for (int q = 0; q < s->n; q++)
+      if (q != p) QOC_CUDA(h, cudaStreamWaitEvent(h->stream, s->ev_pub[q], 0));
+    if ((rc = qoc_shard_phase2_device(h, s->dS_all[p], s->n, p, s->dJ[p], s->dg[p], h->stream)) != QOC_OK) return rc;
+    if (dJdu_out) QOC_CUDA(h, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * gp.nc, s->dg[p], n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (p == 0 && J_out) QOC_CUDA(h, cudaMemcpyAsync(J_out, s->dJ[0], 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  QOC_CUDA(h, cudaEventRecord(s->ev_t1[p], h->stream));
+  if ((rc = queue_mail(h)) != QOC_OK) return rc;
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  rc = check_status(h);
+  h->mail_valid = false;
+  return rc;
+}
+
+static void sharded_worker(qoc_sharded* s, int p) {
+  unsigned long long seen = 0;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(s->mu);
+      s->cv.wait(lk, [&] { return s->quit || s->gen != seen; });
+      if (s->quit) return;
+      seen = s->gen;
+    }
+    int rc = sharded_rank_A(s, p, s->job_u);
+    {   // host barrier: every ev_pub of this evaluation is recorded before anybody waits on one
+      std::unique_lock<std::mutex> lk(s->mu);
+      if (rc != QOC_OK) s->rc_rank[p] = rc;
+      if (++s->arrived == s->n) { s->arrived_gen = seen; s->cv.notify_all(); }
+      else s->cv.wait(lk, [&] { return s->arrived_gen == seen; });
+    }
+    bool any_bad = false;
+    for (int q = 0; q < s->n; q++) any_bad |= s->rc_rank[q] != QOC_OK;
+    if (!any_bad) {
+      rc = sharded_rank_B(s, p, s->job_J, s->job_g);
+      if (rc != QOC_OK) { std::lock_guard<std::mutex> lk(s->mu); s->rc_rank[p] = rc; }
+    }
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      if (++s->done == s->n) s->cv.notify_all();
+    }
+  }
+}
+
 extern "C" int qoc_sharded_eval(qoc_sharded* s, const double* u, double* J_out, double* dJdu_out) {
   if (!s || !u) return QOC_ERR_INVALID;
   const qoc_problem& gp = s->prob;
   const int P = s->n;
-  const size_t d2 = (size_t)2 * gp.d * gp.d;
-  auto sub = [&](int p, int rc) { if (rc != QOC_OK) s->err = std::string("rank ") + std::to_string(p) + ": " + s->h[p]->err; return rc; };
-  int rc;
-  if (s->kind == QOC_SHARD_BATCH) {
-    const size_t per = (size_t)gp.nc * gp.nt;   // doubles per pulse
-    for (int p = 0; p < P; p++) {
-      qoc_handle* h = s->h[p];
-      const size_t n = (size_t)(s->hi[p] - s->lo[p]);
-      QOC_SH(s, cudaSetDevice(s->dev[p]));
-      QOC_SH(s, cudaEventRecord(s->ev_t0[p], h->stream));
-      QOC_SH(s, cudaMemcpyAsync(s->du[p], u + (size_t)s->lo[p] * per, n * per * 8, cudaMemcpyHostToDevice, h->stream));
-      if ((rc = sub(p, qoc_eval_device(h, s->du[p], s->dJ[p], s->dg[p], h->stream))) != QOC_OK) return rc;
-      if (J_out) QOC_SH(s, cudaMemcpyAsync(J_out + s->lo[p], s->dJ[p], n * 8, cudaMemcpyDeviceToHost, h->stream));
-      if (dJdu_out) QOC_SH(s, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * per, s->dg[p], n * per * 8, cudaMemcpyDeviceToHost, h->stream));
-      QOC_SH(s, cudaEventRecord(s->ev_t1[p], h->stream));
-      if ((rc = sub(p, queue_mail(h))) != QOC_OK) return rc;
+  s->rc_rank.assign(P, QOC_OK);
+  if (s->threads) {
+    if (s->workers.empty())
+      for (int p = 0; p < P; p++) s->workers.emplace_back(sharded_worker, s, p);
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      s->job_u = u; s->job_J = J_out; s->job_g = dJdu_out;
+      s->arrived = 0; s->done = 0;
+      s->gen++;
     }
+    s->cv.notify_all();
+    std::unique_lock<std::mutex> lk(s->mu);
+    s->cv.wait(lk, [&] { return s->done == P; });
   } else {
-    // ---- phase 1 + publish, every rank ----
-    for (int p = 0; p < P; p++) {
-      qoc_handle* h = s->h[p];
-      const size_t n = (size_t)(s->hi[p] - s->lo[p]) * gp.nc;
-      QOC_SH(s, cudaSetDevice(s->dev[p]));
-      QOC_SH(s, cudaEventRecord(s->ev_t0[p], h->stream));
-      QOC_SH(s, cudaMemcpyAsync(s->du[p], u + (size_t)s->lo[p] * gp.nc, n * 8, cudaMemcpyHostToDevice, h->stream));
-      if ((rc = sub(p, qoc_shard_phase1_device(h, s->du[p], s->dS_loc[p], h->stream))) != QOC_OK) return rc;
-      if (s->peer) {
-        int bx = (int)((d2 / 2 + 255) / 256);
-        if (bx > 16) bx = 16;
-        shard_publish_kernel<<<dim3(bx, P), 256, 0, h->stream>>>(s->dS_loc[p], (int)(d2 / 2), s->d_dst[p]);
-        QOC_SH(s, cudaGetLastError());
-      } else {
-        for (int q = 0; q < P; q++)
-          QOC_SH(s, cudaMemcpyPeerAsync(s->dS_all[q] + (size_t)p * d2, s->dev[q], s->dS_loc[p], s->dev[p], d2 * 8, h->stream));
-      }
-      QOC_SH(s, cudaEventRecord(s->ev_pub[p], h->stream));
-    }
-    // ---- phase 2 once every S_p has landed; the gradient segment goes straight to its place in the host buffer ----
-    for (int p = 0; p < P; p++) {
-      qoc_handle* h = s->h[p];
-      const size_t n = (size_t)(s->hi[p] - s->lo[p]) * gp.nc;
-      QOC_SH(s, cudaSetDevice(s->dev[p]));
-      for (int q = 0; q < P; q++)
-        if (q != p) QOC_SH(s, cudaStreamWaitEvent(h->stream, s->ev_pub[q], 0));
-      if ((rc = sub(p, qoc_shard_phase2_device(h, s->dS_all[p], P, p, s->dJ[p], s->dg[p], h->stream))) != QOC_OK) return rc;
-      if (dJdu_out) QOC_SH(s, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * gp.nc, s->dg[p], n * 8, cudaMemcpyDeviceToHost, h->stream));
-      if (p == 0 && J_out) QOC_SH(s, cudaMemcpyAsync(J_out, s->dJ[0], 8, cudaMemcpyDeviceToHost, h->stream));
-      QOC_SH(s, cudaEventRecord(s->ev_t1[p], h->stream));
-      if ((rc = sub(p, queue_mail(h))) != QOC_OK) return rc;
-    }
+    bool bad = false;
+    for (int p = 0; p < P; p++) { s->rc_rank[p] = sharded_rank_A(s, p, u); bad |= s->rc_rank[p] != QOC_OK; }
+    for (int p = 0; p < P && !bad; p++) s->rc_rank[p] = sharded_rank_B(s, p, J_out, dJdu_out);
   }
+  for (int p = 0; p < P; p++)
+    if (s->rc_rank[p] != QOC_OK) { s->err = std::string("rank ") + std::to_string(p) + ": " + s->h[p]->err; return s->rc_rank[p]; }
   float worst = 0.f;
   for (int p = 0; p < P; p++) {
-    qoc_handle* h = s->h[p];
-    QOC_SH(s, cudaSetDevice(s->dev[p]));
-    QOC_SH(s, cudaStreamSynchronize(h->stream));
-    if ((rc = sub(p, check_status(h))) != QOC_OK) return rc;
-    h->mail_valid = false;
     float ms = 0.f;
+    cudaSetDevice(s->dev[p]);
     if (cudaEventElapsedTime(&ms, s->ev_t0[p], s->ev_t1[p]) == cudaSuccess && ms > worst) worst = ms;
   }
+  cudaGetLastError();
   s->last_ms = worst;   // device time of the slowest rank (H2D of its inputs to D2H of its results)
   const int nJ = s->kind == QOC_SHARD_BATCH ? gp.batch : 1;
   if (J_out)

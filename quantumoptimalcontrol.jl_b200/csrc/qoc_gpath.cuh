@@ -246,11 +246,13 @@ __global__ void __launch_bounds__(256) g_lin_kernel(GGemm g) {
 template <int WM, int WN, int NWM, int NWN>
 static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
   typedef GemmShape<WM, WN, NWM, NWN> G;
-  static int wave = 0;   // CTAs in one wave of this instantiation (per process: one device model)
+  static int wave_of[64] = {0};   // CTAs in one wave of this instantiation, per device (function attributes are per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& wave = wave_of[dev & 63];
   if (!wave) {
     cudaFuncSetAttribute(g_gemm2_kernel<WM, WN, NWM, NWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-    int dev = 0, nsm = 148, occ = 1;
-    cudaGetDevice(&dev);
+    int nsm = 148, occ = 1;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_gemm2_kernel<WM, WN, NWM, NWN>, G::NTH, G::SMEM);
     wave = nsm * (occ < 1 ? 1 : occ);
@@ -469,7 +471,10 @@ static inline double* g_inverse_blocked(int d, int S, long long slot_d, int nsl,
                                         cudaStream_t st, int* launches) {
   const int nbw = g_gj_panel_width(d);
   const size_t psm = g_gj_panel_smem(d);
-  static size_t attr_set = 0;
+  static size_t attr_of[64] = {0};   // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& attr_set = attr_of[dev & 63];
   if (psm > 40 * 1024 && psm > attr_set) {
     cudaFuncSetAttribute(g_gj_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
     attr_set = psm;
