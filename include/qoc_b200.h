@@ -61,7 +61,8 @@ typedef enum {
 
 typedef struct {
   int32_t d;        /* Hilbert-space dimension: A0, A[j] are d x d                                              */
-  int32_t m;        /* number of propagated state columns: x0 is d x m                                          */
+  int32_t m;        /* number of propagated state columns: x0 is d x m.  m <= 64; more than 8 columns (the reference's
+                     * full-propagator use, m = d, src/penalty_fcns.jl:14) are swept in chunks that share one K1 pass     */
   int32_t nc;       /* number of controls: length(A)                                                            */
   int32_t nt;       /* number of time slices: size(u, 2)                                                        */
   int32_t batch;    /* number of independent pulses evaluated per call (1 = the reference's case)               */

@@ -39,6 +39,12 @@ struct qoc_handle {
   double *dx0 = nullptr, *dT = nullptr, *dxs = nullptr, *dle = nullptr, *dX = nullptr, *dLAM = nullptr;
   double *dxf = nullptr, *dlam0 = nullptr, *dJ = nullptr, *dg = nullptr, *dflops = nullptr, *dlamf = nullptr;
   double *dS = nullptr;
+  // more than 8 state columns (full-propagator use, m = d: src/penalty_fcns.jl:14): the columns evolve independently
+  // (src/gradient_computations.jl:27-29, :52-58 act column by column), so they are swept in nch chunks of prob.m <= 8 columns
+  // (zero-padded) that share one K1 pass; the terminal cost couples them through Omega = tr(T'x) only (chunk_cost_kernel)
+  int m_total = 0, nch = 1;
+  struct ColBufs { double *dx0, *dT, *dxs, *dle, *dX, *dLAM, *dxf, *dlam0, *dlamf, *dcs, *dg; };
+  std::vector<ColBufs> cols;  // nch > 1: cols[0] = the primary buffers above
   // second-generation sweeps (csrc/qoc_sweep.cuh): two-level boundary scan K2G + K3N; used when there is no running penalty
   bool new_k2 = false, new_k3 = false;
   int G = 1;                  // groups per pulse in K2G
@@ -213,6 +219,14 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   cudaSetDevice(h->prob.device);
   double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
                     h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg, h->dQ2, h->dB, h->dc, h->ddc, h->dbnd};
+  if (h->nch > 1 && !h->cols.empty()) {   // the primary pointers may currently alias any chunk: free through the table only
+    for (auto& cb : h->cols) {
+      double* cbufs[] = {cb.dx0, cb.dT, cb.dxs, cb.dle, cb.dX, cb.dLAM, cb.dxf, cb.dlam0, cb.dlamf, cb.dcs, cb.dg};
+      for (double* b : cbufs) if (b) cudaFree(b);
+    }
+    h->dx0 = h->dT = h->dxs = h->dle = h->dX = h->dLAM = h->dxf = h->dlam0 = h->dlamf = h->dcs = h->dg = nullptr;
+    bufs[6] = bufs[7] = bufs[8] = bufs[9] = bufs[10] = bufs[11] = bufs[12] = bufs[13] = bufs[15] = bufs[17] = bufs[19] = nullptr;
+  }
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->dstatus) cudaFree(h->dstatus);
@@ -233,7 +247,19 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   g_create_error.clear();
   if (!prob || !A0 || !x0 || !out || (prob->nc > 0 && !A)) { g_create_error = "NULL argument"; return QOC_ERR_INVALID; }
   *out = nullptr;
-  const qoc_problem& p = *prob;
+  qoc_problem p_local = *prob;
+  int m_total = prob->m, nch = 1;
+  if (p_local.n <= 0) p_local.n = m_total;
+  if (m_total > 8) {   // column chunks of equal width <= 8 (the last one zero-padded)
+    if (m_total > 64) { g_create_error = "m > 64 state columns not supported"; return QOC_ERR_UNSUPPORTED; }
+    if (prob->n_pen_rows > 0 && prob->n_pen_cols > 0 && prob->mu != 0.0) {
+      g_create_error = "the running state penalty is not supported with more than 8 state columns yet";
+      return QOC_ERR_UNSUPPORTED;
+    }
+    nch = (m_total + 7) / 8;
+    p_local.m = (m_total + nch - 1) / nch;
+  }
+  const qoc_problem& p = p_local;
   if (p.d <= 0 || p.m <= 0 || p.nc <= 0 || p.nt <= 0 || p.batch <= 0) { g_create_error = "non-positive size"; return QOC_ERR_DIMENSION; }
   if (p.order < 0 || p.order > 4) { g_create_error = "order must be 0 (Frechet) or 1..4"; return QOC_ERR_INVALID; }
   if (p.cost < 0 || p.cost > 3) { g_create_error = "unknown cost kind"; return QOC_ERR_INVALID; }
@@ -242,7 +268,6 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     return QOC_ERR_DIMENSION;
   }
   if (p.cost != QOC_COST_NONE && !T) { g_create_error = "built-in cost needs a target T"; return QOC_ERR_INVALID; }
-  if (p.m > 8) { g_create_error = "m > 8 state columns not supported yet"; return QOC_ERR_UNSUPPORTED; }
   if (p.nc > 8) { g_create_error = "nc > 8 controls not supported yet"; return QOC_ERR_UNSUPPORTED; }
   if ((p.n_pen_rows > 0) != (p.n_pen_cols > 0) || (p.n_pen_rows > 0 && (!p.pen_rows || !p.pen_cols))) {
     g_create_error = "penalty index lists inconsistent"; return QOC_ERR_INVALID;
@@ -281,7 +306,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   }
   qoc_handle* h = new qoc_handle();
   h->prob = p;
-  if (h->prob.n <= 0) h->prob.n = p.m;
+  h->m_total = m_total; h->nch = nch;
   h->gpath = use_gpath;
   for (int i = 0; i < p.n_pen_rows; i++) {
     if (p.pen_rows[i] < 0 || p.pen_rows[i] >= p.d) { g_create_error = "penalty row index out of range"; delete h; return QOC_ERR_INVALID; }
@@ -525,9 +550,38 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     CR(cudaMemcpy(h->dA0p, tmp.data(), slotB, cudaMemcpyHostToDevice));
     CR(cudaMemcpy(h->dAp, tmp.data() + h->slot_d, slotB * p.nc, cudaMemcpyHostToDevice));
   }
-  CR(cudaMemcpy(h->dx0, x0, dmB, cudaMemcpyHostToDevice));
-  if (T) CR(cudaMemcpy(h->dT, T, dmB, cudaMemcpyHostToDevice));
-  else CR(cudaMemset(h->dT, 0, dmB));
+  if (h->nch == 1) {
+    CR(cudaMemcpy(h->dx0, x0, dmB, cudaMemcpyHostToDevice));
+    if (T) CR(cudaMemcpy(h->dT, T, dmB, cudaMemcpyHostToDevice));
+    else CR(cudaMemset(h->dT, 0, dmB));
+  } else {
+    h->cols.resize(h->nch);
+    h->cols[0] = qoc_handle::ColBufs{h->dx0, h->dT, h->dxs, h->dle, h->dX, h->dLAM, h->dxf, h->dlam0, h->dlamf, h->dcs, h->dg};
+    for (int c = 1; c < h->nch; c++) {
+      qoc_handle::ColBufs& cb = h->cols[c];
+      memset(&cb, 0, sizeof cb);
+      CR(cudaMalloc(&cb.dx0, dmB));
+      CR(cudaMalloc(&cb.dT, dmB));
+      CR(cudaMalloc(&cb.dxs, (size_t)h->nseg * dmB));
+      CR(cudaMalloc(&cb.dle, (size_t)h->nseg * dmB));
+      CR(cudaMalloc(&cb.dX, (size_t)p.batch * (p.nt + 1) * dmB));
+      if (h->dLAM) CR(cudaMalloc(&cb.dLAM, (size_t)p.batch * (p.nt + 1) * dmB));
+      CR(cudaMalloc(&cb.dxf, (size_t)p.batch * dmB));
+      CR(cudaMalloc(&cb.dlam0, (size_t)p.batch * dmB));
+      CR(cudaMalloc(&cb.dlamf, (size_t)p.batch * dmB));
+      CR(cudaMalloc(&cb.dcs, (size_t)h->nseg * dmB));
+      CR(cudaMalloc(&cb.dg, nsl * p.nc * 8));
+    }
+    for (int c = 0; c < h->nch; c++) {   // columns [c mc, (c+1) mc) of x0 / T, zero beyond m_total
+      const int c0 = c * p.m, ncol = (c0 + p.m <= h->m_total) ? p.m : (h->m_total - c0 > 0 ? h->m_total - c0 : 0);
+      CR(cudaMemset(h->cols[c].dx0, 0, dmB));
+      CR(cudaMemset(h->cols[c].dT, 0, dmB));
+      if (ncol > 0) {
+        CR(cudaMemcpy(h->cols[c].dx0, x0 + (size_t)2 * p.d * c0, (size_t)2 * p.d * ncol * 8, cudaMemcpyHostToDevice));
+        if (T) CR(cudaMemcpy(h->cols[c].dT, T + (size_t)2 * p.d * c0, (size_t)2 * p.d * ncol * 8, cudaMemcpyHostToDevice));
+      }
+    }
+  }
 #undef CR
   *out = h;
   return QOC_OK;
@@ -547,15 +601,20 @@ extern "C" int qoc_set_eager_jacobians(qoc_handle* h, int on) {
 extern "C" int qoc_set_cost(qoc_handle* h, int cost, const double* T, int n) {
   if (!h) return QOC_ERR_INVALID;
   if (cost < 0 || cost > 3) { h->err = "unknown cost kind"; return QOC_ERR_INVALID; }
-  if (cost == QOC_COST_ZCAL && h->prob.m != 4) {   // src/penalty_fcns.jl:28-30
+  if (cost == QOC_COST_ZCAL && h->m_total != 4) {   // src/penalty_fcns.jl:28-30
     h->err = "Only works for two-qubit gates, x_target must have four columns";
     return QOC_ERR_DIMENSION;
   }
   if (cost != QOC_COST_NONE && !T) { h->err = "built-in cost needs a target T"; return QOC_ERR_INVALID; }
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
-  if (T) QOC_CUDA(h, cudaMemcpy(h->dT, T, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyHostToDevice));
+  if (T && h->nch == 1) QOC_CUDA(h, cudaMemcpy(h->dT, T, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyHostToDevice));
+  if (T && h->nch > 1)
+    for (int c = 0; c < h->nch; c++) {
+      const int c0 = c * h->prob.m, ncol = (c0 + h->prob.m <= h->m_total) ? h->prob.m : (h->m_total - c0 > 0 ? h->m_total - c0 : 0);
+      if (ncol > 0) QOC_CUDA(h, cudaMemcpy(h->cols[c].dT, T + (size_t)2 * h->prob.d * c0, (size_t)2 * h->prob.d * ncol * 8, cudaMemcpyHostToDevice));
+    }
   h->prob.cost = cost;
-  h->prob.n = n > 0 ? n : h->prob.m;
+  h->prob.n = n > 0 ? n : h->m_total;
   return QOC_OK;
 }
 
@@ -956,6 +1015,111 @@ static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d
 
 static bool has_penalty(const qoc_handle* h) { return h->row_mask != 0u && h->col_mask != 0u && h->prob.mu != 0.0; }
 
+// ---- more than 8 state columns: column chunks sharing one K1 pass ---------------------------------------------------
+static void use_cols(qoc_handle* h, int c) {
+  const qoc_handle::ColBufs& cb = h->cols[c];
+  h->dx0 = cb.dx0; h->dT = cb.dT; h->dxs = cb.dxs; h->dle = cb.dle; h->dX = cb.dX; h->dLAM = cb.dLAM;
+  h->dxf = cb.dxf; h->dlam0 = cb.dlam0; h->dlamf = cb.dlamf; h->dcs = cb.dcs; h->dg = cb.dg;
+}
+struct ChunkCost {
+  int d, mc, nch, cost, n, want_lam;
+  const double* xf[8];
+  const double* T[8];
+  double* lamf[8];
+  double* J;
+};
+// one CTA per pulse: Omega = tr(T'x_N) over ALL columns, J and lambda_N = coef T for every chunk
+// (src/penalty_fcns.jl:15-24; test/test_gradient_computation.jl:24-25)
+__global__ void __launch_bounds__(256) chunk_cost_kernel(ChunkCost q) {
+  __shared__ double ov[16];
+  const int tid = threadIdx.x, lane = tid & 31, b = blockIdx.x;
+  const size_t dm = (size_t)q.d * q.mc;
+  if (tid < 16) ov[tid] = 0.0;
+  __syncthreads();
+  double orr = 0.0, oii = 0.0;
+  for (int c = 0; c < q.nch; c++) {
+    const double2* x = reinterpret_cast<const double2*>(q.xf[c]) + (size_t)b * dm;
+    const double2* t = reinterpret_cast<const double2*>(q.T[c]);
+    for (size_t e = tid; e < dm; e += 256) { orr += t[e].x * x[e].x + t[e].y * x[e].y; oii += t[e].x * x[e].y - t[e].y * x[e].x; }
+  }
+  for (int off = 16; off > 0; off >>= 1) { orr += __shfl_xor_sync(0xffffffffu, orr, off); oii += __shfl_xor_sync(0xffffffffu, oii, off); }
+  if (lane == 0) { atomicAdd(&ov[0], orr); atomicAdd(&ov[1], oii); }
+  __syncthreads();
+  CostCoef cc;
+  cost_from_overlaps(q.cost, q.n, 1, ov, cc);
+  if (tid == 0 && q.J) q.J[b] = cc.J;
+  if (!q.want_lam) return;
+  for (int c = 0; c < q.nch; c++) {
+    const double2* t = reinterpret_cast<const double2*>(q.T[c]);
+    double2* l = reinterpret_cast<double2*>(q.lamf[c]) + (size_t)b * dm;
+    for (size_t e = tid; e < dm; e += 256) l[e] = make_double2(cc.cr[0] * t[e].x - cc.ci[0] * t[e].y, cc.cr[0] * t[e].y + cc.ci[0] * t[e].x);
+  }
+}
+static int run_sweeps(qoc_handle* h, bool want_grad, const double* d_lam_final, double* d_J, double* d_dJdu,
+                      bool store_states, cudaStream_t st);
+__global__ void chunk_sum_kernel(double* out, const double* const g0, const double* const g1, const double* const g2, const double* const g3,
+                                 const double* const g4, const double* const g5, const double* const g6, const double* const g7, int nch, size_t n) {
+  const double* g[8] = {g0, g1, g2, g3, g4, g5, g6, g7};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < nch; c++) s += g[c][i];
+    out[i] = s;
+  }
+}
+// forward sweeps of every chunk (cost switched off: it needs all columns), then J (and lambda_N when want_lam)
+static int chunked_forward(qoc_handle* h, bool store_states, bool want_lam, double* d_J, cudaStream_t st) {
+  const int cost = h->prob.cost;
+  int rc = QOC_OK;
+  h->prob.cost = QOC_COST_NONE;
+  for (int c = 0; c < h->nch && rc == QOC_OK; c++) { use_cols(h, c); rc = run_sweeps(h, false, nullptr, nullptr, nullptr, store_states, st); }
+  h->prob.cost = cost;
+  use_cols(h, 0);
+  if (rc != QOC_OK) return rc;
+  if (cost != QOC_COST_NONE) {
+    ChunkCost q;
+    memset(&q, 0, sizeof q);
+    q.d = h->prob.d; q.mc = h->prob.m; q.nch = h->nch; q.cost = cost; q.n = h->prob.n; q.want_lam = want_lam ? 1 : 0;
+    for (int c = 0; c < h->nch; c++) { q.xf[c] = h->cols[c].dxf; q.T[c] = h->cols[c].dT; q.lamf[c] = h->cols[c].dlamf; }
+    q.J = d_J ? d_J : h->dJ;
+    chunk_cost_kernel<<<h->prob.batch, 256, 0, st>>>(q);
+    h->launches++;
+    QOC_CUDA(h, cudaGetLastError());
+  }
+  return QOC_OK;
+}
+// backward sweeps + gradient contraction of every chunk from its lambda_N (cols[c].dlamf), summed into d_dJdu
+static int chunked_backward(qoc_handle* h, bool store_states, double* d_dJdu, cudaStream_t st) {
+  int rc = QOC_OK;
+  for (int c = 0; c < h->nch && rc == QOC_OK; c++) { use_cols(h, c); rc = run_sweeps(h, true, h->cols[c].dlamf, nullptr, h->cols[c].dg, store_states, st); }
+  use_cols(h, 0);
+  if (rc != QOC_OK) return rc;
+  const double* g[8];
+  for (int c = 0; c < 8; c++) g[c] = h->cols[c < h->nch ? c : 0].dg;
+  const size_t n = (size_t)h->prob.batch * h->prob.nt * h->prob.nc;
+  // (the sum may land in chunk 0's own buffer: every element is read before it is written, by the same thread)
+  chunk_sum_kernel<<<(int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(d_dJdu ? d_dJdu : h->cols[0].dg, g[0], g[1], g[2], g[3],
+                                                                                            g[4], g[5], g[6], g[7], h->nch, n);
+  h->launches++;
+  QOC_CUDA(h, cudaGetLastError());
+  return QOC_OK;
+}
+// d x m_total x batch host array <-> the chunks' d x mc x batch device arrays (column blocks)
+static int chunked_copy(qoc_handle* h, double* host, bool to_host, size_t per_pulse_items, int which /*0 xf, 1 lamf*/, cudaStream_t st) {
+  const qoc_problem& p = h->prob;
+  (void)per_pulse_items;
+  for (int c = 0; c < h->nch; c++) {
+    const int c0 = c * p.m, ncol = (c0 + p.m <= h->m_total) ? p.m : (h->m_total - c0 > 0 ? h->m_total - c0 : 0);
+    double* dev = which == 0 ? h->cols[c].dxf : h->cols[c].dlamf;
+    if (!to_host) QOC_CUDA(h, cudaMemsetAsync(dev, 0, (size_t)p.batch * 2 * p.d * p.m * 8, st));
+    if (ncol == 0) continue;
+    const size_t hp = (size_t)2 * p.d * h->m_total * 8, dpitch = (size_t)2 * p.d * p.m * 8, w = (size_t)2 * p.d * ncol * 8;
+    double* hptr = host + (size_t)2 * p.d * c0;
+    if (to_host) QOC_CUDA(h, cudaMemcpy2DAsync(hptr, hp, dev, dpitch, w, p.batch, cudaMemcpyDeviceToHost, st));
+    else QOC_CUDA(h, cudaMemcpy2DAsync(dev, dpitch, hptr, hp, w, p.batch, cudaMemcpyHostToDevice, st));
+  }
+  return QOC_OK;
+}
+
 // Everything after K1.  Without a running penalty: K2 (forward, cost, backward) then K3.  With it the costate
 // recurrence is affine, lambda_k = U_k' lambda_{k+1} + dL_dx(x_k) (src/gradient_computations.jl:55-57), so the
 // segment-level scan needs the per-segment affine terms first:
@@ -1012,7 +1176,9 @@ static int check_status(qoc_handle* h) {
   return QOC_OK;
 }
 
-static double sweep_flops(const qoc_problem& p, bool grad) {
+static double sweep_flops(const qoc_problem& p0, bool grad, int m_total = 0) {
+  qoc_problem p = p0;
+  if (m_total > 0) p.m = m_total;
   const double d2 = (double)p.d * p.d;
   const double per = grad ? 8.0 * d2 * p.m * (2 + p.nc) + 4.0 * p.nc * d2 : 8.0 * d2 * p.m;
   return per * (double)p.nt * (double)p.batch;
@@ -1028,6 +1194,11 @@ extern "C" int qoc_eval_device(qoc_handle* h, const double* d_u, double* d_J, do
   if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[0], st));
   if ((rc = launch_k1(h, d_u, true, st)) != QOC_OK) return rc;
   if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[1], st));
+  if (h->nch > 1) {
+    if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[2], st));
+    if ((rc = chunked_forward(h, false, true, d_J, st)) != QOC_OK) return rc;
+    if ((rc = chunked_backward(h, h->prob.store_costates != 0, d_dJdu ? d_dJdu : h->cols[0].dg, st)) != QOC_OK) return rc;
+  } else
   if (!has_penalty(h) && !h->gpath) {
     if ((rc = launch_k2(h, 0, false, nullptr, nullptr, d_J, st)) != QOC_OK) return rc;
     if (h->profiling) QOC_CUDA(h, cudaEventRecord(h->ev[2], st));
@@ -1052,7 +1223,7 @@ static int fetch_flops(qoc_handle* h, bool grad) {
   double f[2] = {0, 0};
   if (h->mail_valid) { f[0] = h->h_mail[0]; f[1] = h->h_mail[1]; h->mail_valid = false; }
   else QOC_CUDA(h, cudaMemcpy(f, h->dflops, 16, cudaMemcpyDeviceToHost));
-  h->alg_flops = f[0] + sweep_flops(h->prob, grad);
+  h->alg_flops = f[0] + sweep_flops(h->prob, grad, h->m_total);
   h->k1_exec_flops = f[1];
   return QOC_OK;
 }
@@ -1095,10 +1266,15 @@ extern "C" int qoc_propagate(qoc_handle* h, const double* u, double* J_out, doub
   // qoc_set_eager_jacobians(h, 1) produces them here (they share the Pade powers) when f_grad always follows f.
   if ((rc = launch_k1(h, h->du, h->eager_jac, h->stream)) != QOC_OK) return rc;
   const bool builtin = p.cost != QOC_COST_NONE || has_penalty(h);  // J (or its penalty part) is formed on the device
-  if ((rc = run_sweeps(h, false, nullptr, nullptr, nullptr, false, h->stream)) != QOC_OK) return rc;
+  if (h->nch > 1) {
+    if ((rc = chunked_forward(h, false, false, nullptr, h->stream)) != QOC_OK) return rc;
+    if (x_final_out && (rc = chunked_copy(h, x_final_out, true, 0, 0, h->stream)) != QOC_OK) return rc;
+  } else {
+    if ((rc = run_sweeps(h, false, nullptr, nullptr, nullptr, false, h->stream)) != QOC_OK) return rc;
+    if (x_final_out)
+      QOC_CUDA(h, cudaMemcpyAsync(x_final_out, h->dxf, (size_t)p.batch * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
   if (J_out && builtin) QOC_CUDA(h, cudaMemcpyAsync(J_out, h->dJ, (size_t)p.batch * 8, cudaMemcpyDeviceToHost, h->stream));
-  if (x_final_out)
-    QOC_CUDA(h, cudaMemcpyAsync(x_final_out, h->dxf, (size_t)p.batch * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost, h->stream));
   if ((rc = queue_mail(h)) != QOC_OK) return rc;
   h->last_u.assign(u, u + nu);   // (host copy for the stale-cache check: overlaps the device work queued above)
   QOC_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1129,31 +1305,64 @@ extern "C" int qoc_gradient(qoc_handle* h, const double* u, const double* lambda
     if ((rc = launch_k1(h, h->du, true, h->stream)) != QOC_OK) return rc;
     k1_rerun = true;
   }
+  if (h->nch > 1) {
+    if (lambda_final) { if ((rc = chunked_copy(h, const_cast<double*>(lambda_final), false, 0, 1, h->stream)) != QOC_OK) return rc; }
+    else if ((rc = chunked_forward(h, false, true, nullptr, h->stream)) != QOC_OK) return rc;   // lambda_N of the built-in cost
+    if ((rc = chunked_backward(h, true, h->cols[0].dg, h->stream)) != QOC_OK) return rc;
+    QOC_CUDA(h, cudaMemcpyAsync(dJdu_out, h->cols[0].dg, nu * 8, cudaMemcpyDeviceToHost, h->stream));
+  } else {
   if (lambda_final)
     QOC_CUDA(h, cudaMemcpyAsync(h->dlamf, lambda_final, (size_t)p.batch * 2 * p.d * p.m * 8, cudaMemcpyHostToDevice, h->stream));
   if ((rc = run_sweeps(h, true, lambda_final ? h->dlamf : nullptr, nullptr, nullptr, true, h->stream)) != QOC_OK) return rc;
   QOC_CUDA(h, cudaMemcpyAsync(dJdu_out, h->dg, nu * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
   if (k1_rerun && (rc = queue_mail(h)) != QOC_OK) return rc;
   QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   if (k1_rerun) {
     if ((rc = check_status(h)) != QOC_OK) return rc;
     if ((rc = fetch_flops(h, true)) != QOC_OK) return rc;
   } else
-    h->alg_flops += sweep_flops(p, true) - sweep_flops(p, false);
+    h->alg_flops += sweep_flops(p, true, h->m_total) - sweep_flops(p, false, h->m_total);
   return QOC_OK;
 }
 
 // ---- getters ----------------------------------------------------------------------------------------------------
+
+static int recompute_states(qoc_handle* h) {
+  return (h->gpath && h->gs2) ? gpath_sweep2(h, 1, true, false, nullptr, nullptr, nullptr, nullptr, h->stream)
+         : h->gpath ? gpath_sweep(h, 1, false, nullptr, nullptr, nullptr, nullptr, h->stream)
+                  : launch_k3(h, false, true, nullptr, h->stream);
+}
+// chunked handles: the d x mc x (Nt+1) x batch arrays of the chunks -> d x m_total x (Nt+1) x batch
+static int gather_chunks(qoc_handle* h, bool costates, double* out) {
+  const qoc_problem& p = h->prob;
+  const size_t nk = (size_t)p.batch * (p.nt + 1), dm = (size_t)2 * p.d * p.m;
+  std::vector<double> tmp(nk * dm);
+  for (int c = 0; c < h->nch; c++) {
+    const int c0 = c * p.m, ncol = (c0 + p.m <= h->m_total) ? p.m : (h->m_total - c0 > 0 ? h->m_total - c0 : 0);
+    if (ncol == 0) continue;
+    QOC_CUDA(h, cudaMemcpy(tmp.data(), costates ? h->cols[c].dLAM : h->cols[c].dX, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < nk; k++)
+      memcpy(out + (k * h->m_total + c0) * 2 * p.d, tmp.data() + k * dm, (size_t)2 * p.d * ncol * 8);
+  }
+  return QOC_OK;
+}
 
 extern "C" int qoc_get_states(qoc_handle* h, double* x_out) {
   if (!h || !x_out) return QOC_ERR_INVALID;
   if (!h->have_u) { h->err = "no propagation cached"; return QOC_ERR_STALE_CACHE; }
   const qoc_problem& p = h->prob;
   QOC_CUDA(h, cudaSetDevice(p.device));
+  if (h->nch > 1) {
+    if (!h->states_valid) {
+      for (int c = 0; c < h->nch; c++) { use_cols(h, c); const int rc = recompute_states(h); if (rc != QOC_OK) { use_cols(h, 0); return rc; } }
+      use_cols(h, 0);
+    }
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return gather_chunks(h, false, x_out);
+  }
   if (!h->states_valid) {
-    int rc = (h->gpath && h->gs2) ? gpath_sweep2(h, 1, true, false, nullptr, nullptr, nullptr, nullptr, h->stream)
-             : h->gpath ? gpath_sweep(h, 1, false, nullptr, nullptr, nullptr, nullptr, h->stream)
-                      : launch_k3(h, false, true, nullptr, h->stream);
+    int rc = recompute_states(h);
     if (rc != QOC_OK) return rc;
   }
   QOC_CUDA(h, cudaMemcpyAsync(x_out, h->dX, (size_t)p.batch * (p.nt + 1) * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1166,6 +1375,7 @@ extern "C" int qoc_get_costates(qoc_handle* h, double* lam_out) {
   if (!h->prob.store_costates || !h->costates_valid) { h->err = "costates not stored (store_costates=0 or no gradient yet)"; return QOC_ERR_STALE_CACHE; }
   const qoc_problem& p = h->prob;
   QOC_CUDA(h, cudaSetDevice(p.device));
+  if (h->nch > 1) return gather_chunks(h, true, lam_out);
   QOC_CUDA(h, cudaMemcpy(lam_out, h->dLAM, (size_t)p.batch * (p.nt + 1) * 2 * p.d * p.m * 8, cudaMemcpyDeviceToHost));
   return QOC_OK;
 }
@@ -1236,6 +1446,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) kq_reduce_kernel(const double*
 // two-level sweeps.  Never a silent fallback: anything else is QOC_ERR_UNSUPPORTED.
 static int shard_guard(qoc_handle* h) {
   if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
+  if (h->nch > 1) { h->err = "time sharding with more than 8 state columns is not supported yet"; return QOC_ERR_UNSUPPORTED; }
   if (has_penalty(h) || (h->row_mask64 != 0ull && h->col_mask != 0u && h->prob.mu != 0.0)) {
     h->err = "the qoc_shard_* phase API does not carry the running state penalty (affine costate term)";
     return QOC_ERR_UNSUPPORTED;
