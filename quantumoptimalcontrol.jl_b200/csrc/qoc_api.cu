@@ -66,6 +66,12 @@ struct qoc_handle {
   double* dQ2 = nullptr;      // second segment-propagator buffer (ping-pong of the batched products)
   int gL = 1;                 // slices per segment on the general path (the last segment of a pulse may be shorter)
   bool gs2 = false;
+  // Jacobians streamed instead of stored (general path, two-level sweeps): when U_k and all dU_k/du_j do not fit the device
+  // (d = 256, Nt = 1e5, nc = 2: 106 GB + 213 GB), dL holds ONE chunk; the gradient pass re-runs K1 chunk by chunk after the
+  // sweeps and contracts each chunk's Jacobians with the stored x_k, lambda_{k+1} at once.  Costs one extra expm per slice
+  // ((pi + s + 4/3) M of (pi + s + 4/3 + nc G) M).  QOC_STREAM_JAC=1 forces it (tests), =0 forbids it.
+  bool stream_jac = false;
+  const double* k1_u = nullptr;   // the u of the last K1 launch (device pointer), for the streamed gradient pass
   bool k1_skewh = false;      // A0 and every A_j skew-Hermitian (bitwise): k1s_kernel forms A E + E A, A2 M2 + M2 A2, X E as P + P^dagger
   bool k1s_ok = false;        // d <= 9, nc <= 4: the small-dimension kernel (nine lanes per slice, three slices per warp)
   int k1s_wpb = 0;            // its warps per CTA (what fits shared memory)
@@ -462,7 +468,15 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   CR(cudaMalloc(&h->dAp, slotB * p.nc));
   CR(cudaMalloc(&h->du, nsl * p.nc * 8));
   CR(cudaMalloc(&h->dU, nsl * slotB));
-  CR(cudaMalloc(&h->dL, nsl * p.nc * slotB));
+  if (h->gpath && h->gs2) {
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    const char* sj = getenv("QOC_STREAM_JAC");
+    // (U_k is allocated already) the Jacobians + the chunk workspace + states, costates and boundary buffers still to come
+    const double need = (double)nsl * p.nc * slotB + (double)h->gnw * h->gchunk * slotB + 4.0 * (double)p.batch * (p.nt + 1) * dmB;
+    h->stream_jac = (sj && sj[0] == '1') || (!(sj && sj[0] == '0') && need > 0.9 * (double)fr);
+  }
+  CR(cudaMalloc(&h->dL, (h->stream_jac ? (size_t)h->gchunk : nsl) * p.nc * slotB));
   CR(cudaMalloc(&h->dQ, (size_t)h->nseg * slotB));
   CR(cudaMalloc(&h->dx0, dmB));
   CR(cudaMalloc(&h->dT, dmB));
@@ -742,8 +756,12 @@ static int gpath_sweep2(qoc_handle* h, int mode, bool skip_bwd, bool want_grad, 
 static const double kB13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
                                 10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
 
-static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_t st) {
+static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_t st, bool stream_contract = false,
+                    double* d_dJdu = nullptr) {
   const qoc_problem& p = h->prob;
+  h->k1_u = d_u;
+  // Jacobian slots of the chunk at c0: the full array, or (streamed) the one-chunk buffer that is contracted right away
+  auto Lbase = [&](size_t c0) { return h->stream_jac ? (size_t)0 : c0; };
   const int nc = p.nc, d = p.d;
   const size_t nsl = (size_t)p.batch * p.nt;
   const bool taylor = p.order != 0;
@@ -810,7 +828,7 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
     if (want_jac) {
       for (int j = 0; j < nc; j++) {
         const GOp E{h->dAp + (size_t)j * h->slot_d, 0};
-        double* Lout = h->dL + (c0 * nc + j) * h->slot_d;
+        double* Lout = h->dL + (Lbase(c0) * nc + j) * h->slot_d;
         const long long lstride = (long long)nc * h->slot_d;
         if (taylor) {
           // expm_jacobian!  src/gradient_computations.jl:177-213 (dt = 1), X = unscaled generator
@@ -863,7 +881,7 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
         for (int j = 0; j < nc; j++) {
           GOp Lj = g.W(L0 + j);
           GOp Aa[2] = {Rop, Lj}, Bb[2] = {Lj, Rop};
-          if (last) g.gemm(h->dL + (c0 * nc + j) * h->slot_d, (long long)nc * h->slot_d, 2, Aa, Bb, 1.0, 0, nullptr, nullptr, 0.0);
+          if (last) g.gemm(h->dL + (Lbase(c0) * nc + j) * h->slot_d, (long long)nc * h->slot_d, 2, Aa, Bb, 1.0, 0, nullptr, nullptr, 0.0);
           else {
             g.gemm(g.Wp(TMP), h->slot_d, 2, Aa, Bb, 1.0, 0, nullptr, nullptr, 0.0);
             GOp D[1] = {g.W(TMP)}; double be[1] = {1.0}; g.lin(L0 + j, 1, D, be);
@@ -873,6 +891,17 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
       double* Rn = last ? h->dU + c0 * h->slot_d : g.Wp(TMPR);
       g.gemm(Rn, h->slot_d, 1, &Rop, &Rop, 1.0, 0, nullptr, nullptr, 0.0);
       if (!last) { GOp D[1] = {g.W(TMPR)}; double be[1] = {1.0}; g.lin(R, 1, D, be); }
+    }
+    if (stream_contract) {   // dJ/du of this chunk's slices from its Jacobians and the stored x_k, lambda_{k+1} (:65-74, :217-223)
+      GS gc;
+      memset(&gc, 0, sizeof gc);
+      gc.d = p.d; gc.S = h->S; gc.m = p.m; gc.nc = p.nc; gc.nt = p.nt; gc.slot = h->slot_d;
+      gc.L_ = h->dL; gc.X = h->dX; gc.LAM = h->dLAM; gc.dJdu = d_dJdu ? d_dJdu : h->dg;
+      gc.sl0 = (long long)c0; gc.L_chunked = 1;
+      const size_t c_smem = (size_t)(h->S + p.d) * 2 * p.m * 8;
+      if (c_smem > 40 * 1024) QOC_CUDA(h, cudaFuncSetAttribute(gs_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
+      gs_contract_kernel<<<dim3((unsigned)nb, p.nc), 256, c_smem, st>>>(gc);
+      h->launches++;
     }
     QOC_CUDA(h, cudaGetLastError());
   }
@@ -885,7 +914,8 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
     const double f2[2] = {f, 0.0};   // executed flops are not tracked on the general path
     QOC_CUDA(h, cudaMemcpyAsync(h->dflops, f2, 16, cudaMemcpyHostToDevice, st));
   }
-  h->have_jac = want_jac;
+  h->have_jac = want_jac || h->stream_jac;   // streamed: they are re-formed by the gradient pass, never stored
+  if (stream_contract) return QOC_OK;        // (the segment products exist already)
   if (h->gs2) return gpath_build_Q(h, st);
   return QOC_OK;
 }
@@ -913,7 +943,7 @@ static int gpath_sweep(qoc_handle* h, int phase, bool want_grad, const double* d
 }
 
 static int launch_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_t st) {
-  if (h->gpath) return gpath_k1(h, d_u, want_jac, st);
+  if (h->gpath) return gpath_k1(h, d_u, want_jac && !h->stream_jac, st);
   const qoc_problem& p = h->prob;
   K1Params k;
   k.d = p.d; k.nc = p.nc; k.nt = p.nt; k.batch = p.batch; k.order = p.order;
@@ -1128,6 +1158,11 @@ static int run_sweeps(qoc_handle* h, bool want_grad, const double* d_lam_final, 
                       bool store_states, cudaStream_t st) {
   int rc;
   const bool builtin = h->prob.cost != QOC_COST_NONE;
+  if (h->gpath && h->gs2 && h->stream_jac && (want_grad || d_lam_final)) {
+    // sweeps first (states and costates to HBM, no contraction), then the streamed Jacobian pass contracts chunk by chunk
+    if ((rc = gpath_sweep2(h, d_lam_final ? 2 : 0, false, false, d_lam_final, nullptr, d_J, d_dJdu, st)) != QOC_OK) return rc;
+    return gpath_k1(h, h->k1_u, true, st, true, d_dJdu);
+  }
   if (h->gpath && h->gs2) {
     if (d_lam_final) return gpath_sweep2(h, 2, false, true, d_lam_final, nullptr, d_J, d_dJdu, st);
     if (want_grad) return gpath_sweep2(h, 0, false, true, nullptr, nullptr, d_J, d_dJdu, st);
@@ -1396,6 +1431,7 @@ extern "C" int qoc_get_propagators(qoc_handle* h, double* U_out) {
 extern "C" int qoc_get_jacobians(qoc_handle* h, double* dU_out) {
   if (!h || !dU_out) return QOC_ERR_INVALID;
   if (!h->have_u) { h->err = "no propagation cached"; return QOC_ERR_STALE_CACHE; }
+  if (h->stream_jac) { h->err = "this handle streams its Jacobians (they do not fit the device): nothing is stored"; return QOC_ERR_UNSUPPORTED; }
   if (!h->have_jac) {   // lazy: K1 with Jacobians on the cached u
     QOC_CUDA(h, cudaSetDevice(h->prob.device));
     const int rc = launch_k1(h, h->du, true, h->stream);
@@ -1525,6 +1561,10 @@ extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_e
   int rc;
   if (h->gpath) {   // backward from the external costate over the states the forward call left in HBM
     if (!h->states_valid) { h->err = "qoc_shard_backward_device needs qoc_shard_forward_device first"; return QOC_ERR_STALE_CACHE; }
+    if (h->stream_jac) {
+      rc = gpath_sweep2(h, 2, false, false, d_lambda_end, nullptr, nullptr, d_dJdu, st);
+      if (rc == QOC_OK) rc = gpath_k1(h, h->k1_u, true, st, true, d_dJdu);
+    } else
     rc = gpath_sweep2(h, 2, false, true, d_lambda_end, nullptr, nullptr, d_dJdu, st);
   } else {
     rc = launch_k2(h, 2, false, d_lambda_end, nullptr, nullptr, st);
@@ -1558,6 +1598,10 @@ extern "C" int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int
   }
   h->launches += 1;
   int rc;
+  if (h->gpath && h->stream_jac) {
+    if ((rc = gpath_sweep2(h, 4, false, false, q.lam_end, q.x_start, nullptr, d_dJdu, st)) != QOC_OK) return rc;
+    return gpath_k1(h, h->k1_u, true, st, true, d_dJdu);
+  }
   if (h->gpath) return gpath_sweep2(h, 4, false, true, q.lam_end, q.x_start, nullptr, d_dJdu, st);
   if (h->new_k2) {
     if ((rc = launch_k2(h, 4, false, q.lam_end, q.x_start, nullptr, st)) != QOC_OK) return rc;

@@ -765,6 +765,8 @@ struct GS {
   double* lam_start;
   double* J;
   double* dJdu;
+  long long sl0;       // gs_contract_kernel: flat index of the first slice of this launch
+  int L_chunked;       // ... and L_ holds the Jacobians of the slices [sl0, sl0 + gridDim.x) only (streamed Jacobians)
 };
 
 // one CTA per pulse: boundary walk over the segment propagators
@@ -884,7 +886,7 @@ __global__ void __launch_bounds__(256) gs_contract_kernel(GS g) {
   double* lk = xk + (size_t)S * W;               // d rows
   __shared__ double red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t sl = blockIdx.x;                  // flat slice index b*nt + k
+  const size_t sl = (size_t)g.sl0 + blockIdx.x;  // flat slice index b*nt + k
   const int j = blockIdx.y;
   const int b = (int)(sl / g.nt), k = (int)(sl - (size_t)b * g.nt);
   for (int e = tid; e < (S + d) * W; e += 256) xk[e] = 0.0;
@@ -892,7 +894,7 @@ __global__ void __launch_bounds__(256) gs_contract_kernel(GS g) {
   gs_from_global(xk, g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, d, m, tid, 256);
   gs_from_global(lk, g.LAM + ((size_t)b * (g.nt + 1) + k + 1) * 2 * dm, d, m, tid, 256);
   __syncthreads();
-  const double* Lre = g.L_ + (sl * g.nc + j) * g.slot;
+  const double* Lre = g.L_ + ((g.L_chunked ? (size_t)blockIdx.x : sl) * g.nc + j) * g.slot;
   const double* Lim = Lre + (size_t)d * S;
   const int units = d * S / 2, S2 = S / 2;
   double s = 0.0;

@@ -113,3 +113,42 @@ def test_time_sharding_on_two_real_ranks():
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0 and "TWO_RANK_PARITY_OK" in r.stdout
+
+
+# ---- streamed Jacobians (what lets C5 d = 256, Nt = 1e5 run on one 180 GB device) -----------------------------------------
+@pytest.mark.parametrize("d,nt,order", [(32, 5000, 0), (64, 2500, 3), (40, 700, 0)])
+def test_streamed_jacobians_equal_stored_jacobians(d, nt, order, monkeypatch):
+    """QOC_STREAM_JAC=1 forces the mode a handle picks by itself when U_k plus every dU_k/du_j would not fit the device:
+    dU_k/du_j of one chunk at a time, re-formed after the sweeps and contracted at once.  Same arithmetic, same order of
+    operations per slice -> the gradient must agree with the stored-Jacobian evaluation to rounding (1e-12), several chunks."""
+    cfg = o.config_synthetic(d, nt) if d != 40 else o.config_cavity(20, Nt=550)
+    J0, g0, c0 = gpu_eval(cfg, order)
+    c0.close()
+    monkeypatch.setenv("QOC_STREAM_JAC", "1")
+    J1, g1, c1 = gpu_eval(cfg, order)
+    assert abs(J1 - J0) <= 1e-13
+    assert np.abs(g1 - g0).max() <= 1e-12 * np.abs(g0).max()
+    # the split calls (propagate, then grape_sensitivity with a host closure) go through the same streamed pass
+    Jf, dJf = o.cost_closures(cfg)
+    q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], c1)
+    g2 = q.grape_sensitivity(cfg["A0"], cfg["A"], dJf, cfg["u"], cfg["x0"], c1, dUkdp_order=order)
+    assert np.abs(g2 - g0).max() <= 1e-12 * np.abs(g0).max()
+    with pytest.raises(q.QOCError):   # nothing is stored: the Jacobian getter says so
+        _ = c1.dUkdu
+    c1.close()
+
+
+def test_streamed_jacobians_time_sharded_in_library(monkeypatch):
+    import torch
+    from qoc_b200 import sharding
+    cfg = o.config_synthetic(32, 6000)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"])
+    J0, g0, c0 = gpu_eval(cfg, 0)
+    c0.close()
+    monkeypatch.setenv("QOC_STREAM_JAC", "1")
+    ngpu = torch.cuda.device_count()
+    sh = sharding.InProcessSharded(cfg["A0"], cfg["A"], cfg["x0"], cost[1], cfg["u"].shape, [r % ngpu for r in range(3)], kind="time",
+                                   dUkdp_order=0)
+    J, g = sh.evaluate(cfg["u"])
+    assert abs(J - J0) <= 1e-10 and np.abs(g - g0).max() <= 1e-8 * np.abs(g0).max()
+    sh.close()
