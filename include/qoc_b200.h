@@ -103,6 +103,13 @@ int qoc_set_cost(qoc_handle* h, int cost, const double* T, int n);
  * on the cached u.  on != 0: qoc_propagate produces them together with U_k (they share the Pade powers), which is
  * cheaper when f_grad always follows f.  qoc_eval always does both in one pass.                                  */
 int qoc_set_eager_jacobians(qoc_handle* h, int on);
+/* Optional promise |u[j,k]| <= umax[j] for every later call (an optimiser with box bounds knows them:
+ * examples/zz_coupling_ipopt_exp.jl:54-56).  On the general path (d > 28) the Pade degree and the number of squarings are
+ * chosen per launch from a bound on ||X_k||_1; without the promise that bound is max_k |u_jk|, read back from the device
+ * (one small synchronisation per call); with it qoc_eval_device never synchronises (and can be captured in a CUDA graph).
+ * The promise is checked on the device: a violation makes the next synchronising call fail with QOC_ERR_INVALID.
+ * umax: nc doubles; NULL withdraws the promise.  Smaller dimensions choose (degree, s) per slice on the device: no effect.  */
+int qoc_set_control_bounds(qoc_handle* h, const double* umax);
 
 /* ---- the hot path, host buffers in / host buffers out ------------------------------------------------------ */
 

@@ -31,6 +31,7 @@ SYMBOLS = {
     "qoc_set_order": (C.c_int, [_vp, C.c_int]),
     "qoc_set_cost": (C.c_int, [_vp, C.c_int, _dp, C.c_int]),
     "qoc_set_eager_jacobians": (C.c_int, [_vp, C.c_int]),
+    "qoc_set_control_bounds": (C.c_int, [_vp, _dp]),
     "qoc_create_sharded": (C.c_int, [C.POINTER(Problem), _dp, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
     "qoc_sharded_destroy": (C.c_int, [_vp]),
     "qoc_sharded_set_order": (C.c_int, [_vp, C.c_int]),

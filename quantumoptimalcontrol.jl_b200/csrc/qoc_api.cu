@@ -58,6 +58,7 @@ struct qoc_handle {
   int gchunk = 0, gnw = 0;
   double* gW = nullptr;       // workspace: gnw slots x gchunk slices
   double* dumax = nullptr;    // max_k |u_jk| per control
+  double* dubound = nullptr;  // the caller's bounds (qoc_set_control_bounds), device copy
   double* dk1s_scr = nullptr; // k1s_kernel: per-lane-group scratch (A4, W)
   int* dpiv = nullptr;        // pivot rows of the blocked Gauss-Jordan inverse: gchunk x d
   double* dbnd = nullptr;     // time sharding: x_start and lambda_end of the local segment (2 x d x m c128)
@@ -70,6 +71,8 @@ struct qoc_handle {
   // (d = 256, Nt = 1e5, nc = 2: 106 GB + 213 GB), dL holds ONE chunk; the gradient pass re-runs K1 chunk by chunk after the
   // sweeps and contracts each chunk's Jacobians with the stored x_k, lambda_{k+1} at once.  Costs one extra expm per slice
   // ((pi + s + 4/3) M of (pi + s + 4/3 + nc G) M).  QOC_STREAM_JAC=1 forces it (tests), =0 forbids it.
+  bool have_ubound = false;       // qoc_set_control_bounds: |u_jk| <= ubound[j] promised by the caller
+  double ubound[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool stream_jac = false;
   const double* k1_u = nullptr;   // the u of the last K1 launch (device pointer), for the streamed gradient pass
   bool k1_skewh = false;      // A0 and every A_j skew-Hermitian (bitwise): k1s_kernel forms A E + E A, A2 M2 + M2 A2, X E as P + P^dagger
@@ -240,6 +243,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->dsync) cudaFree(h->dsync);
   if (h->dpiv) cudaFree(h->dpiv);
   if (h->dk1s_scr) cudaFree(h->dk1s_scr);
+  if (h->dubound) cudaFree(h->dubound);
   if (h->dpen_rows) cudaFree(h->dpen_rows);
   if (h->dpen_cols) cudaFree(h->dpen_cols);
   for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
@@ -607,6 +611,19 @@ extern "C" int qoc_set_order(qoc_handle* h, int order) {
   if (order != h->prob.order) { h->prob.order = order; h->have_jac = false; }
   return QOC_OK;
 }
+extern "C" int qoc_set_control_bounds(qoc_handle* h, const double* umax) {
+  if (!h) return QOC_ERR_INVALID;
+  if (!umax) { h->have_ubound = false; return QOC_OK; }
+  for (int j = 0; j < h->prob.nc && j < 8; j++) {
+    if (!(umax[j] >= 0.0) || !std::isfinite(umax[j])) { h->err = "control bounds must be finite and non-negative"; return QOC_ERR_INVALID; }
+    h->ubound[j] = umax[j];
+  }
+  QOC_CUDA(h, cudaSetDevice(h->prob.device));
+  if (!h->dubound) QOC_CUDA(h, cudaMalloc(&h->dubound, 64));
+  QOC_CUDA(h, cudaMemcpy(h->dubound, h->ubound, 64, cudaMemcpyHostToDevice));
+  h->have_ubound = true;
+  return QOC_OK;
+}
 extern "C" int qoc_set_eager_jacobians(qoc_handle* h, int on) {
   if (!h) return QOC_ERR_INVALID;
   h->eager_jac = on != 0;
@@ -766,12 +783,20 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
   const size_t nsl = (size_t)p.batch * p.nt;
   const bool taylor = p.order != 0;
   // number of squarings from the bound ||X_k||_1 <= ||A0||_1 + sum_j max_k|u_jk| ||A_j||_1 (uniform over the launch)
-  QOC_CUDA(h, cudaMemsetAsync(h->dumax, 0, 64, st));
-  g_umax_kernel<<<64, 256, 0, st>>>(d_u, nc, (long long)nsl, h->dumax);
-  h->launches++;
   double umax[8];
-  QOC_CUDA(h, cudaMemcpyAsync(umax, h->dumax, 64, cudaMemcpyDeviceToHost, st));
-  QOC_CUDA(h, cudaStreamSynchronize(st));
+  if (h->have_ubound) {
+    // the caller promised |u_jk| <= ubound[j] (qoc_set_control_bounds): nothing to read back, the call stays asynchronous;
+    // the promise is checked on the device and a violation is reported like a singular Pade denominator, at the next sync
+    for (int j = 0; j < 8; j++) umax[j] = h->ubound[j];
+    g_ubound_check_kernel<<<64, 256, 0, st>>>(d_u, nc, (long long)nsl, h->dubound, h->dstatus);
+    h->launches++;
+  } else {
+    QOC_CUDA(h, cudaMemsetAsync(h->dumax, 0, 64, st));
+    g_umax_kernel<<<64, 256, 0, st>>>(d_u, nc, (long long)nsl, h->dumax);
+    h->launches++;
+    QOC_CUDA(h, cudaMemcpyAsync(umax, h->dumax, 64, cudaMemcpyDeviceToHost, st));
+    QOC_CUDA(h, cudaStreamSynchronize(st));
+  }
   double bound = h->normA0;
   for (int j = 0; j < nc; j++) bound += umax[j] * h->normA[j];
   const double theta = taylor ? 5.4 : 4.74;
@@ -911,8 +936,8 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
     double G = 0.0;
     if (want_jac) G = taylor ? (p.order == 1 ? 0.0 : p.order == 2 ? 2.0 : p.order == 3 ? 5.0 : 10.0) : (2.0 * pi_q + 2.0 * sq + 2.0);
     const double f = M * ((pi_q + sq + 4.0 / 3.0) + nc * G) * (double)nsl;
-    const double f2[2] = {f, 0.0};   // executed flops are not tracked on the general path
-    QOC_CUDA(h, cudaMemcpyAsync(h->dflops, f2, 16, cudaMemcpyHostToDevice, st));
+    // (executed flops are not tracked on the general path; a kernel, not a copy from the host stack: graph-capturable)
+    g_set2_kernel<<<1, 1, 0, st>>>(h->dflops, f, 0.0);
   }
   h->have_jac = want_jac || h->stream_jac;   // streamed: they are re-formed by the gradient pass, never stored
   if (stream_contract) return QOC_OK;        // (the segment products exist already)
@@ -1205,6 +1230,7 @@ static int check_status(qoc_handle* h) {
   if (st != 0) {
     h->mail_valid = false;
     cudaMemset(h->dstatus, 0, 4);
+    if (st == 9) { h->err = "a control amplitude exceeds the bound given to qoc_set_control_bounds"; return QOC_ERR_INVALID; }
     h->err = "zero pivot while inverting the Pade denominator";
     return QOC_ERR_SINGULAR;
   }

@@ -330,6 +330,16 @@ __global__ void g_umax_kernel(const double* u, int nc, long long n, double* out)
   }
 }
 
+__global__ void g_set2_kernel(double* p, double a, double b) { p[0] = a; p[1] = b; }
+
+// |u[k][j]| <= bound[j] for every slice (the promise behind qoc_set_control_bounds): status 9 otherwise
+__global__ void g_ubound_check_kernel(const double* u, int nc, long long n, const double* bound, int* status) {
+  bool bad = false;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+    for (int j = 0; j < nc && j < 8; j++) bad |= !(fabs(u[k * nc + j]) <= bound[j]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(status, 9);
+}
+
 // ---- blocked Gauss-Jordan inverse with partial (row) pivoting -------------------------------------------------------------
 // Replaces round 1's g_inverse_kernel (whole matrix eliminated in L2, d steps of d^2 work behind four barriers each: 23 % of
 // the step at d = 64, 74 % at d = 256).  The matrix is processed in column panels K of nb <= 32 columns:

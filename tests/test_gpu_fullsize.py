@@ -152,3 +152,42 @@ def test_streamed_jacobians_time_sharded_in_library(monkeypatch):
     J, g = sh.evaluate(cfg["u"])
     assert abs(J - J0) <= 1e-10 and np.abs(g - g0).max() <= 1e-8 * np.abs(g0).max()
     sh.close()
+
+
+# ---- control bounds: the general path without its one synchronisation, CUDA-graph capture --------------------------------
+def test_control_bounds_make_the_general_path_asynchronous_and_capturable():
+    import ctypes as C
+    import torch
+    from qoc_b200 import _lib
+    from qoc_b200.grape import _u_arr
+    lib = _lib.load()
+    cfg = o.config_synthetic(32, 300)
+    J0, g0, cache = gpu_eval(cfg, 0)
+    dp = C.POINTER(C.c_double)
+    ub = np.array([0.5, 0.5])    # config_synthetic draws u ~ U(-0.5, 0.5)
+    assert lib.qoc_set_control_bounds(cache.handle, ub.ctypes.data_as(dp)) == 0
+    J1, g1 = q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cost_of(cfg)[1], dUkdp_order=0)
+    assert abs(J1 - J0) <= 1e-13 and np.abs(g1 - g0).max() <= 1e-12 * np.abs(g0).max()
+    # device-resident evaluation captured in a CUDA graph and replayed on new inputs
+    dev = torch.device("cuda", 0)
+    d_u = torch.from_numpy(_u_arr(cfg["u"], cache)).to(dev)
+    d_J = torch.zeros(1, dtype=torch.float64, device=dev)
+    d_g = torch.zeros(d_u.shape, dtype=torch.float64, device=dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        rc = lib.qoc_eval_device(cache.handle, C.c_void_p(d_u.data_ptr()), C.c_void_p(d_J.data_ptr()), C.c_void_p(d_g.data_ptr()),
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    u2 = 0.9 * cfg["u"]
+    d_u.copy_(torch.from_numpy(_u_arr(u2, cache)))
+    graph.replay()
+    torch.cuda.synchronize()
+    c2 = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=0, store_costates=False)
+    J2, g2 = q.evaluate(c2, cfg["A0"], cfg["A"], u2, cfg["x0"], cost_of(cfg)[1], dUkdp_order=0)
+    assert abs(float(d_J.cpu()[0]) - J2) <= 1e-12
+    assert np.abs(d_g.cpu().numpy().T - g2).max() <= 1e-12 * np.abs(g2).max()
+    c2.close()
+    # a broken promise is reported, not silently under-scaled
+    with pytest.raises(q.QOCError, match="exceeds the bound"):
+        q.evaluate(cache, cfg["A0"], cfg["A"], 1.5 * cfg["u"], cfg["x0"], cost_of(cfg)[1], dUkdp_order=0)
+    cache.close()
