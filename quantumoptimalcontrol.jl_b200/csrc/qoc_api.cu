@@ -1231,6 +1231,7 @@ static int check_status(qoc_handle* h) {
     h->mail_valid = false;
     cudaMemset(h->dstatus, 0, 4);
     if (st == 9) { h->err = "a control amplitude exceeds the bound given to qoc_set_control_bounds"; return QOC_ERR_INVALID; }
+    if (st == 10) { h->err = "time-sharded evaluation: a peer rank never published its propagator (timeout)"; return QOC_ERR_CUDA; }
     h->err = "zero pivot while inverting the Pade denominator";
     return QOC_ERR_SINGULAR;
   }
@@ -1742,7 +1743,13 @@ struct qoc_sharded {
   std::vector<cudaEvent_t> ev_pub, ev_t0, ev_t1;
   std::vector<double*> dS_loc, dS_all, du, dJ, dg;
   std::vector<double**> d_dst;      // per rank: device array of n pointers (slot p of every rank's S_all)
+  std::vector<unsigned*> d_flags, d_done;   // per rank: n arrival flags (written by the peers), n block counters of its publish kernel
+  std::vector<unsigned**> d_dstflag;        // per rank: device array of n pointers (flag p of every rank)
+  unsigned epoch = 0;
   bool peer = true;                 // every pair of distinct devices has a peer mapping
+  bool flags = false;               // exchange by peer stores + flags (every rank on its own device, all pairs mapped); else events:
+                                    // ranks that share a device must not park a spinning kernel in front of each other's
+                                    // cooperative launches
   float last_ms = 0.f;
   std::string err;
   // one host thread per rank (persistent): job hand-over and the barrier between the two halves of an evaluation
@@ -1760,10 +1767,40 @@ struct qoc_sharded {
 
 static thread_local std::string g_sharded_error;
 
-__global__ void shard_publish_kernel(const double* S, int n2, double* const* dst) {
+// Fused exchange: rank p stores its S_p into slot p of EVERY rank's S_all buffer through the NVLink peer mappings and then
+// raises its flag there (release at system scope); nothing on the host takes part.  grid = (blocks, ranks); the last block of
+// a target column to finish publishes the flag.
+__global__ void shard_publish_kernel(const double* S, int n2, double* const* dst, unsigned* const* dstflag, unsigned* done,
+                                     unsigned epoch) {
   double2* o = reinterpret_cast<double2*>(dst[blockIdx.y]);
   const double2* s = reinterpret_cast<const double2*>(S);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) o[i] = s[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&done[blockIdx.y], 1u) == gridDim.x - 1) {
+      done[blockIdx.y] = 0u;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dstflag[blockIdx.y]), "r"(epoch) : "memory");
+    }
+  }
+}
+// flags only (a rank whose phase 1 failed still releases its peers)
+__global__ void shard_flag_kernel(unsigned* const* dstflag, int nranks, unsigned epoch) {
+  if (threadIdx.x < nranks) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dstflag[threadIdx.x]), "r"(epoch) : "memory");
+}
+// phase 2 of a rank starts behind this kernel: one lane per peer spins (acquire at system scope) until that peer's flag
+// has reached this evaluation's epoch.  Bounded: ~4 s without progress sets status 10 instead of hanging the device.
+__global__ void shard_wait_kernel(const unsigned* flags, int nranks, unsigned epoch, int* status) {
+  if (threadIdx.x >= nranks) return;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    if (clock64() - t0 > 8000000000ll) { atomicExch(status, 10); break; }
+    __nanosleep(200);
+  }
 }
 
 extern "C" const char* qoc_sharded_last_error(const qoc_sharded* s) { return s ? s->err.c_str() : g_sharded_error.c_str(); }
@@ -1778,16 +1815,21 @@ extern "C" int qoc_sharded_destroy(qoc_sharded* s) {
     for (auto& t : s->workers) t.join();
   }
   for (int p = 0; p < s->n; p++) {
-    if (p < (int)s->dev.size()) cudaSetDevice(s->dev[p]);
+    if (!(p < (int)s->h.size() && s->h[p])) continue;   // nothing was created for this rank (its device may not even exist)
+    cudaSetDevice(s->dev[p]);
     if (p < (int)s->dS_loc.size() && s->dS_loc[p]) cudaFree(s->dS_loc[p]);
     if (p < (int)s->dS_all.size() && s->dS_all[p]) cudaFree(s->dS_all[p]);
     if (p < (int)s->du.size() && s->du[p]) cudaFree(s->du[p]);
     if (p < (int)s->dJ.size() && s->dJ[p]) cudaFree(s->dJ[p]);
     if (p < (int)s->dg.size() && s->dg[p]) cudaFree(s->dg[p]);
     if (p < (int)s->d_dst.size() && s->d_dst[p]) cudaFree(s->d_dst[p]);
+    if (p < (int)s->d_flags.size() && s->d_flags[p]) cudaFree(s->d_flags[p]);
+    if (p < (int)s->d_done.size() && s->d_done[p]) cudaFree(s->d_done[p]);
+    if (p < (int)s->d_dstflag.size() && s->d_dstflag[p]) cudaFree(s->d_dstflag[p]);
     if (p < (int)s->ev_pub.size()) { cudaEventDestroy(s->ev_pub[p]); cudaEventDestroy(s->ev_t0[p]); cudaEventDestroy(s->ev_t1[p]); }
     if (p < (int)s->h.size() && s->h[p]) qoc_destroy(s->h[p]);
   }
+  cudaGetLastError();   // leave no stale error behind for an unrelated later call to pick up
   delete s;
   return QOC_OK;
 }
@@ -1820,6 +1862,7 @@ extern "C" int qoc_create_sharded(const qoc_problem* prob, const double* A0, con
   s->h.assign(n_ranks, nullptr);
   s->dS_loc.assign(n_ranks, nullptr); s->dS_all.assign(n_ranks, nullptr); s->du.assign(n_ranks, nullptr);
   s->dJ.assign(n_ranks, nullptr); s->dg.assign(n_ranks, nullptr); s->d_dst.assign(n_ranks, nullptr);
+  s->d_flags.assign(n_ranks, nullptr); s->d_done.assign(n_ranks, nullptr); s->d_dstflag.assign(n_ranks, nullptr);
   auto fail = [&](int rc, const std::string& msg) { g_sharded_error = msg; qoc_sharded_destroy(s); return rc; };
   for (int p = 0; p < n_ranks; p++) {
     s->dev[p] = devices ? devices[p] : p;
@@ -1840,6 +1883,13 @@ extern "C" int qoc_create_sharded(const qoc_problem* prob, const double* A0, con
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) s->peer = false;
       cudaGetLastError();
     }
+  {
+    bool distinct = true;
+    for (int p = 0; p < n_ranks; p++)
+      for (int q = 0; q < p; q++) distinct = distinct && s->dev[p] != s->dev[q];
+    const char* nf = getenv("QOC_SHARD_NO_FLAGS");
+    s->flags = s->peer && distinct && shard_kind == QOC_SHARD_TIME && !(nf && nf[0] == '1');
+  }
   const size_t d2 = (size_t)2 * prob->d * prob->d;   // doubles of one c128 d x d matrix
   for (int p = 0; p < n_ranks; p++) {
     qoc_problem pp = *prob;
@@ -1853,7 +1903,10 @@ extern "C" int qoc_create_sharded(const qoc_problem* prob, const double* A0, con
               cudaMalloc(&s->dJ[p], (size_t)pp.batch * 8) == cudaSuccess;
     if (shard_kind == QOC_SHARD_TIME)
       ok = ok && cudaMalloc(&s->dS_loc[p], d2 * 8) == cudaSuccess && cudaMalloc(&s->dS_all[p], d2 * 8 * n_ranks) == cudaSuccess &&
-           cudaMalloc(&s->d_dst[p], sizeof(double*) * n_ranks) == cudaSuccess;
+           cudaMalloc(&s->d_dst[p], sizeof(double*) * n_ranks) == cudaSuccess &&
+           cudaMalloc(&s->d_flags[p], 4 * n_ranks) == cudaSuccess && cudaMemset(s->d_flags[p], 0, 4 * n_ranks) == cudaSuccess &&
+           cudaMalloc(&s->d_done[p], 4 * n_ranks) == cudaSuccess && cudaMemset(s->d_done[p], 0, 4 * n_ranks) == cudaSuccess &&
+           cudaMalloc(&s->d_dstflag[p], sizeof(unsigned*) * n_ranks) == cudaSuccess;
     if (!ok) return fail(QOC_ERR_CUDA, "device allocation failed");
   }
   s->ev_pub.resize(n_ranks); s->ev_t0.resize(n_ranks); s->ev_t1.resize(n_ranks);
@@ -1865,7 +1918,10 @@ extern "C" int qoc_create_sharded(const qoc_problem* prob, const double* A0, con
     if (shard_kind == QOC_SHARD_TIME) {
       std::vector<double*> dst(n_ranks);
       for (int q = 0; q < n_ranks; q++) dst[q] = s->dS_all[q] + (size_t)p * d2;
-      if (cudaMemcpy(s->d_dst[p], dst.data(), sizeof(double*) * n_ranks, cudaMemcpyHostToDevice) != cudaSuccess)
+      std::vector<unsigned*> df(n_ranks);
+      for (int q = 0; q < n_ranks; q++) df[q] = s->d_flags[q] + p;
+      if (cudaMemcpy(s->d_dst[p], dst.data(), sizeof(double*) * n_ranks, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(s->d_dstflag[p], df.data(), sizeof(unsigned*) * n_ranks, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(QOC_ERR_CUDA, "upload of the peer table failed");
     }
   }
@@ -1905,13 +1961,14 @@ static int sharded_rank_A(qoc_sharded* s, int p, const double* u) {
   if (s->peer) {
     int bx = (int)((d2 / 2 + 255) / 256);
     if (bx > 16) bx = 16;
-    shard_publish_kernel<<<dim3(bx, s->n), 256, 0, h->stream>>>(s->dS_loc[p], (int)(d2 / 2), s->d_dst[p]);
+    shard_publish_kernel<<<dim3(bx, s->n), 256, 0, h->stream>>>(s->dS_loc[p], (int)(d2 / 2), s->d_dst[p], s->d_dstflag[p], s->d_done[p],
+                                                              s->epoch);
     QOC_CUDA(h, cudaGetLastError());
   } else {
     for (int q = 0; q < s->n; q++)
       QOC_CUDA(h, cudaMemcpyPeerAsync(s->dS_all[q] + (size_t)p * d2, s->dev[q], s->dS_loc[p], s->dev[p], d2 * 8, h->stream));
   }
-  QOC_CUDA(h, cudaEventRecord(s->ev_pub[p], h->stream));
+  if (!s->flags) QOC_CUDA(h, cudaEventRecord(s->ev_pub[p], h->stream));
   return QOC_OK;
 }
 
@@ -1927,6 +1984,10 @@ static int sharded_rank_B(qoc_sharded* s, int p, double* J_out, double* dJdu_out
     if (dJdu_out) QOC_CUDA(h, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * per, s->dg[p], n * per * 8, cudaMemcpyDeviceToHost, h->stream));
   } else {
     const size_t n = (size_t)(s->hi[p] - s->lo[p]) * gp.nc;
+    if (s->flags) {   // behind a kernel that spins on the peers' flags: no event, no host rendezvous
+      shard_wait_kernel<<<1, 32, 0, h->stream>>>(s->d_flags[p], s->n, s->epoch, h->dstatus);
+      QOC_CUDA(h, cudaGetLastError());
+    } else
     for (int q = 0; q < s->n; q++)
       if (q != p) QOC_CUDA(h, cudaStreamWaitEvent(h->stream, s->ev_pub[q], 0));
     if ((rc = qoc_shard_phase2_device(h, s->dS_all[p], s->n, p, s->dJ[p], s->dg[p], h->stream)) != QOC_OK) return rc;
@@ -1951,14 +2012,19 @@ static void sharded_worker(qoc_sharded* s, int p) {
       seen = s->gen;
     }
     int rc = sharded_rank_A(s, p, s->job_u);
-    {   // host barrier: every ev_pub of this evaluation is recorded before anybody waits on one
+    if (rc != QOC_OK && s->flags) {   // release the peers that will spin on this rank's flag
+      cudaSetDevice(s->dev[p]);
+      shard_flag_kernel<<<1, 32, 0, s->h[p]->stream>>>(s->d_dstflag[p], s->n, s->epoch);
+    }
+    bool any_bad = rc != QOC_OK;
+    if (rc != QOC_OK) { std::lock_guard<std::mutex> lk(s->mu); s->rc_rank[p] = rc; }
+    if (!(s->flags || s->kind == QOC_SHARD_BATCH)) {
+      // event path: host barrier, every ev_pub of this evaluation is recorded before anybody waits on one
       std::unique_lock<std::mutex> lk(s->mu);
-      if (rc != QOC_OK) s->rc_rank[p] = rc;
       if (++s->arrived == s->n) { s->arrived_gen = seen; s->cv.notify_all(); }
       else s->cv.wait(lk, [&] { return s->arrived_gen == seen; });
+      for (int q = 0; q < s->n; q++) any_bad |= s->rc_rank[q] != QOC_OK;
     }
-    bool any_bad = false;
-    for (int q = 0; q < s->n; q++) any_bad |= s->rc_rank[q] != QOC_OK;
     if (!any_bad) {
       rc = sharded_rank_B(s, p, s->job_J, s->job_g);
       if (rc != QOC_OK) { std::lock_guard<std::mutex> lk(s->mu); s->rc_rank[p] = rc; }
@@ -1975,6 +2041,7 @@ extern "C" int qoc_sharded_eval(qoc_sharded* s, const double* u, double* J_out, 
   const qoc_problem& gp = s->prob;
   const int P = s->n;
   s->rc_rank.assign(P, QOC_OK);
+  s->epoch += 1;
   if (s->threads) {
     if (s->workers.empty())
       for (int p = 0; p < P; p++) s->workers.emplace_back(sharded_worker, s, p);
@@ -1989,7 +2056,10 @@ extern "C" int qoc_sharded_eval(qoc_sharded* s, const double* u, double* J_out, 
     s->cv.wait(lk, [&] { return s->done == P; });
   } else {
     bool bad = false;
-    for (int p = 0; p < P; p++) { s->rc_rank[p] = sharded_rank_A(s, p, u); bad |= s->rc_rank[p] != QOC_OK; }
+    for (int p = 0; p < P; p++) {
+      s->rc_rank[p] = sharded_rank_A(s, p, u);
+      bad |= s->rc_rank[p] != QOC_OK;
+    }
     for (int p = 0; p < P && !bad; p++) s->rc_rank[p] = sharded_rank_B(s, p, J_out, dJdu_out);
   }
   for (int p = 0; p < P; p++)
