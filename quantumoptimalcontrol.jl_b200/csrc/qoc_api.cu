@@ -15,6 +15,7 @@
 #include "qoc_k1s.cuh"
 #include "qoc_k23.cuh"
 #include "qoc_sweep.cuh"
+#include "qoc_k3s.cuh"
 #include "qoc_gpath.cuh"
 #include "qoc_basis.cuh"
 
@@ -78,6 +79,8 @@ struct qoc_handle {
   bool k1_skewh = false;      // A0 and every A_j skew-Hermitian (bitwise): k1s_kernel forms A E + E A, A2 M2 + M2 A2, X E as P + P^dagger
   bool k1s_ok = false;        // d <= 9, nc <= 4: the small-dimension kernel (nine lanes per slice, three slices per warp)
   int k1s_wpb = 0;            // its warps per CTA (what fits shared memory)
+  bool k3s_ok = false;        // d <= 9, m <= 4, nc <= 4: the small-dimension sweeps (nine lanes per segment)
+  int k3s_grid = 0;
   bool k1_sym = false;        // ... with symmetric H0, H_j: Pade denominator inverted through the real SPD matrix N N^dagger
   bool k1_realh = false;      // K1 real-Hamiltonian fast path (Re A0 = Re A_j = 0, Frechet mode, [13/13] instantiation)
   bool k1_low = true;         // K1 instantiation with the low-degree Pade forms (false when ||A0||_1 alone is far above theta7)           // second-generation general-path sweeps (no running penalty)
@@ -440,6 +443,16 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
         if (occ3 < 1) occ3 = 1;
         h->k3n_grid = h->nseg < h->nsm * occ3 ? h->nseg : h->nsm * occ3;
         h->new_k3 = true;
+        {
+          const char* off3 = getenv("QOC_NO_K3S");
+          h->k3s_ok = p.d <= K3S_D && p.m <= K3S_M && p.nc <= 4 && C::S == 12 && !(off3 && off3[0] == '1');
+          if (h->k3s_ok) {
+            QOC_CUDA(h, cudaFuncSetAttribute(k3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3s_smem_bytes()));
+            int occs = 1;
+            QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, k3s_kernel, K3S_WPB * 32, k3s_smem_bytes()));
+            h->k3s_grid = h->nsm * (occs < 1 ? 1 : occs);
+          }
+        }
       }
       // K2G: G groups per pulse, chosen to balance the spp/G tile products against the 2 G + 2 spp/G mat-vec steps;
       // every CTA of the launch must be resident at once (per-pulse barrier)
@@ -1049,6 +1062,12 @@ static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d
   q.store_states = store_states ? 1 : 0;
   if (d_dJdu) q.dJdu = d_dJdu;
   const int grid = h->nseg < h->nsm * 2 ? h->nseg : h->nsm * 2;
+  if (h->new_k3 && mode == 0 && h->k3s_ok) {
+    // small-dimension form: nine lanes per segment, no CTA barriers (qoc_k3s.cuh)
+    const int per_cta = K3S_WPB * 3;
+    const int ctas = (h->nseg + per_cta - 1) / per_cta;
+    k3s_kernel<<<ctas < h->k3s_grid ? ctas : h->k3s_grid, K3S_WPB * 32, k3s_smem_bytes(), st>>>(q, h->S);
+  } else
   if (h->new_k3 && mode == 0)
     with_cfg(h->cfg, [&](auto c) {
       typedef decltype(c) C;
