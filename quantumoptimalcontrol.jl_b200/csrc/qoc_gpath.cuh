@@ -137,6 +137,11 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
 #pragma unroll
     for (int b = 0; b < WN; b++) colv[b] = tn * TN + (wn * WN + b) * 8 < d;
     const bool work = rowv[0] && colv[0];
+    bool fullw = true;   // every 8 x 8 tile of this warp lies inside the matrix
+#pragma unroll
+    for (int a = 0; a < WM; a++) fullw = fullw && rowv[a];
+#pragma unroll
+    for (int b = 0; b < WN; b++) fullw = fullw && colv[b];
     for (int it = 0; it < total; it++) {
       g_cp_async_wait<NST - 2>();
       __syncthreads();
@@ -150,6 +155,30 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
         const double* aim = are + G::A_PLANE;
         const double* bre = st + 2 * G::A_PLANE + q4 * BS + wn * WN * 8 + gq;
         const double* bim = bre + G::B_PLANE;
+        if (fullw && ksmax == KC / 4) {
+          // interior warp tile, whole chunk: straight-line code, no predicate between the DMMAs (the predicated form below
+          // spends ~9 instructions per DMMA on warp-uniform branches, WARPSYNC and NOP padding: ncu, d = 256)
+#pragma unroll
+          for (int ks = 0; ks < KC / 4; ks++) {
+            double ar[WM], ai[WM], as[WM], br[WN], bi[WN], bs[WN];
+#pragma unroll
+            for (int a = 0; a < WM; a++) { ar[a] = are[a * 8 * AS + ks * 4]; ai[a] = aim[a * 8 * AS + ks * 4]; }
+#pragma unroll
+            for (int b = 0; b < WN; b++) { br[b] = bre[ks * 4 * BS + b * 8]; bi[b] = bim[ks * 4 * BS + b * 8]; }
+#pragma unroll
+            for (int a = 0; a < WM; a++) as[a] = ar[a] + ai[a];
+#pragma unroll
+            for (int b = 0; b < WN; b++) bs[b] = br[b] + bi[b];
+#pragma unroll
+            for (int b = 0; b < WN; b++)
+#pragma unroll
+              for (int a = 0; a < WM; a++) {
+                dmma(T1[a][b][0], T1[a][b][1], ar[a], br[b]);
+                dmma(T2[a][b][0], T2[a][b][1], ai[a], bi[b]);
+                dmma(T3[a][b][0], T3[a][b][1], as[a], bs[b]);
+              }
+          }
+        } else {
 #pragma unroll
         for (int ks = 0; ks < KC / 4; ks++) {
           if (ks < ksmax) {
@@ -172,6 +201,7 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
               }
             }
           }
+        }
         }
       }
       cstage = (cstage + 1 == NST) ? 0 : cstage + 1;

@@ -339,6 +339,24 @@ def test_zz_batch_4096_properties():
         Jo, go, _ = o.evaluate(cfg, order=0, u=ub[b])
         assert_parity(Jb[b], gb[b], Jo, go)
     assert cache.launch_count() >= 3
+    cache.close()
+
+
+@pytest.mark.parametrize("order", [0, 3])
+def test_zz_batch_4096_every_pulse_vs_c_restatement(order):
+    """C4 in full: every one of the 4096 pulses (J and all 200 gradient components each) against the C restatement of the
+    reference (oracle/qoc_ref.c, which agrees with the numpy oracle to 1e-15: tests/test_oracle.py), both gradient modes."""
+    cfg = o.config_zz_batch(4096)
+    ub = cfg["u_batch"]
+    Jb, gb, cache = gpu_eval(cfg, order, u=ub, batch=4096)
+    worst_J = worst_g = 0.0
+    for b in range(4096):
+        r = qoc_ref.ref_eval(cfg, order=order, nthreads=1, u=ub[b])
+        worst_J = max(worst_J, abs(Jb[b] - r["J"]) / max(1.0, abs(r["J"])))
+        worst_g = max(worst_g, np.abs(gb[b] - r["dJdu"]).max() / np.abs(r["dJdu"]).max())
+    print(f"order {order}: worst |dJ| = {worst_J:.2e}, worst rel |dg| = {worst_g:.2e} over 4096 pulses")
+    assert worst_J <= TOL_J and worst_g <= TOL_G
+    cache.close()
 
 
 # ---- running state penalty (src/penalty_fcns.jl:1-11; affine costate recurrence, gradient_computations.jl:47-57) -------
