@@ -72,6 +72,10 @@ struct qoc_handle {
   // (d = 256, Nt = 1e5, nc = 2: 106 GB + 213 GB), dL holds ONE chunk; the gradient pass re-runs K1 chunk by chunk after the
   // sweeps and contracts each chunk's Jacobians with the stored x_k, lambda_{k+1} at once.  Costs one extra expm per slice
   // ((pi + s + 4/3) M of (pi + s + 4/3 + nc G) M).  QOC_STREAM_JAC=1 forces it (tests), =0 forbids it.
+  bool pen_any = false;           // a running state penalty is configured
+  std::vector<unsigned char> penrow_host;
+  bool pen_hi = false;            // a penalised row >= 64: only the two-level sweeps (byte mask) can carry it
+  unsigned char* dpenrow = nullptr;   // [d] 1 = penalised row (general path, two-level sweeps)
   bool have_ubound = false;       // qoc_set_control_bounds: |u_jk| <= ubound[j] promised by the caller
   double ubound[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool stream_jac = false;
@@ -247,6 +251,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->dpiv) cudaFree(h->dpiv);
   if (h->dk1s_scr) cudaFree(h->dk1s_scr);
   if (h->dubound) cudaFree(h->dubound);
+  if (h->dpenrow) cudaFree(h->dpenrow);
   if (h->dpen_rows) cudaFree(h->dpen_rows);
   if (h->dpen_cols) cudaFree(h->dpen_cols);
   for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
@@ -310,8 +315,9 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     cfg = 5;
     // dynamic shared memory of the general-path sweep kernels (gs_scan / gs_seg: two interleaved states; gs_contract: x_k and
     // lambda_{k+1}; g_sweep: three planar states; shard_boundary: two column-major states): rejected here, not at launch
-    const size_t need = (size_t)6 * (p.d + 8) * p.m * 8 > (size_t)(2 * p.d + 8) * 2 * p.m * 8 ? (size_t)6 * (p.d + 8) * p.m * 8
-                                                                                          : (size_t)(2 * p.d + 8) * 2 * p.m * 8;
+    // (three states with the running penalty: x_k rides along with the costate)
+    const size_t need = (size_t)6 * (p.d + 8) * p.m * 8 > (size_t)(3 * p.d + 24) * 2 * p.m * 8 ? (size_t)6 * (p.d + 8) * p.m * 8
+                                                                                           : (size_t)(3 * p.d + 24) * 2 * p.m * 8;
     if (need > (size_t)dp.sharedMemPerBlockOptin) {
       g_create_error = "d x m state working set of the general-path sweeps exceeds shared memory";
       return QOC_ERR_UNSUPPORTED;
@@ -323,10 +329,13 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   h->gpath = use_gpath;
   for (int i = 0; i < p.n_pen_rows; i++) {
     if (p.pen_rows[i] < 0 || p.pen_rows[i] >= p.d) { g_create_error = "penalty row index out of range"; delete h; return QOC_ERR_INVALID; }
-    if (use_gpath && p.pen_rows[i] >= 64) { g_create_error = "penalty rows >= 64 not supported on the general path yet"; delete h; return QOC_ERR_UNSUPPORTED; }
+    if (p.pen_rows[i] >= 64) h->pen_hi = true;   // beyond the 64-bit row mask of the serial general-path sweep (checked below)
     if (p.pen_rows[i] < 32) h->row_mask |= 1u << p.pen_rows[i];
-    h->row_mask64 |= 1ull << p.pen_rows[i];
+    if (p.pen_rows[i] < 64) h->row_mask64 |= 1ull << p.pen_rows[i];
+    h->penrow_host.resize(p.d, 0);
+    h->penrow_host[p.pen_rows[i]] = 1;
   }
+  h->pen_any = p.n_pen_rows > 0 && p.n_pen_cols > 0 && p.mu != 0.0;
   for (int i = 0; i < p.n_pen_cols; i++) {
     if (p.pen_cols[i] < 0 || p.pen_cols[i] >= p.m) { g_create_error = "penalty column index out of range"; delete h; return QOC_ERR_INVALID; }
     h->col_mask |= 1u << p.pen_cols[i];
@@ -346,8 +355,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     h->spp = 1; h->nseg = p.batch; h->seg_cap = p.nt; h->k1_grid = 0; h->k3_threads = 256;
     {
       const char* old_sw = getenv("QOC_OLD_SWEEPS");
-      const bool pen = h->row_mask64 != 0ull && h->col_mask != 0u && p.mu != 0.0;
-      if (!pen && !(old_sw && old_sw[0] == '1') && p.nt >= 4) {
+      if (!(old_sw && old_sw[0] == '1') && p.nt >= 4) {   // (with or without the running penalty)
         // two-level sweeps: L slices per segment ~ sqrt(nt) balances the boundary walk (2 spp steps) against the
         // per-segment sweeps (2 L steps)
         int L = (int)ceil(sqrt((double)p.nt));
@@ -355,6 +363,11 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
         const int spp = (p.nt + L - 1) / L;
         if ((long long)spp * p.batch <= 65535) { h->gs2 = true; h->gL = L; h->spp = spp; h->nseg = spp * p.batch; h->seg_cap = L; }
       }
+    }
+    if (h->pen_hi && !h->gs2) {
+      g_create_error = "penalty rows >= 64 need the two-level sweeps of the general path (nt >= 4)";
+      delete h;
+      return QOC_ERR_UNSUPPORTED;
     }
     h->k1_smem = h->k2_smem = h->k3_smem = 0;
     h->gnw = 25 + p.nc;
@@ -563,6 +576,11 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     CR(cudaMalloc(&h->gW, (size_t)h->gnw * h->gchunk * slotB));
     CR(cudaMalloc(&h->dumax, 8 * 8));
     CR(cudaMalloc(&h->dpiv, (size_t)h->gchunk * p.d * 4));
+    if (h->pen_any) {
+      h->penrow_host.resize(p.d, 0);
+      CR(cudaMalloc(&h->dpenrow, p.d));
+      CR(cudaMemcpy(h->dpenrow, h->penrow_host.data(), p.d, cudaMemcpyHostToDevice));
+    }
   }
   if (h->new_k2) {
     CR(cudaMalloc(&h->dPg, (size_t)p.batch * h->G * slotB));
@@ -761,16 +779,42 @@ static int gpath_sweep2(qoc_handle* h, int mode, bool skip_bwd, bool want_grad, 
   g.U = h->dU; g.L_ = h->dL; g.Q = h->dQ; g.x0 = h->dx0; g.x_start_ext = d_x_start; g.T = h->dT; g.lam_final = d_lam_final;
   g.xs_start = h->dxs; g.lam_end = h->dle; g.X = h->dX; g.LAM = h->dLAM; g.x_final = h->dxf; g.lam_start = h->dlam0;
   g.J = d_J ? d_J : h->dJ; g.dJdu = d_dJdu ? d_dJdu : h->dg;
-  const size_t st_smem = (size_t)2 * ((p.d + 7) / 8 * 8) * 2 * p.m * 8;
+  const bool pen = h->pen_any;
+  const size_t st_smem = (size_t)(pen ? 3 : 2) * ((p.d + 7) / 8 * 8) * 2 * p.m * 8;
   if (st_smem > 40 * 1024) {   // qoc_create checked it against sharedMemPerBlockOptin
     QOC_CUDA(h, cudaFuncSetAttribute(gs_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
     QOC_CUDA(h, cudaFuncSetAttribute(gs_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
   }
+  const int grid = h->nseg < h->nsm * 4 ? h->nseg : h->nsm * 4;
+  if (pen) {
+    // running penalty: the costate recurrence is affine (src/gradient_computations.jl:55-57), a segment is (Q_seg, c_seg):
+    //   boundary walk forward -> per-segment forward states + c_seg + sum L(x_k) -> cost + affine boundary walk -> per-segment
+    //   affine backward sweeps -> contraction.  Everything but the two boundary walks is parallel over the segments.
+    if (mode == 4) { h->err = "time sharding does not carry the running state penalty"; return QOC_ERR_UNSUPPORTED; }
+    g.pen_row = h->dpenrow; g.col_mask = h->col_mask; g.mu = p.mu; g.cs = h->dcs; g.Jpen = h->dJpen;
+    if (mode != 2) {
+      QOC_CUDA(h, cudaMemsetAsync(h->dJpen, 0, (size_t)p.batch * 8, st));
+      g.mode = 1;
+      gs_scan_kernel<<<p.batch, GS_NW * 32, st_smem, st>>>(g);
+      g.pen_prepass = 1;
+      gs_seg_kernel<<<grid, GS_NW * 32, st_smem, st>>>(g, h->nseg);
+      g.pen_prepass = 0;
+      h->launches += 2;
+    }
+    g.mode = (mode == 2) ? 2 : 3;
+    gs_scan_kernel<<<p.batch, GS_NW * 32, st_smem, st>>>(g);
+    h->launches++;
+    if (!(mode == 0 && skip_bwd) && mode != 1) {
+      gs_seg_kernel<<<grid, GS_NW * 32, st_smem, st>>>(g, h->nseg);
+      h->launches++;
+    }
+    g.mode = mode;
+  } else {
   gs_scan_kernel<<<p.batch, GS_NW * 32, st_smem, st>>>(g);
   h->launches++;
-  const int grid = h->nseg < h->nsm * 4 ? h->nseg : h->nsm * 4;
   gs_seg_kernel<<<grid, GS_NW * 32, st_smem, st>>>(g, h->nseg);
   h->launches++;
+  }
   if (want_grad && (mode == 2 || mode == 4 || (mode == 0 && !skip_bwd))) {
     const size_t c_smem = (size_t)(h->S + p.d) * 2 * p.m * 8;
     if (c_smem > 40 * 1024) QOC_CUDA(h, cudaFuncSetAttribute(gs_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
@@ -1087,7 +1131,7 @@ static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d
   return QOC_OK;
 }
 
-static bool has_penalty(const qoc_handle* h) { return h->row_mask != 0u && h->col_mask != 0u && h->prob.mu != 0.0; }
+static bool has_penalty(const qoc_handle* h) { return h->pen_any; }
 
 // ---- more than 8 state columns: column chunks sharing one K1 pass ---------------------------------------------------
 static void use_cols(qoc_handle* h, int c) {

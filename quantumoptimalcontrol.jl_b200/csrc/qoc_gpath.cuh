@@ -807,7 +807,38 @@ struct GS {
   double* dJdu;
   long long sl0;       // gs_contract_kernel: flat index of the first slice of this launch
   int L_chunked;       // ... and L_ holds the Jacobians of the slices [sl0, sl0 + gridDim.x) only (streamed Jacobians)
+  // running state penalty L(x) = mu sum |x[pen rows, pen cols]|^2 (src/penalty_fcns.jl:1-11): the costate recurrence becomes
+  // affine, lambda_k = U_k' lambda_{k+1} + dL_dx(x_k) (src/gradient_computations.jl:47-49, :55-57), so a segment is summarised
+  // by (Q_seg, c_seg): lambda_{k0} = Q_seg' lambda_{k1} + c_seg, c_seg = the recurrence run from a zero costate.
+  const unsigned char* pen_row;   // [d] 1 = penalised row (NULL: no penalty)
+  unsigned col_mask;
+  double mu;
+  double* cs;          // [b*spp + s] d x m c128 affine terms
+  double* Jpen;        // [batch] sum over the slices' states of |x[pen]|^2 (atomicAdd)
+  int pen_prepass;     // gs_seg_kernel: forward states + c_seg + the penalty sum, nothing else
 };
+
+// xs[r][c] += 2 mu x[r][c] on the penalised entries (interleaved shared layouts, W = 2 m doubles per row)
+__device__ __forceinline__ void gs_add_penalty(double* ys, const double* xs, const GS& g, int tid, int nth) {
+  const int W = 2 * g.m;
+  for (int e = tid; e < g.d * g.m; e += nth) {
+    const int r = e / g.m, c = e - r * g.m;
+    if (g.pen_row[r] && ((g.col_mask >> c) & 1u)) {
+      ys[r * W + 2 * c] = fma(2.0 * g.mu, xs[r * W + 2 * c], ys[r * W + 2 * c]);
+      ys[r * W + 2 * c + 1] = fma(2.0 * g.mu, xs[r * W + 2 * c + 1], ys[r * W + 2 * c + 1]);
+    }
+  }
+}
+// sum of |x[r][c]|^2 over the penalised entries, this thread's share
+__device__ __forceinline__ double gs_penalty_sum(const double* xs, const GS& g, int tid, int nth) {
+  const int W = 2 * g.m;
+  double s = 0.0;
+  for (int e = tid; e < g.d * g.m; e += nth) {
+    const int r = e / g.m, c = e - r * g.m;
+    if (g.pen_row[r] && ((g.col_mask >> c) & 1u)) s += xs[r * W + 2 * c] * xs[r * W + 2 * c] + xs[r * W + 2 * c + 1] * xs[r * W + 2 * c + 1];
+  }
+  return s;
+}
 
 // one CTA per pulse: boundary walk over the segment propagators
 __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
@@ -822,7 +853,13 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
   for (int e = tid; e < 2 * rows_pad * W; e += nth) b0[e] = 0.0;
   __syncthreads();
   double* cur = b0; double* nxt = b1;
-  const bool do_fwd = g.mode != 2, do_bwd = g.mode == 2 || g.mode == 4 || (g.mode == 0 && !g.skip_bwd);
+  // mode 3 (penalty): cost + affine boundary walk from the stored x_N (the forward walk ran as mode 1, the c_seg in between)
+  const bool pen = g.pen_row != nullptr;
+  const bool do_fwd = g.mode != 2 && g.mode != 3, do_bwd = g.mode == 2 || g.mode == 4 || ((g.mode == 0 || g.mode == 3) && !g.skip_bwd);
+  if (g.mode == 3 || (g.mode == 2 && pen)) {
+    gs_from_global(cur, g.X + ((size_t)b * (g.nt + 1) + g.nt) * 2 * dm, d, m, tid, nth);
+    __syncthreads();
+  }
   if (do_fwd) {
     gs_from_global(cur, g.x_start_ext ? g.x_start_ext + (size_t)b * 2 * dm : g.x0, d, m, tid, nth);
     __syncthreads();
@@ -836,17 +873,24 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
     gs_to_global(g.X + ((size_t)b * (g.nt + 1) + g.nt) * 2 * dm, cur, d, m, tid, nth);
   }
   if (g.mode == 1) return;
-  const bool builtin = do_fwd && g.cost != 2 && g.mode != 4;
+  const bool builtin = (do_fwd || g.mode == 3) && g.cost != 2 && g.mode != 4;
   if (tid < 16) ov[tid] = 0.0;
   __syncthreads();
   CostCoef cc;
+  cc.J = 0.0;
   if (builtin) {
     cost_overlaps_accumulate(g.T, d, m, [&](int r, int c) { return *reinterpret_cast<const double2*>(cur + r * W + 2 * c); },
                              ov, tid, nth, lane);
     __syncthreads();
     cost_from_overlaps(g.cost, g.n, m, ov, cc);
-    if (tid == 0 && g.J) g.J[b] = cc.J;
   }
+  if (pen && g.mode == 3) {   // J = Jfinal(x_N) + sum_k L(x_k), k = 0 .. N (examples/ipopt_callbacks_exp.jl:18)
+    double ps = gs_penalty_sum(cur, g, tid, nth);
+    for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+    if (lane == 0) atomicAdd(&ov[8], ps);
+    __syncthreads();
+    if (tid == 0 && g.J) g.J[b] = cc.J + g.mu * (g.Jpen[b] + ov[8]);
+  } else if (builtin && tid == 0 && g.J) g.J[b] = cc.J;
   if (!do_bwd) return;
   for (int c = 0; c < m; c++)
     for (int r = tid; r < d; r += nth) {
@@ -863,12 +907,19 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
       }
       *reinterpret_cast<double2*>(nxt + r * W + 2 * c) = l;
     }
-  { double* t = cur; cur = nxt; nxt = t; }
   __syncthreads();
+  if (pen) { gs_add_penalty(nxt, cur, g, tid, nth); __syncthreads(); }   // lambda_N += dL_dx(x_N)  (:47-49)
+  { double* t = cur; cur = nxt; nxt = t; }
   for (int s = g.spp - 1; s >= 0; s--) {
     gs_to_global(g.lam_end + ((size_t)b * g.spp + s) * 2 * dm, cur, d, m, tid, nth);
     gs_mv_any<true>(g.Q + ((size_t)b * g.spp + s) * g.slot, d, g.S, m, cur, nxt, warp, lane);
     __syncthreads();
+    if (pen) {   // + c_seg
+      const double2* cg = reinterpret_cast<const double2*>(g.cs + ((size_t)b * g.spp + s) * 2 * dm);
+      for (int c = 0; c < m; c++)
+        for (int r = tid; r < d; r += nth) { const double2 v = cg[r + (size_t)d * c]; nxt[r * W + 2 * c] += v.x; nxt[r * W + 2 * c + 1] += v.y; }
+      __syncthreads();
+    }
     double* t = cur; cur = nxt; nxt = t;
   }
   if (g.lam_start) gs_to_global(g.lam_start + (size_t)b * 2 * dm, cur, d, m, tid, nth);
@@ -881,19 +932,25 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_seg_kernel(GS g, int nseg_total
   const int rows_pad = (d + 7) / 8 * 8;
   double* b0 = reinterpret_cast<double*>(gsm);
   double* b1 = b0 + rows_pad * W;
+  double* b2 = b1 + rows_pad * W;   // penalty only: x_k next to the costate
+  __shared__ double psum;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nth = blockDim.x;
-  for (int e = tid; e < 2 * rows_pad * W; e += nth) b0[e] = 0.0;
+  const bool pen = g.pen_row != nullptr;
+  for (int e = tid; e < (pen ? 3 : 2) * rows_pad * W; e += nth) b0[e] = 0.0;
   __syncthreads();
-  const bool do_fwd = g.mode != 2, do_bwd = g.mode == 2 || g.mode == 4 || (g.mode == 0 && !g.skip_bwd);
+  const bool do_fwd = (g.mode != 2 && g.mode != 3) || g.pen_prepass;
+  const bool do_bwd = !g.pen_prepass && (g.mode == 2 || g.mode == 3 || g.mode == 4 || (g.mode == 0 && !g.skip_bwd));
   for (int seg = blockIdx.x; seg < nseg_total; seg += gridDim.x) {
     const int b = seg / g.spp, si = seg - b * g.spp;
     const int k0 = si * g.L, k1 = (k0 + g.L < g.nt) ? k0 + g.L : g.nt;
     double* cur = b0; double* nxt = b1;
     if (do_fwd) {
+      double ps = 0.0;
       gs_from_global(cur, g.xs_start + (size_t)seg * 2 * dm, d, m, tid, nth);
       __syncthreads();
       for (int k = k0; k < k1; k++) {
         gs_to_global(g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, cur, d, m, tid, nth);
+        if (g.pen_prepass) ps += gs_penalty_sum(cur, g, tid, nth);
         if (k + 1 < k1) {
           gs_mv_any<false>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
           __syncthreads();
@@ -901,14 +958,37 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_seg_kernel(GS g, int nseg_total
         }
       }
       __syncthreads();
+      if (g.pen_prepass) {
+        // sum_k L(x_k)/mu of this segment, and c_seg: the affine costate recurrence from a zero costate
+        if (tid == 0) psum = 0.0;
+        __syncthreads();
+        for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+        if (lane == 0) atomicAdd(&psum, ps);
+        __syncthreads();
+        if (tid == 0) atomicAdd(g.Jpen + b, psum);
+        for (int e = tid; e < rows_pad * W; e += nth) cur[e] = 0.0;
+        __syncthreads();
+        for (int k = k1 - 1; k >= k0; k--) {
+          gs_from_global(b2, g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, d, m, tid, nth);
+          gs_mv_any<true>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
+          __syncthreads();
+          gs_add_penalty(nxt, b2, g, tid, nth);
+          __syncthreads();
+          double* t = cur; cur = nxt; nxt = t;
+        }
+        gs_to_global(g.cs + (size_t)seg * 2 * dm, cur, d, m, tid, nth);
+        __syncthreads();
+      }
     }
     if (do_bwd) {
       gs_from_global(cur, g.lam_end + (size_t)seg * 2 * dm, d, m, tid, nth);
       __syncthreads();
       for (int k = k1 - 1; k >= k0; k--) {
         gs_to_global(g.LAM + ((size_t)b * (g.nt + 1) + k + 1) * 2 * dm, cur, d, m, tid, nth);
+        if (pen) gs_from_global(b2, g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, d, m, tid, nth);
         gs_mv_any<true>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
         __syncthreads();
+        if (pen) { gs_add_penalty(nxt, b2, g, tid, nth); __syncthreads(); }   // + dL_dx(x_k)  (:55-57)
         double* t = cur; cur = nxt; nxt = t;
       }
       if (k0 == 0) gs_to_global(g.LAM + ((size_t)b * (g.nt + 1)) * 2 * dm, cur, d, m, tid, nth);

@@ -108,3 +108,31 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "qoc_oracle" not in txt and "qoc_ref" not in txt, f
+
+
+def test_c_driver_compiles_and_links_against_the_header():
+    """tests/abi_driver.c (plain C99) builds against include/qoc_b200.h and links the in-tree library: the header is usable from
+    C as shipped.  (It runs on the GPU box: tests/test_gpu_abi_driver.py.)"""
+    _lib.load()
+    libdir = os.path.dirname(_lib.lib_path())
+    exe = "/tmp/qoc_abi_driver_linkcheck"
+    r = subprocess.run(["gcc", "-O1", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "abi_driver.c"), "-o", exe, "-L", libdir, "-lqoc_b200", "-lm",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_sharded_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less build container")
+    lib = _lib.load()
+    pr = _lib.Problem()
+    pr.d, pr.m, pr.nc, pr.nt, pr.batch, pr.order, pr.cost, pr.n, pr.device = 4, 1, 1, 8, 1, 0, 0, 1, 0
+    z = np.zeros(64)
+    dp = C.POINTER(C.c_double)
+    h = C.c_void_p()
+    rc = lib.qoc_create_sharded(C.byref(pr), z.ctypes.data_as(dp), z.ctypes.data_as(dp), z.ctypes.data_as(dp), z.ctypes.data_as(dp), 2, None, 1,
+                                C.byref(h))
+    assert rc == _lib.ERR_NO_DEVICE and h.value is None
+    assert b"CUDA" in lib.qoc_sharded_last_error(None)

@@ -191,3 +191,42 @@ def test_control_bounds_make_the_general_path_asynchronous_and_capturable():
     with pytest.raises(q.QOCError, match="exceeds the bound"):
         q.evaluate(cache, cfg["A0"], cfg["A"], 1.5 * cfg["u"], cfg["x0"], cost_of(cfg)[1], dUkdp_order=0)
     cache.close()
+
+
+# ---- running state penalty on the general path: two-level (parallel) sweeps, any row ------------------------------------------
+@pytest.mark.parametrize("d,nt,m,rows,cols,order", [(32, 300, 3, [1, 5, 31], [0, 2], 0), (40, 150, 2, [3, 39], [0, 1], 3),
+                                                     (80, 60, 2, [2, 64, 65, 79], [1], 0)])
+def test_state_penalty_general_path_vs_oracle(d, nt, m, rows, cols, order):
+    """src/penalty_fcns.jl:1-11 with src/gradient_computations.jl:47-49, :55-57 at d > 28: the costate recurrence is affine, a
+    segment is summarised by (Q_seg, c_seg); rows >= 64 included (round 1's serial sweep carried a 64-bit row mask)."""
+    cfg = o.config_synthetic(d, nt, nc=2, m=m, seed=d)
+    pen = (rows, cols, 0.41)
+    Jo, go, co = o.evaluate(cfg, order=order, penalty=pen)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"])
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=order)
+    J, g = q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cost[1], dUkdp_order=order, penalty=q.setup_state_penalty(*pen))
+    assert abs(J - Jo) <= TOL_J * max(1.0, abs(Jo))
+    assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+    assert np.abs(cache.lam - co["lam"]).max() < 1e-11
+    # the reference's split calls with host closures for cost and penalty (examples/ipopt_callbacks_exp.jl:16-18, :27)
+    Jf, dJf = o.setup_infidelity(cfg["T"], cfg["n"])
+    L, dL = q.setup_state_penalty(*pen)
+    c2 = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape)      # no built-in cost on this handle
+    q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], c2, penalty=(L, dL))
+    x = c2.x
+    assert abs(Jf(x[-1]) + sum(L(xk) for xk in x) - Jo) <= TOL_J * max(1.0, abs(Jo))
+    assert abs(c2.J - sum(L(xk) for xk in x)) < 1e-11                  # device-side running sum of the penalty alone
+    g2 = q.grape_sensitivity(cfg["A0"], cfg["A"], dJf, cfg["u"], cfg["x0"], c2, dUkdp_order=order, dL_dx=dL)
+    assert np.abs(g2 - go).max() <= TOL_G * np.abs(go).max()
+    cache.close(); c2.close()
+
+
+def test_state_penalty_small_case_forced_onto_the_general_path(golden_dir, monkeypatch):
+    monkeypatch.setenv("QOC_FORCE_GPATH", "1")
+    gd = np.load(os.path.join(golden_dir, "zz_penalty_order4.npz"))
+    cfg = o.config_zz()
+    pen = q.setup_state_penalty([6, 7, 8], [0, 1, 2, 3], 0.22)
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], (2, 100), dUkdp_order=4)
+    J, g = q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], q.setup_infidelity(cfg["T"], cfg["n"])[1], dUkdp_order=4, penalty=pen)
+    assert abs(J - float(gd["J"])) <= TOL_J and np.abs(g - gd["dJdu"]).max() <= TOL_G * np.abs(gd["dJdu"]).max()
+    cache.close()
