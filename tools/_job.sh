@@ -1,8 +1,12 @@
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/r02b_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02b_pytest.log
-for wl in synth64x2000 synth128x512 synth256x296 cavity20 cavity40; do
-  python tools/run_once.py $wl frechet 3 > gpurun_out/r02b_plain_$wl.log 2>&1 && \
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02b_launches_$wl.csv python tools/run_once.py $wl frechet 2 > gpurun_out/r02b_ncu_$wl.log 2>&1
-done
-( time python bench.py > gpurun_out/r02b_bench.json 2> gpurun_out/r02b_bench.err ) 2> gpurun_out/r02b_bench.time
-( time python bench.py --impl reference > gpurun_out/r02b_bench_ref.json 2> gpurun_out/r02b_bench_ref.err ) 2> gpurun_out/r02b_bench_ref.time
+python -m pytest tests -m gpu -q > gpurun_out/r02j_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02j_pytest.log
+( time python bench.py > gpurun_out/r02j_bench.json 2> gpurun_out/r02j_bench.err ) 2> gpurun_out/r02j_bench.time
+( time python bench.py --impl reference > gpurun_out/r02j_bench_ref.json 2> gpurun_out/r02j_bench_ref.err ) 2> gpurun_out/r02j_bench_ref.time
+# launch lists (ncu serialises and runs cold: shares, not absolutes) -- only after the plain runs above exited
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02j_launches_bus.csv python tools/prof_run.py bus 10000 3 0 > gpurun_out/r02j_ncu_l_bus.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02j_launches_zz_batch.csv python tools/prof_run.py zz_batch 4096 3 0 > gpurun_out/r02j_ncu_l_zzb.log 2>&1
+# full captures of the last evaluation's kernels
+ncu --set full --clock-control none --import-source on -s 6 -c 3 -o gpurun_out/r02j_full_bus -f python tools/prof_run.py bus 10000 3 0 > gpurun_out/r02j_ncu_f_bus.log 2>&1
+ncu --set full --clock-control none --import-source on -s 6 -c 3 -o gpurun_out/r02j_full_zzb -f python tools/prof_run.py zz_batch 4096 3 0 > gpurun_out/r02j_ncu_f_zzb.log 2>&1
+ncu --set full --clock-control none -k regex:g_gemm2 -s 40 -c 1 -o gpurun_out/r02j_full_gemm128 -f python tools/run_once.py synth128x512 frechet 1 > gpurun_out/r02j_ncu_f_g128.log 2>&1
+ls -la gpurun_out/*.ncu-rep
