@@ -77,7 +77,7 @@ def ncu_traffic_bytes(kernel_prefix, workload):
     tag = {"bus": "", "zz_batch": "_zz_batch"}.get(workload)
     if tag is None:
         return None
-    for rnd in ("r02", "r01f"):
+    for rnd in ("r02j", "r01f"):
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", f"{rnd}_ncu_full_summary{tag}.json")))
             for k in prof["kernels"]:
