@@ -37,6 +37,9 @@ struct GGemm {
   int gj_k0, gj_nb;   // gj_nb > 0: rank-nb update of the blocked Gauss-Jordan inverse (k range [gj_k0, gj_k0 + gj_nb), D[0] = cur)
 };
 
+#ifndef QOC_GEMM_KC64
+#define QOC_GEMM_KC64 32
+#endif
 #ifndef QOC_3M
 #error "qoc_gpath.cuh assumes the 3M complex product (Acc carries T1/T2/T3)"
 #endif
@@ -59,7 +62,8 @@ __device__ __forceinline__ void g_cp_async_wait() { asm volatile("cp.async.wait_
 // ran): 0.41 of the FP64 peak at best.  gj_nb > 0 selects the rank-nb update of the blocked Gauss-Jordan inverse below.
 template <int WM, int WN, int NWM, int NWN>
 struct GemmShape {
-  static constexpr int NTH = 32 * NWM * NWN, TM = 8 * WM * NWM, TN = 8 * WN * NWN, KC = 16, NST = 3;
+  // k-chunk: 32 wide for the 64 x 64 tile (3 x 72 KB of ring: one CTA per SM anyway, half as many barriers per flop), 16 otherwise
+  static constexpr int NTH = 32 * NWM * NWN, TM = 8 * WM * NWM, TN = 8 * WN * NWN, KC = (WM * NWM >= 8 && WN * NWN >= 8) ? QOC_GEMM_KC64 : 16, NST = 3;
   static constexpr int AS = KC + 4, BS = TN + 4;
   static constexpr int A_PLANE = TM * AS, B_PLANE = KC * BS, STAGE = 2 * A_PLANE + 2 * B_PLANE;   // doubles
   static constexpr size_t SMEM = (size_t)NST * STAGE * 8;
