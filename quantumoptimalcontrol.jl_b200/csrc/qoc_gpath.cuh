@@ -92,10 +92,24 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
   const int total = g.npairs * nkc;   // chunks per item
   const int tps = ntm * ntn;          // tiles per slice
 
-  // producer cursor: (item, chunk) of the next chunk to put in flight, and the ring stage it goes to
-  int pw = blockIdx.x, pc = 0, pstage = 0;
+  // Ring hand-over by mbarriers instead of a CTA-wide barrier per chunk: full[s] completes when every thread's cp.async of the
+  // chunk in stage s has landed (cp.async.mbarrier.arrive.noinc), done[s] when every thread has finished reading it.  A warp
+  // consumes chunk c as soon as it is there and refills the stage of chunk c - 1 afterwards, by which time everybody has
+  // long left it: warps drift by up to a chunk instead of meeting at a barrier 2 x (d / 16) times per product.
+  __shared__ __align__(8) unsigned long long ring_bar[2 * NST];
+  unsigned long long* full = ring_bar;
+  unsigned long long* done = ring_bar + NST;
+  if (tid == 0) {
+    for (int i = 0; i < NST; i++) { mbar_init(full + i, NTH); mbar_init(done + i, NTH); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // producer cursor: (item, chunk) of the next chunk to put in flight, and its running number (stage = number % NST)
+  int pw = blockIdx.x, pc = 0, pgc = 0;
   auto issue_next = [&]() {
     if (pw < nitems) {
+      const int pstage = pgc % NST, use = pgc / NST;
+      if (use >= 1) mbar_wait(done + pstage, (unsigned)((use - 1) & 1));
       const int s = pw / tps, r = pw - s * tps, tm = r / ntn, tn = r - tm * ntn;
       const int p = pc / nkc, kc = pc - p * nkc, kb = kbeg + kc * KC;
       const double* Ag = g.A[p].p + g.A[p].off(s);
@@ -119,15 +133,15 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
         g_cp_async16(sb + rr * BS + cc, src, bytes);
         g_cp_async16(sb + G::B_PLANE + rr * BS + cc, bytes ? src + plane : Bg, bytes);
       }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full + pstage)) : "memory");
+      pgc++;
       if (++pc == total) { pc = 0; pw += gridDim.x; }
     }
-    pstage = (pstage + 1 == NST) ? 0 : pstage + 1;
-    g_cp_async_commit();
   };
 
 #pragma unroll
   for (int c = 0; c < NST - 1; c++) issue_next();
-  int cstage = 0;   // consumer stage
+  int cgc = 0;   // consumer: running chunk number
   for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
     const int s = w / tps, r = w - s * tps, tm = r / ntn, tn = r - tm * ntn;
     double T1[WM][WN][2], T2[WM][WN][2], T3[WM][WN][2];
@@ -147,9 +161,8 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
 #pragma unroll
     for (int b = 0; b < WN; b++) fullw = fullw && colv[b];
     for (int it = 0; it < total; it++) {
-      g_cp_async_wait<NST - 2>();
-      __syncthreads();
-      issue_next();
+      const int cstage = cgc % NST;
+      mbar_wait(full + cstage, (unsigned)((cgc / NST) & 1));
       if (work) {
         const double* st = sm + (size_t)cstage * G::STAGE;
         const int kc = it % nkc;
@@ -208,7 +221,9 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
         }
         }
       }
-      cstage = (cstage + 1 == NST) ? 0 : cstage + 1;
+      mbar_arrive(done + cstage);
+      cgc++;
+      issue_next();
     }
     double* Cg = g.C + (g.cinner > 0 ? (long long)(s / g.cinner) * g.cstride2 + (long long)(s % g.cinner) * g.cstride
                                      : (long long)s * g.cstride);
