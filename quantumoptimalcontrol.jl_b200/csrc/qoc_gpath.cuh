@@ -310,7 +310,8 @@ static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
   const long long items = (long long)tm * tn * nb;
   // small tiles (d < 64: two or three chunks per item) run one CTA per item: several CTAs are resident per SM anyway and the
   // per-chunk bookkeeping of the persistent walk costs more than it hides (d = 32, Nt = 1e5: 74 ms vs 84 ms persistent)
-  const long long grid = (G::TM >= 64 && items > wave) ? wave : items;
+  static const int persist_all = [] { const char* e = getenv("QOC_GEMM_PERSIST"); return (e && e[0] == '1') ? 1 : 0; }();
+  const long long grid = ((G::TM >= 64 || persist_all) && items > wave) ? wave : items;
   g_gemm2_kernel<WM, WN, NWM, NWN><<<(int)grid, G::NTH, G::SMEM, st>>>(g, tm, tn, (int)items);
 }
 static inline int g_gemm_tile(int d) {
