@@ -446,6 +446,17 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     // second-generation sweeps (no running penalty)
     const char* old_sw = getenv("QOC_OLD_SWEEPS");
     const bool pen = h->row_mask != 0u && h->col_mask != 0u && p.mu != 0.0;
+    {
+      // small-dimension sweeps (with or without the running penalty: they carry the affine recurrence and its pre-pass)
+      const char* off3 = getenv("QOC_NO_K3S");
+      h->k3s_ok = p.d <= K3S_D && p.m <= K3S_M && p.nc <= 4 && C::S == 12 && !(off3 && off3[0] == '1') && !(old_sw && old_sw[0] == '1');
+      if (h->k3s_ok) {
+        QOC_CUDA(h, cudaFuncSetAttribute(k3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3s_smem_bytes()));
+        int occs = 1;
+        QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, k3s_kernel, K3S_WPB * 32, k3s_smem_bytes()));
+        h->k3s_grid = h->nsm * (occs < 1 ? 1 : occs);
+      }
+    }
     if (!pen && !(old_sw && old_sw[0] == '1')) {
       h->k3n_threads = (C::NT + 1 + K3N_CW) * 32;
       h->k3n_smem = k3n_smem_bytes<C>(p.d, p.m, p.nc, h->seg_cap);
@@ -456,16 +467,6 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
         if (occ3 < 1) occ3 = 1;
         h->k3n_grid = h->nseg < h->nsm * occ3 ? h->nseg : h->nsm * occ3;
         h->new_k3 = true;
-        {
-          const char* off3 = getenv("QOC_NO_K3S");
-          h->k3s_ok = p.d <= K3S_D && p.m <= K3S_M && p.nc <= 4 && C::S == 12 && !(off3 && off3[0] == '1');
-          if (h->k3s_ok) {
-            QOC_CUDA(h, cudaFuncSetAttribute(k3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3s_smem_bytes()));
-            int occs = 1;
-            QOC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occs, k3s_kernel, K3S_WPB * 32, k3s_smem_bytes()));
-            h->k3s_grid = h->nsm * (occs < 1 ? 1 : occs);
-          }
-        }
       }
       // K2G: G groups per pulse, chosen to balance the spp/G tile products against the 2 G + 2 spp/G mat-vec steps;
       // every CTA of the launch must be resident at once (per-pulse barrier)
@@ -1106,7 +1107,7 @@ static int launch_k3(qoc_handle* h, bool want_grad, bool store_states, double* d
   q.store_states = store_states ? 1 : 0;
   if (d_dJdu) q.dJdu = d_dJdu;
   const int grid = h->nseg < h->nsm * 2 ? h->nseg : h->nsm * 2;
-  if (h->new_k3 && mode == 0 && h->k3s_ok) {
+  if (h->k3s_ok && (mode == 0 || mode == 1) && !h->dbg) {
     // small-dimension form: nine lanes per segment, no CTA barriers (qoc_k3s.cuh)
     const int per_cta = K3S_WPB * 3;
     const int ctas = (h->nseg + per_cta - 1) / per_cta;

@@ -98,6 +98,13 @@ __global__ void __launch_bounds__(K3S_WPB * 32, 1) k3s_kernel(K23Params p, int S
   __syncwarp();
   const int gid = (blockIdx.x * K3S_WPB + warp) * 3 + g, gstride = gridDim.x * K3S_WPB * 3;
   const bool contract = p.want_grad != 0;
+  // running state penalty (src/penalty_fcns.jl:1-11): lambda_k = U_k' lambda_{k+1} + 2 mu x_k on the penalised entries
+  // (src/gradient_computations.jl:55-57).  k3_mode 1 = the pre-pass of the affine segment recurrence: forward states, sum of
+  // L(x_k) over the segment, and c_seg = the recurrence run from a zero costate (K2 adds it at the segment boundaries).
+  const bool pen = p.row_mask != 0u && p.col_mask != 0u;
+  const bool prepass = p.k3_mode == 1;
+  const bool rowpen = pen && L.rowok && ((p.row_mask >> L.r) & 1u);
+  const double two_mu = 2.0 * p.mu;
 
   for (int seg = gid; __any_sync(FULL, seg < p.nseg); seg += gstride) {
     const bool on = act && seg < p.nseg;
@@ -120,8 +127,14 @@ __global__ void __launch_bounds__(K3S_WPB * 32, 1) k3s_kernel(K23Params p, int S
     double2 a[K3S_D];
     if (len > 1) k3s_load_row(L, p.U + sl0 * slot_d, a);
     int buf = 0;
+    double ps = 0.0;
     for (int i = 0; i < maxlen; i++) {
       const bool live = i < len;
+      if (prepass && rowpen && wr && live) {
+#pragma unroll
+        for (int c = 0; c < K3S_M; c++)
+          if ((p.col_mask >> c) & 1u) ps += x[c].x * x[c].x + x[c].y * x[c].y;
+      }
       if (wr && live) {
         double2* Xk = reinterpret_cast<double2*>(p.X + ((size_t)b * (p.nt + 1) + k0 + i) * 2 * dm);
 #pragma unroll
@@ -151,13 +164,18 @@ __global__ void __launch_bounds__(K3S_WPB * 32, 1) k3s_kernel(K23Params p, int S
       }
       buf ^= 1;
     }
-    if (!contract) continue;
+    if (prepass) {   // sum_{k in segment} L(x_k)     src/penalty_fcns.jl:2-4
+      ps = k3s_group_sum(ps, L.r);
+      if (on && L.r == 0 && ps != 0.0) atomicAdd(&p.Jpen[b], p.mu * ps);
+    }
+    if (!contract && !prepass) continue;
 
     // ---------------- backward: lambda_{k1} = lambda_end(seg); gradient of slice k; lambda_k = U_k' lambda_{k+1} ----------------
+    // (pre-pass: the same recurrence from a zero costate, no gradient: its result is c_seg)
     double2 lam[K3S_M];
 #pragma unroll
     for (int c = 0; c < K3S_M; c++)
-      lam[c] = (wr && c < m) ? reinterpret_cast<const double2*>(p.lam_end + (size_t)sg * 2 * dm)[L.r + d * c] : make_double2(0.0, 0.0);
+      lam[c] = (wr && c < m && !prepass) ? reinterpret_cast<const double2*>(p.lam_end + (size_t)sg * 2 * dm)[L.r + d * c] : make_double2(0.0, 0.0);
     for (int it = 0; it < maxlen; it++) {
       const bool live = it < len;
       const int k = k1 - 1 - it;                         // slice index within the pulse
@@ -171,7 +189,7 @@ __global__ void __launch_bounds__(K3S_WPB * 32, 1) k3s_kernel(K23Params p, int S
 #pragma unroll
         for (int c = 0; c < K3S_M; c++) xk[c] = (wr && c < m) ? Xk[L.r + d * c] : make_double2(0.0, 0.0);
       }
-      if (wr && live && p.store_costates && p.LAM) {
+      if (wr && live && p.store_costates && p.LAM && !prepass) {
         double2* Lk = reinterpret_cast<double2*>(p.LAM + ((size_t)b * (p.nt + 1) + k + 1) * 2 * dm);
 #pragma unroll
         for (int c = 0; c < K3S_M; c++)
@@ -184,6 +202,7 @@ __global__ void __launch_bounds__(K3S_WPB * 32, 1) k3s_kernel(K23Params p, int S
         for (int c = 0; c < K3S_M; c++) { ls[L.r * K3S_M + c] = lam[c]; xs[L.r * K3S_M + c] = xk[c]; }
       }
       __syncwarp();
+      if (contract) {
       // weights of my row: w[cc] = sum_l conj(lambda[r][l]) x_k[cc][l]
       double2 w[K3S_D];
 #pragma unroll
@@ -206,13 +225,28 @@ __global__ void __launch_bounds__(K3S_WPB * 32, 1) k3s_kernel(K23Params p, int S
         s = k3s_group_sum(s, L.r);
         if (on && live && L.r == 0) p.dJdu[sl * nc + j] = s;
       }
-      // costate: lambda_k[r][c] = sum_rr conj(U[rr][r]) lambda_{k+1}[rr][c]
+      }
+      // costate: lambda_k[r][c] = sum_rr conj(U[rr][r]) lambda_{k+1}[rr][c]  (+ dL_dx(x_k))
       double2 y[K3S_M];
       k3s_row_times(uc, ls, y);
+      if (rowpen) {
+#pragma unroll
+        for (int c = 0; c < K3S_M; c++)
+          if ((p.col_mask >> c) & 1u) { y[c].x = fma(two_mu, xk[c].x, y[c].x); y[c].y = fma(two_mu, xk[c].y, y[c].y); }
+      }
       if (live) {
 #pragma unroll
         for (int c = 0; c < K3S_M; c++) lam[c] = y[c];
       }
+    }
+    if (prepass) {
+      if (wr) {
+        double2* cs = reinterpret_cast<double2*>(p.cs + (size_t)sg * 2 * dm);
+#pragma unroll
+        for (int c = 0; c < K3S_M; c++)
+          if (c < m) cs[L.r + d * c] = lam[c];
+      }
+      continue;
     }
     if (wr && k0 == 0 && p.store_costates && p.LAM) {
       double2* L0 = reinterpret_cast<double2*>(p.LAM + ((size_t)b * (p.nt + 1)) * 2 * dm);
