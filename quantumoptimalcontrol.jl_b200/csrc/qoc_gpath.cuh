@@ -66,7 +66,7 @@ __device__ __forceinline__ void g_cp_async_wait() { asm volatile("cp.async.wait_
 template <int WM, int WN, int NWM, int NWN>
 struct GemmShape {
   // k-chunk: 32 wide for the 64 x 64 tile (3 x 72 KB of ring: one CTA per SM anyway, half as many barriers per flop), 16 otherwise
-  static constexpr int NTH = 32 * NWM * NWN, TM = 8 * WM * NWM, TN = 8 * WN * NWN, KC = (WM * NWM >= 8 && WN * NWN >= 8) ? QOC_GEMM_KC64 : QOC_GEMM_KCS, NST = 3;
+  static constexpr int NTH = 32 * NWM * NWN, TM = 8 * WM * NWM, TN = 8 * WN * NWN, KC = (WM * NWM == 8 && WN * NWN == 8) ? QOC_GEMM_KC64 : QOC_GEMM_KCS, NST = 3;
   static constexpr int AS = KC + 4, BS = TN + 4;
   static constexpr int A_PLANE = TM * AS, B_PLANE = KC * BS, STAGE = 2 * A_PLANE + 2 * B_PLANE;   // doubles
   static constexpr size_t SMEM = (size_t)NST * STAGE * 8;
@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(256) g_lin_kernel(GGemm g) {
 }
 
 // host-side launch helper: the CTA tile that wastes least of the d x d matrix (ties: the larger tile)
-//   32 x 32 (8 warps of 1 x 2 tiles) | 40 x 40 (5 warps of 1 x 5) | 48 x 48 (6 warps of 1 x 6) | 64 x 64 (16 warps of 2 x 2)
+//   32 x 32 (8 warps of 1 x 2 tiles) | 40 x 40 (5 warps of 1 x 5) | 48 x 48 (6 warps of 1 x 6) | 64 x 64 (16 warps of 2 x 2) |
+//   80 x 80 (10 warps of 1 x 10)
 template <int WM, int WN, int NWM, int NWN>
 static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
   typedef GemmShape<WM, WN, NWM, NWN> G;
@@ -318,9 +319,9 @@ static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
   g_gemm2_kernel<WM, WN, NWM, NWN><<<(int)grid, G::NTH, G::SMEM, st>>>(g, tm, tn, (int)items);
 }
 static inline int g_gemm_tile(int d) {
-  static const int cand[4] = {64, 48, 40, 32};
+  static const int cand[5] = {80, 64, 48, 40, 32};
   int best = 64, bestpad = 1 << 30;
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 5; i++) {
     const int t = cand[i], pad = (d + t - 1) / t * t;
     if (pad < bestpad) { bestpad = pad; best = t; }
   }
@@ -340,6 +341,7 @@ static inline void g_gemm_launch(const GGemm& g, int nb, cudaStream_t st) {
     case 32: g_gemm2_launch_t<1, 2, 4, 2>(g, nb, st); break;
     case 40: g_gemm2_launch_t<1, 5, 5, 1>(g, nb, st); break;
     case 48: g_gemm2_launch_t<1, 6, 6, 1>(g, nb, st); break;
+    case 80: g_gemm2_launch_t<1, 10, 10, 1>(g, nb, st); break;
     default: g_gemm2_launch_t<2, 2, 4, 4>(g, nb, st); break;
   }
 }
