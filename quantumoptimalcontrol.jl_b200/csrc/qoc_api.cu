@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -1824,12 +1825,24 @@ struct qoc_sharded {
   unsigned long long gen = 0, arrived_gen = 0;
   int arrived = 0, done = 0;
   bool quit = false;
+  // low-latency hand-over for back-to-back evaluations (an optimiser loop): workers and the caller spin on these for a short
+  // while (~100 us) before they fall back to the condition variable
+  std::atomic<unsigned long long> gen_a{0};
+  std::atomic<int> done_a{0};
+  std::atomic<int> sleepers{0};
   const double* job_u = nullptr;
   double *job_J = nullptr, *job_g = nullptr;
   std::vector<int> rc_rank;
 };
 
 static thread_local std::string g_sharded_error;
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  asm volatile("pause" ::: "memory");
+#else
+  std::this_thread::yield();
+#endif
+}
 
 // Fused exchange: rank p stores its S_p into slot p of EVERY rank's S_all buffer through the NVLink peer mappings and then
 // raises its flag there (release at system scope); nothing on the host takes part.  grid = (blocks, ranks); the last block of
@@ -2070,10 +2083,20 @@ static void sharded_worker(qoc_sharded* s, int p) {
   unsigned long long seen = 0;
   for (;;) {
     {
-      std::unique_lock<std::mutex> lk(s->mu);
-      s->cv.wait(lk, [&] { return s->quit || s->gen != seen; });
+      bool got = false;
+      for (int spin = 0; spin < 20000 && !got; spin++) {   // ~100 us of polling
+        got = s->gen_a.load(std::memory_order_acquire) != seen;
+        if (!got) cpu_relax();
+      }
+      if (!got) {
+        std::unique_lock<std::mutex> lk(s->mu);
+        s->sleepers.fetch_add(1);
+        s->cv.wait(lk, [&] { return s->quit || s->gen != seen; });
+        s->sleepers.fetch_sub(1);
+        if (s->quit) return;
+      }
       if (s->quit) return;
-      seen = s->gen;
+      seen = s->gen_a.load(std::memory_order_acquire);
     }
     int rc = sharded_rank_A(s, p, s->job_u);
     if (rc != QOC_OK && s->flags) {   // release the peers that will spin on this rank's flag
@@ -2093,9 +2116,10 @@ static void sharded_worker(qoc_sharded* s, int p) {
       rc = sharded_rank_B(s, p, s->job_J, s->job_g);
       if (rc != QOC_OK) { std::lock_guard<std::mutex> lk(s->mu); s->rc_rank[p] = rc; }
     }
-    {
+    if (s->done_a.fetch_add(1, std::memory_order_acq_rel) + 1 == s->n) {
       std::lock_guard<std::mutex> lk(s->mu);
-      if (++s->done == s->n) s->cv.notify_all();
+      s->done = s->n;
+      s->cv.notify_all();
     }
   }
 }
@@ -2113,11 +2137,22 @@ extern "C" int qoc_sharded_eval(qoc_sharded* s, const double* u, double* J_out, 
       std::lock_guard<std::mutex> lk(s->mu);
       s->job_u = u; s->job_J = J_out; s->job_g = dJdu_out;
       s->arrived = 0; s->done = 0;
+      s->done_a.store(0, std::memory_order_relaxed);
       s->gen++;
+      s->gen_a.store(s->gen, std::memory_order_release);
     }
-    s->cv.notify_all();
-    std::unique_lock<std::mutex> lk(s->mu);
-    s->cv.wait(lk, [&] { return s->done == P; });
+    if (s->sleepers.load() > 0) s->cv.notify_all();
+    {
+      bool fin = false;
+      for (int spin = 0; spin < 2000000 && !fin; spin++) {   // a few ms of polling, then sleep
+        fin = s->done_a.load(std::memory_order_acquire) == P;
+        if (!fin) cpu_relax();
+      }
+      if (!fin) {
+        std::unique_lock<std::mutex> lk(s->mu);
+        s->cv.wait(lk, [&] { return s->done == P; });
+      }
+    }
   } else {
     bool bad = false;
     for (int p = 0; p < P; p++) {

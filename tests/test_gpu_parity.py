@@ -659,3 +659,46 @@ def test_time_sharding_small_dimension_kernel_virtual_ranks(order):
         assert abs(float(J.cpu()[0]) - Jo) <= TOL_J
         g[:, lo:hi] = gl.cpu().numpy().T
     assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+
+
+@pytest.mark.parametrize("d,nt,order", [(32, 91, 0), (40, 60, 3)])
+def test_time_sharding_general_path_with_a_host_closure_cost(d, nt, order):
+    """The three-call phase API (phase 1 / forward / backward) on the GENERAL path with a cost that is an arbitrary host closure
+    (here the z-calibrated infidelity's host twin and the oracle's trace infidelity): qoc_shard_forward_device /
+    qoc_shard_backward_device route through the two-level sweeps of qoc_gpath.cuh (round 1 launched the shared-memory kernels
+    with d > 28: ADVICE.md).  P = 3 virtual ranks on one GPU."""
+    import torch
+    from qoc_b200 import sharding
+    cfg = o.config_synthetic(d, nt, nc=2, m=4, seed=3)
+    P = 3
+    for cost_o, cost_h in ((o.setup_infidelity(cfg["T"], cfg["n"]), o.setup_infidelity(cfg["T"], cfg["n"])),
+                           (o.setup_infidelity_zcalibrated(cfg["T"]), q.setup_infidelity_zcalibrated(cfg["T"], device=False))):
+        co = o.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape)
+        xs = o.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], co)["x"]
+        Jo = cost_o[0](xs[-1])
+        go = o.grape_sensitivity(cfg["A0"], cfg["A"], cost_o[1], cfg["u"], cfg["x0"], co, dUkdp_order=order).copy()
+        engines, S = [], []
+        for r in range(P):
+            lo, hi = sharding.time_partition(nt, P, r)
+            e = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, 4, 0, order=order)
+            S.append(e.phase1(cfg["u"][:, lo:hi]).clone())
+            engines.append(e)
+        x = torch.as_tensor(cfg["x0"]).to(engines[0].device)
+        starts = []
+        for r in range(P):
+            starts.append(x)
+            x = S[r] @ x
+        xN = x.cpu().numpy()
+        assert np.abs(xN - xs[-1]).max() < 1e-11
+        assert abs(float(cost_h[0](xN)) - Jo) <= TOL_J
+        lam = torch.as_tensor(np.asarray(cost_h[1](xN), dtype=np.complex128)).to(engines[0].device)
+        g = np.zeros_like(go)
+        for r in range(P - 1, -1, -1):
+            lo, hi = sharding.time_partition(nt, P, r)
+            engines[r].forward(starts[r])
+            gl, _ = engines[r].backward(lam)
+            g[:, lo:hi] = gl.cpu().numpy()
+            lam = S[r].conj().t() @ lam
+        # (the z-calibrated gradient is defined to ~1e-7 by the reference's own golden-section search: tests/test_gpu_zcal.py)
+        tol = 1e-6 if cost_h[1] is not cost_o[1] else TOL_G
+        assert np.abs(g - go).max() <= tol * np.abs(go).max()
