@@ -721,6 +721,24 @@ struct GRun {
     g_gemm_launch(g, nb, st);
     h->launches++;
   }
+  // the same with up to two extra outputs (workspace slots) that reuse the product and the D operands:
+  //   slot xs[k] = ax[k] P + sum_q bx[k][q] D_q + gx[k] I
+  void gemm_x(double* C, long long cstride, int npairs, const GOp* A, const GOp* B, double alpha, int nadd, const GOp* D,
+              const double* beta, double gamma, int nx, const int* xs, const double* ax, const double (*bx)[3], const double* gx) const {
+    GGemm g;
+    memset(&g, 0, sizeof g);
+    g.d = h->prob.d; g.S = h->S; g.nb = nb; g.npairs = npairs; g.nadd = nadd; g.alpha = alpha; g.gamma = gamma;
+    for (int i = 0; i < npairs; i++) { g.A[i] = A[i]; g.B[i] = B[i]; }
+    for (int i = 0; i < nadd; i++) { g.D[i] = D[i]; g.beta[i] = beta[i]; }
+    g.C = C; g.cstride = cstride;
+    g.nextra = nx;
+    for (int k = 0; k < nx; k++) {
+      g.Cx[k] = Wp(xs[k]); g.cxstride[k] = h->slot_d; g.alphax[k] = ax[k]; g.gammax[k] = gx[k];
+      for (int q = 0; q < 3; q++) g.betax[k][q] = q < nadd ? bx[k][q] : 0.0;
+    }
+    g_gemm_launch(g, nb, st);
+    h->launches++;
+  }
   void mm1(int c, GOp a, GOp b, double alpha = 1.0, int nadd = 0, const GOp* D = nullptr, const double* beta = nullptr, double gamma = 0.0) const {
     gemm(Wp(c), h->slot_d, 1, &a, &b, alpha, nadd, D, beta, gamma);
   }
@@ -885,24 +903,31 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
     g_build_kernel<<<nb, 256, 0, st>>>(d, h->S, nc, h->dA0p, h->dAp, d_u + c0 * nc, sc, g.Wp(A),
                                        (taylor && want_jac && p.order >= 2) ? g.Wp(X) : nullptr, h->slot_d);
     h->launches++;
+    // (the linear combinations of the program ride in the epilogues of the products that complete their last term: gemm_x)
+    const double zero3[3] = {0.0, 0.0, 0.0};
     g.mm1(A2, g.W(A), g.W(A));
-    g.mm1(A4, g.W(A2), g.W(A2));
-    if (q == 13) {
-      g.mm1(A6, g.W(A2), g.W(A4));
-      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[13], b[11], b[9]}; g.lin(W1, 3, D, be); }
-      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[12], b[10], b[8]}; g.lin(Z1, 3, D, be); }
-      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[7], b[5], b[3]}; g.mm1(Wm, g.W(A6), g.W(W1), 1.0, 3, D, be, b[1]); }
-      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[6], b[4], b[2]}; g.mm1(V, g.W(A6), g.W(Z1), 1.0, 3, D, be, b[0]); }
-    } else if (q == 7) {   // U = A (b7 A6 + b5 A4 + b3 A2 + b1 I), V = b6 A6 + b4 A4 + b2 A2 + b0 I
-      g.mm1(A6, g.W(A2), g.W(A4));
-      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[7], b[5], b[3]}; g.lin(Wm, 3, D, be, b[1]); }
-      { GOp D[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[6], b[4], b[2]}; g.lin(V, 3, D, be, b[0]); }
-    } else {               // U = A (b5 A4 + b3 A2 + b1 I), V = b4 A4 + b2 A2 + b0 I
-      { GOp D[2] = {g.W(A4), g.W(A2)}; double be[2] = {b[5], b[3]}; g.lin(Wm, 2, D, be, b[1]); }
-      { GOp D[2] = {g.W(A4), g.W(A2)}; double be[2] = {b[4], b[2]}; g.lin(V, 2, D, be, b[0]); }
+    if (q == 5) {          // A4 = A2 A2;  W = b5 A4 + b3 A2 + b1 I,  V = b4 A4 + b2 A2 + b0 I
+      GOp a1 = g.W(A2), b1 = g.W(A2), D[1] = {g.W(A2)};
+      const int xs[2] = {Wm, V}; const double ax[2] = {b[5], b[4]}, bx[2][3] = {{b[3], 0, 0}, {b[2], 0, 0}}, gx[2] = {b[1], b[0]};
+      g.gemm_x(g.Wp(A4), h->slot_d, 1, &a1, &b1, 1.0, 1, D, zero3, 0.0, 2, xs, ax, bx, gx);
+    } else {
+      g.mm1(A4, g.W(A2), g.W(A2));
+      GOp a1 = g.W(A2), b1 = g.W(A4), D[2] = {g.W(A4), g.W(A2)};
+      if (q == 13) {       // A6 = A2 A4;  W1 = b13 A6 + b11 A4 + b9 A2,  Z1 = b12 A6 + b10 A4 + b8 A2
+        const int xs[2] = {W1, Z1}; const double ax[2] = {b[13], b[12]}, bx[2][3] = {{b[11], b[9], 0}, {b[10], b[8], 0}}, gx[2] = {0.0, 0.0};
+        g.gemm_x(g.Wp(A6), h->slot_d, 1, &a1, &b1, 1.0, 2, D, zero3, 0.0, 2, xs, ax, bx, gx);
+        { GOp D3[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[7], b[5], b[3]}; g.mm1(Wm, g.W(A6), g.W(W1), 1.0, 3, D3, be, b[1]); }
+        { GOp D3[3] = {g.W(A6), g.W(A4), g.W(A2)}; double be[3] = {b[6], b[4], b[2]}; g.mm1(V, g.W(A6), g.W(Z1), 1.0, 3, D3, be, b[0]); }
+      } else {             // A6 = A2 A4;  W = b7 A6 + b5 A4 + b3 A2 + b1 I,  V = b6 A6 + b4 A4 + b2 A2 + b0 I
+        const int xs[2] = {Wm, V}; const double ax[2] = {b[7], b[6]}, bx[2][3] = {{b[5], b[3], 0}, {b[4], b[2], 0}}, gx[2] = {b[1], b[0]};
+        g.gemm_x(g.Wp(A6), h->slot_d, 1, &a1, &b1, 1.0, 2, D, zero3, 0.0, 2, xs, ax, bx, gx);
+      }
     }
-    g.mm1(U, g.W(A), g.W(Wm));
-    { GOp D[2] = {g.W(V), g.W(U)}; double be[2] = {1.0, -1.0}; g.lin(V, 2, D, be); }   // N = V - U (in place: elementwise)
+    {   // U = A W, and N = V - U in the same epilogue (in place on V: every element is read before it is written, by one thread)
+      GOp a1 = g.W(A), b1 = g.W(Wm), D[1] = {g.W(V)};
+      const int xs[1] = {V}; const double ax[1] = {-1.0}, bx[1][3] = {{1.0, 0, 0}}, gx[1] = {0.0};
+      g.gemm_x(g.Wp(U), h->slot_d, 1, &a1, &b1, 1.0, 1, D, zero3, 0.0, 1, xs, ax, bx, gx);
+    }
     // N^-1: blocked Gauss-Jordan (panels in shared memory, rank-32 DMMA updates), V and NI as the two buffers
     const GOp Ninv{g_inverse_blocked(d, h->S, h->slot_d, nb, g.Wp(V), g.Wp(NI), h->dpiv, h->dstatus, st, &h->launches), (long long)h->slot_d};
     // R = I + 2 N^-1 U
@@ -936,23 +961,29 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
         }
         // exact Frechet derivative, structured block-triangular evaluation (Al-Mohy & Higham 2009, Alg. 6.4)
         g.mm2(M2, g.W(A), E, E, g.W(A));
-        g.mm2(M4, g.W(A2), g.W(M2), g.W(M2), g.W(A2));
-        if (q == 13) {
-          g.mm2(M6, g.W(A4), g.W(M2), g.W(M4), g.W(A2));
-          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[13], b[11], b[9]}; g.lin(T1, 3, D, be); }
-          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[12], b[10], b[8]}; g.lin(T2, 3, D, be); }
-          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[7], b[5], b[3]}; g.mm2(Lw, g.W(A6), g.W(T1), g.W(M6), g.W(W1), 1.0, 3, D, be); }
-          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[6], b[4], b[2]}; g.mm2(Lv, g.W(A6), g.W(T2), g.W(M6), g.W(Z1), 1.0, 3, D, be); }
-        } else if (q == 7) {   // Lw, Lv are linear combinations of M6, M4, M2
-          g.mm2(M6, g.W(A4), g.W(M2), g.W(M4), g.W(A2));
-          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[7], b[5], b[3]}; g.lin(Lw, 3, D, be); }
-          { GOp D[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[6], b[4], b[2]}; g.lin(Lv, 3, D, be); }
+        if (q == 5) {      // M4 = A2 M2 + M2 A2;  Lw = b5 M4 + b3 M2,  Lv = b4 M4 + b2 M2
+          GOp Aa[2] = {g.W(A2), g.W(M2)}, Bb[2] = {g.W(M2), g.W(A2)}, D[1] = {g.W(M2)};
+          const int xs[2] = {Lw, Lv}; const double ax[2] = {b[5], b[4]}, bx[2][3] = {{b[3], 0, 0}, {b[2], 0, 0}}, gx[2] = {0.0, 0.0};
+          g.gemm_x(g.Wp(M4), h->slot_d, 2, Aa, Bb, 1.0, 1, D, zero3, 0.0, 2, xs, ax, bx, gx);
         } else {
-          { GOp D[2] = {g.W(M4), g.W(M2)}; double be[2] = {b[5], b[3]}; g.lin(Lw, 2, D, be); }
-          { GOp D[2] = {g.W(M4), g.W(M2)}; double be[2] = {b[4], b[2]}; g.lin(Lv, 2, D, be); }
+          g.mm2(M4, g.W(A2), g.W(M2), g.W(M2), g.W(A2));
+          GOp Aa[2] = {g.W(A4), g.W(M4)}, Bb[2] = {g.W(M2), g.W(A2)}, D[2] = {g.W(M4), g.W(M2)};
+          if (q == 13) {   // M6 = A4 M2 + M4 A2;  T1 = b13 M6 + b11 M4 + b9 M2,  T2 = b12 M6 + b10 M4 + b8 M2
+            const int xs[2] = {T1, T2}; const double ax[2] = {b[13], b[12]}, bx[2][3] = {{b[11], b[9], 0}, {b[10], b[8], 0}}, gx[2] = {0.0, 0.0};
+            g.gemm_x(g.Wp(M6), h->slot_d, 2, Aa, Bb, 1.0, 2, D, zero3, 0.0, 2, xs, ax, bx, gx);
+            { GOp D3[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[7], b[5], b[3]}; g.mm2(Lw, g.W(A6), g.W(T1), g.W(M6), g.W(W1), 1.0, 3, D3, be); }
+            { GOp D3[3] = {g.W(M6), g.W(M4), g.W(M2)}; double be[3] = {b[6], b[4], b[2]}; g.mm2(Lv, g.W(A6), g.W(T2), g.W(M6), g.W(Z1), 1.0, 3, D3, be); }
+          } else {         // M6 = A4 M2 + M4 A2;  Lw = b7 M6 + b5 M4 + b3 M2,  Lv = b6 M6 + b4 M4 + b2 M2
+            const int xs[2] = {Lw, Lv}; const double ax[2] = {b[7], b[6]}, bx[2][3] = {{b[5], b[3], 0}, {b[4], b[2], 0}}, gx[2] = {0.0, 0.0};
+            g.gemm_x(g.Wp(M6), h->slot_d, 2, Aa, Bb, 1.0, 2, D, zero3, 0.0, 2, xs, ax, bx, gx);
+          }
         }
-        { GOp D[1] = {g.W(Lv)}; double be[1] = {-1.0}; g.mm2(Dd, g.W(A), g.W(Lw), E, g.W(Wm), 1.0, 1, D, be); }        // D = Lu - Lv
-        { GOp D[2] = {g.W(Dd), g.W(Lv)}; double be[2] = {1.0, 2.0}; g.lin(Ss, 2, D, be); }                          // S = Lu + Lv
+        {   // D = Lu - Lv and S = Lu + Lv from one product pair (Lu = A Lw + E W)
+          GOp Aa[2] = {g.W(A), E}, Bb[2] = {g.W(Lw), g.W(Wm)}, D[1] = {g.W(Lv)};
+          const double be[3] = {-1.0, 0, 0};
+          const int xs[1] = {Ss}; const double ax[1] = {1.0}, bx[1][3] = {{1.0, 0, 0}}, gx[1] = {0.0};
+          g.gemm_x(g.Wp(Dd), h->slot_d, 2, Aa, Bb, 1.0, 1, D, be, 0.0, 1, xs, ax, bx, gx);
+        }
         { GOp D[1] = {g.W(Ss)}; double be[1] = {1.0}; g.mm1(RH, g.W(Dd), Rop, 1.0, 1, D, be); }                       // rhs = S + D R
         double* Lj = (sq == 0) ? Lout : g.Wp(L0 + j);
         { GOp a1 = Ninv, b1 = g.W(RH); g.gemm(Lj, (sq == 0) ? lstride : (long long)h->slot_d, 1, &a1, &b1, sc, 0, nullptr, nullptr, 0.0); }

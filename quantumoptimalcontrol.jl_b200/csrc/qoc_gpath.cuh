@@ -35,6 +35,12 @@ struct GGemm {
   int cinner;
   long long cstride2;
   int gj_k0, gj_nb;   // gj_nb > 0: rank-nb update of the blocked Gauss-Jordan inverse (k range [gj_k0, gj_k0 + gj_nb), D[0] = cur)
+  // up to two more outputs from the same product P = sum_p A_p B_p and the same D operands (the linear combinations of the
+  // Pade / Frechet program that used to be launches of their own):  Cx_k = alphax_k P + sum_q betax_k[q] D_q + gammax_k I
+  int nextra;
+  double* Cx[2];
+  long long cxstride[2];
+  double alphax[2], betax[2][3], gammax[2];
 };
 
 #ifndef QOC_GEMM_KC64
@@ -78,7 +84,7 @@ struct GemmShape {
 // One-CTA-per-tile launches exposed a prologue (first chunk: an L2 / HBM round trip) and an epilogue per tile with
 // nothing to overlap them when only one CTA fits an SM (the 64 x 64 tile: 16 warps x ~100 registers): at d = 64, where a
 // tile is only four chunks long, that was half the kernel.
-template <int WM, int WN, int NWM, int NWN>
+template <int WM, int WN, int NWM, int NWN, bool XTRA>   // XTRA: the epilogue also writes the extra outputs (more registers)
 __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int ntm, int ntn, int nitems) {
   typedef GemmShape<WM, WN, NWM, NWN> G;
   constexpr int NTH = G::NTH, TM = G::TM, TN = G::TN, KC = G::KC, NST = G::NST, AS = G::AS, BS = G::BS;
@@ -238,8 +244,9 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
         const int col = tn * TN + (wn * WN + b) * 8 + 2 * q4;
         if (row < d && col < d) {
           // 3M: Re = T1 - T2, Im = T3 - T1 - T2
-          double r0 = g.alpha * (T1[a][b][0] - T2[a][b][0]), r1 = g.alpha * (T1[a][b][1] - T2[a][b][1]);
-          double i0 = g.alpha * ((T3[a][b][0] - T1[a][b][0]) - T2[a][b][0]), i1 = g.alpha * ((T3[a][b][1] - T1[a][b][1]) - T2[a][b][1]);
+          const double p0 = T1[a][b][0] - T2[a][b][0], p1 = T1[a][b][1] - T2[a][b][1];
+          const double q0 = (T3[a][b][0] - T1[a][b][0]) - T2[a][b][0], q1 = (T3[a][b][1] - T1[a][b][1]) - T2[a][b][1];
+          double r0 = g.alpha * p0, r1 = g.alpha * p1, i0 = g.alpha * q0, i1 = g.alpha * q1;
           const size_t o = (size_t)row * S + col;
           if (gj) {
             // blocked Gauss-Jordan step on the panel K = [kbeg, kend): the K columns of `cur` already hold the transformation
@@ -249,14 +256,34 @@ __global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int nt
             if (col >= kbeg && col < kend) { r0 = u.x; r1 = u.y; i0 = v.x; i1 = v.y; }
             else if (!(row >= kbeg && row < kend)) { r0 += u.x; r1 += u.y; i0 += v.x; i1 += v.y; }
           } else {
-            for (int q = 0; q < g.nadd; q++) {
-              const double* Dg = g.D[q].p + g.D[q].off(s);
-              const double2 u = *reinterpret_cast<const double2*>(Dg + o), v = *reinterpret_cast<const double2*>(Dg + plane + o);
-              r0 = fma(g.beta[q], u.x, r0); r1 = fma(g.beta[q], u.y, r1);
-              i0 = fma(g.beta[q], v.x, i0); i1 = fma(g.beta[q], v.y, i1);
+            double2 du[3], dv[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+              du[q] = make_double2(0.0, 0.0); dv[q] = du[q];
+              if (q < g.nadd) {
+                const double* Dg = g.D[q].p + g.D[q].off(s);
+                du[q] = *reinterpret_cast<const double2*>(Dg + o); dv[q] = *reinterpret_cast<const double2*>(Dg + plane + o);
+                r0 = fma(g.beta[q], du[q].x, r0); r1 = fma(g.beta[q], du[q].y, r1);
+                i0 = fma(g.beta[q], dv[q].x, i0); i1 = fma(g.beta[q], dv[q].y, i1);
+              }
             }
             if (row == col) r0 += g.gamma;
             if (row == col + 1) r1 += g.gamma;
+            for (int x = 0; XTRA && x < g.nextra; x++) {
+              double xr0 = g.alphax[x] * p0, xr1 = g.alphax[x] * p1, xi0 = g.alphax[x] * q0, xi1 = g.alphax[x] * q1;
+#pragma unroll
+              for (int q = 0; q < 3; q++)
+                if (q < g.nadd) {
+                  xr0 = fma(g.betax[x][q], du[q].x, xr0); xr1 = fma(g.betax[x][q], du[q].y, xr1);
+                  xi0 = fma(g.betax[x][q], dv[q].x, xi0); xi1 = fma(g.betax[x][q], dv[q].y, xi1);
+                }
+              if (row == col) xr0 += g.gammax[x];
+              if (row == col + 1) xr1 += g.gammax[x];
+              if (col + 1 >= d) { xr1 = 0.0; xi1 = 0.0; }
+              double* Xg = g.Cx[x] + (long long)s * g.cxstride[x];
+              *reinterpret_cast<double2*>(Xg + o) = make_double2(xr0, xr1);
+              *reinterpret_cast<double2*>(Xg + plane + o) = make_double2(xi0, xi1);
+            }
           }
           if (col + 1 >= d) { r1 = 0.0; i1 = 0.0; }
           *reinterpret_cast<double2*>(Cg + o) = make_double2(r0, r1);
@@ -296,18 +323,18 @@ __global__ void __launch_bounds__(256) g_lin_kernel(GGemm g) {
 // host-side launch helper: the CTA tile that wastes least of the d x d matrix (ties: the larger tile)
 //   32 x 32 (8 warps of 1 x 2 tiles) | 40 x 40 (5 warps of 1 x 5) | 48 x 48 (6 warps of 1 x 6) | 64 x 64 (16 warps of 2 x 2) |
 //   80 x 80 (10 warps of 1 x 10)
-template <int WM, int WN, int NWM, int NWN>
-static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
+template <int WM, int WN, int NWM, int NWN, bool XTRA>
+static inline void g_gemm2_launch_x(const GGemm& g, int nb, cudaStream_t st) {
   typedef GemmShape<WM, WN, NWM, NWN> G;
   static int wave_of[64] = {0};   // CTAs in one wave of this instantiation, per device (function attributes are per device)
   int dev = 0;
   cudaGetDevice(&dev);
   int& wave = wave_of[dev & 63];
   if (!wave) {
-    cudaFuncSetAttribute(g_gemm2_kernel<WM, WN, NWM, NWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    cudaFuncSetAttribute(g_gemm2_kernel<WM, WN, NWM, NWN, XTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     int nsm = 148, occ = 1;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_gemm2_kernel<WM, WN, NWM, NWN>, G::NTH, G::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_gemm2_kernel<WM, WN, NWM, NWN, XTRA>, G::NTH, G::SMEM);
     wave = nsm * (occ < 1 ? 1 : occ);
   }
   const int tm = (g.d + G::TM - 1) / G::TM, tn = (g.d + G::TN - 1) / G::TN;
@@ -316,7 +343,12 @@ static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
   // per-chunk bookkeeping of the persistent walk costs more than it hides (d = 32, Nt = 1e5: 74 ms vs 84 ms persistent)
   static const int persist_all = [] { const char* e = getenv("QOC_GEMM_PERSIST"); return (e && e[0] == '1') ? 1 : 0; }();
   const long long grid = ((G::TM >= 64 || persist_all) && items > wave) ? wave : items;
-  g_gemm2_kernel<WM, WN, NWM, NWN><<<(int)grid, G::NTH, G::SMEM, st>>>(g, tm, tn, (int)items);
+  g_gemm2_kernel<WM, WN, NWM, NWN, XTRA><<<(int)grid, G::NTH, G::SMEM, st>>>(g, tm, tn, (int)items);
+}
+template <int WM, int WN, int NWM, int NWN>
+static inline void g_gemm2_launch_t(const GGemm& g, int nb, cudaStream_t st) {
+  if (g.nextra > 0) g_gemm2_launch_x<WM, WN, NWM, NWN, true>(g, nb, st);
+  else g_gemm2_launch_x<WM, WN, NWM, NWN, false>(g, nb, st);
 }
 static inline int g_gemm_tile(int d) {
   static const int cand[4] = {64, 48, 40, 32};   // (80 x 80 exists for A/B runs, QOC_GEMM_TILE=80: 5.2 vs 4.1 ms on cavity-40)
