@@ -46,6 +46,9 @@ struct GGemm {
 #ifndef QOC_GEMM_KC64
 #define QOC_GEMM_KC64 32
 #endif
+#ifndef QOC_GEMM_NST64
+#define QOC_GEMM_NST64 3
+#endif
 #ifndef QOC_GEMM_KCS
 #define QOC_GEMM_KCS 16
 #endif
@@ -72,7 +75,8 @@ __device__ __forceinline__ void g_cp_async_wait() { asm volatile("cp.async.wait_
 template <int WM, int WN, int NWM, int NWN>
 struct GemmShape {
   // k-chunk: 32 wide for the 64 x 64 tile (3 x 72 KB of ring: one CTA per SM anyway, half as many barriers per flop), 16 otherwise
-  static constexpr int NTH = 32 * NWM * NWN, TM = 8 * WM * NWM, TN = 8 * WN * NWN, KC = (WM * NWM == 8 && WN * NWN == 8) ? QOC_GEMM_KC64 : QOC_GEMM_KCS, NST = 3;
+  static constexpr int NTH = 32 * NWM * NWN, TM = 8 * WM * NWM, TN = 8 * WN * NWN, KC = (WM * NWM == 8 && WN * NWN == 8) ? QOC_GEMM_KC64 : QOC_GEMM_KCS,
+                       NST = (WM * NWM == 8 && WN * NWN == 8) ? QOC_GEMM_NST64 : 3;
   static constexpr int AS = KC + 4, BS = TN + 4;
   static constexpr int A_PLANE = TM * AS, B_PLANE = KC * BS, STAGE = 2 * A_PLANE + 2 * B_PLANE;   // doubles
   static constexpr size_t SMEM = (size_t)NST * STAGE * 8;
