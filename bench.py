@@ -48,6 +48,7 @@ METRIC = "GRAPE fidelity+gradient evals/s (slices*pulses/s)"
 UNIT = "slices*pulses/s"
 FP64_PEAK_FALLBACK_TFLOPS = 37.1  # measured DMMA m8n8k4 on this pool (profiles/r01_fp64_peak.jsonl)
 TOL_J, TOL_G = 1e-10, 1e-8        # north star: relative 1e-10 on (in)fidelity, 1e-8 on each gradient component
+PARITY_FAILURES = []              # in-bench parity assertions that failed (the JSON line is still printed; exit code 1)
 
 
 def fp64_peak_tflops():
@@ -532,7 +533,8 @@ def run_time_sharded(cx, name, mode, steps, warmup):
            "parity": {"vs": "single-GPU evaluation of the same pulse (rank 0)", "abs_dJ": dJ, "rel_dg_max": dg,
                       "tol_J": TOL_J, "tol_g": TOL_G, "ok_all_ranks": bool(okall)},
            "J": J, "gpu_launches": int(5 * steps * cx.world)}
-    assert okall, f"time-sharded result disagrees with the single-GPU evaluation: |dJ|={dJ:.3e} rel|dg|={dg:.3e} ({name}, {mode})"
+    if not okall:   # reported in the record AND fatal: the line is printed first, the process then exits non-zero (main)
+        PARITY_FAILURES.append(f"time-sharded ({name}, {mode}): |dJ|={dJ:.3e} rel|dg|={dg:.3e}")
     del ev, eng
     torch.cuda.empty_cache()
     return rec
@@ -549,7 +551,10 @@ def run_in_library_sharded(cx, name, mode, steps, warmup):
     rec = None
     torch.cuda.synchronize()
     cx.dist.barrier(group=cx.cpu_group)   # every GPU idle from here on (no NCCL kernel parked on it)
-    if cx.rank == 0:
+    if cx.rank == 0 and torch.cuda.device_count() < cx.world:
+        rec = {"workload": name, "mode": mode, "skipped": f"rank 0 sees {torch.cuda.device_count()} device(s), needs {cx.world} "
+               "(CUDA_VISIBLE_DEVICES restricts this process): the one-process route cannot be measured in this launch"}
+    elif cx.rank == 0:
         order = 0 if mode == "frechet" else 3
         cfg, u, batch, desc = build_workload(name, 0, mode)
         nc, nt = u.shape
@@ -583,7 +588,8 @@ def run_in_library_sharded(cx, name, mode, steps, warmup):
                "parity": {"vs": "single-GPU evaluation of the same pulse", "abs_dJ": dJ, "rel_dg_max": dg, "tol_J": TOL_J,
                           "tol_g": TOL_G, "ok": bool(ok)}, "J": J}
         sh.close()
-        assert ok, f"in-library sharded result disagrees with the single-GPU evaluation: |dJ|={dJ:.3e} rel|dg|={dg:.3e} ({name}, {mode})"
+        if not ok:
+            PARITY_FAILURES.append(f"in-library sharded ({name}, {mode}): |dJ|={dJ:.3e} rel|dg|={dg:.3e}")
     cx.dist.barrier(group=cx.cpu_group)
     return rec
 
@@ -691,10 +697,15 @@ def main():
                 if r is not None:
                     inlib.append(r)
             out["strong_in_library"] = inlib
+    if PARITY_FAILURES:
+        out["parity_failures"] = PARITY_FAILURES
     if cx.rank == 0:
         print(json.dumps(out))
     if cx.world > 1:
         cx.dist.destroy_process_group()
+    if PARITY_FAILURES:
+        sys.stderr.write("PARITY ASSERTION FAILED: " + "; ".join(PARITY_FAILURES) + "\n")
+        return 1
     return 0
 
 
