@@ -950,10 +950,14 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
   }
   if (pen && g.mode == 3) {   // J = Jfinal(x_N) + sum_k L(x_k), k = 0 .. N (examples/ipopt_callbacks_exp.jl:18)
     double ps = gs_penalty_sum(cur, g, tid, nth);
-    for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
-    if (lane == 0) atomicAdd(&ov[8], ps);
+    // (its own accumulator: ov[0 .. 2m) holds the per-column overlaps, m up to 8)
+    __shared__ double pen_xN;
+    if (tid == 0) pen_xN = 0.0;
     __syncthreads();
-    if (tid == 0 && g.J) g.J[b] = cc.J + g.mu * (g.Jpen[b] + ov[8]);
+    for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+    if (lane == 0) atomicAdd(&pen_xN, ps);
+    __syncthreads();
+    if (tid == 0 && g.J) g.J[b] = cc.J + g.mu * (g.Jpen[b] + pen_xN);
   } else if (builtin && tid == 0 && g.J) g.J[b] = cc.J;
   if (!do_bwd) return;
   for (int c = 0; c < m; c++)

@@ -195,7 +195,11 @@ def test_control_bounds_make_the_general_path_asynchronous_and_capturable():
 
 # ---- running state penalty on the general path: two-level (parallel) sweeps, any row ------------------------------------------
 @pytest.mark.parametrize("d,nt,m,rows,cols,order", [(32, 300, 3, [1, 5, 31], [0, 2], 0), (40, 150, 2, [3, 39], [0, 1], 3),
-                                                     (80, 60, 2, [2, 64, 65, 79], [1], 0)])
+                                                     (80, 60, 2, [2, 64, 65, 79], [1], 0),
+                                                     # five and more columns: the penalty accumulator used to share a slot with
+                                                     # the overlap of column 4 (found by tools/stress_parity.py)
+                                                     (33, 40, 5, [21, 28], [3], 2), (44, 12, 7, [38, 40], [1, 2], 0),
+                                                     (28, 15, 8, [2], [0, 7], 0)])
 def test_state_penalty_general_path_vs_oracle(d, nt, m, rows, cols, order):
     """src/penalty_fcns.jl:1-11 with src/gradient_computations.jl:47-49, :55-57 at d > 28: the costate recurrence is affine, a
     segment is summarised by (Q_seg, c_seg); rows >= 64 included (round 1's serial sweep carried a 64-bit row mask)."""
