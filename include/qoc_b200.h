@@ -156,7 +156,16 @@ int qoc_shard_forward_device(qoc_handle* h, const double* d_x_start, double* d_x
 int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_end, double* d_dJdu, double* d_lambda_start,
                               void* stream);
 
-/* Phase 2 in one call for the built-in costs: d_S_all = the nranks all-gathered rank propagators (c128 d x d each,
+/* Running state penalty (n_pen_rows > 0) under time sharding.  The costate recurrence is then affine (src/gradient_computations.jl
+ * :47-49, :55-57): over the local segment  lambda_start = S_p' lambda_end + c_p.  After qoc_shard_forward_device this call writes
+ * c_p (c128 d x m) and the local sum_k L(x_k) over the nt_local + 1 local states (1 double, may be NULL).  The caller exchanges
+ * the c_p next to the S_p and walks the boundary costates down from the last rank; a boundary state belongs to two ranks, so
+ * it subtracts L and dL_dx of x_start(p), p >= 1, once (quantumoptimalcontrol.jl_b200/sharding.py does exactly this).
+ * lambda_end handed to qoc_shard_backward_device is, as for qoc_gradient, the costate BEFORE dL_dx of the last local state is
+ * added.  Returns QOC_ERR_INVALID without a penalty, QOC_ERR_STALE_CACHE before the forward call.                           */
+int qoc_shard_affine_device(qoc_handle* h, double* d_c_out, double* d_Jpen_out, void* stream);
+
+/* Phase 2 in one call for the built-in costs (no running penalty: QOC_ERR_UNSUPPORTED, use the three calls above): d_S_all = the nranks all-gathered rank propagators (c128 d x d each,
  * rank order); computes x_start / J / lambda_end on the device (redundantly on every rank, src/penalty_fcns.jl:15-24)
  * and runs the local boundary scan and sweeps.  d_J: 1 double, d_dJdu: nc x nt_local doubles (device memory).        */
 int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int nranks, int rank, double* d_J, double* d_dJdu,

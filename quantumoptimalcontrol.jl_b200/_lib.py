@@ -48,6 +48,7 @@ SYMBOLS = {
     "qoc_shard_phase1_device": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qoc_shard_forward_device": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qoc_shard_backward_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "qoc_shard_affine_device": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qoc_shard_phase2_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "qoc_get_states": (C.c_int, [_vp, _dp]),
     "qoc_get_costates": (C.c_int, [_vp, _dp]),

@@ -84,6 +84,7 @@ struct qoc_handle {
   bool k1_skewh = false;      // A0 and every A_j skew-Hermitian (bitwise): k1s_kernel forms A E + E A, A2 M2 + M2 A2, X E as P + P^dagger
   bool k1s_ok = false;        // d <= 9, nc <= 4: the small-dimension kernel (nine lanes per slice, three slices per warp)
   int k1s_wpb = 0;            // its warps per CTA (what fits shared memory)
+  bool shard_fwd_done = false;   // qoc_shard_forward_device ran on the current propagators (the affine call needs its c_s)
   bool k3s_ok = false;        // d <= 9, m <= 4, nc <= 4: the small-dimension sweeps (nine lanes per segment)
   int k3s_grid = 0;
   bool k1_sym = false;        // ... with symmetric H0, H_j: Pade denominator inverted through the real SPD matrix N N^dagger
@@ -790,7 +791,7 @@ static int gpath_build_Q(qoc_handle* h, cudaStream_t st) {
 }
 
 static int gpath_sweep2(qoc_handle* h, int mode, bool skip_bwd, bool want_grad, const double* d_lam_final, const double* d_x_start,
-                        double* d_J, double* d_dJdu, cudaStream_t st) {
+                        double* d_J, double* d_dJdu, cudaStream_t st, bool scan_only = false) {
   const qoc_problem& p = h->prob;
   GS g;
   memset(&g, 0, sizeof g);
@@ -824,7 +825,7 @@ static int gpath_sweep2(qoc_handle* h, int mode, bool skip_bwd, bool want_grad, 
     g.mode = (mode == 2) ? 2 : 3;
     gs_scan_kernel<<<p.batch, GS_NW * 32, st_smem, st>>>(g);
     h->launches++;
-    if (!(mode == 0 && skip_bwd) && mode != 1) {
+    if (!(mode == 0 && skip_bwd) && mode != 1 && !scan_only) {
       gs_seg_kernel<<<grid, GS_NW * 32, st_smem, st>>>(g, h->nseg);
       h->launches++;
     }
@@ -1600,14 +1601,15 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) kq_reduce_kernel(const double*
   }
 }
 
-// Preconditions shared by every qoc_shard_* entry point: one pulse, no running penalty (its affine costate term needs a
-// second exchange that the phase API does not carry; qoc_create_sharded / qoc_sharded_eval do), and on the general path the
-// two-level sweeps.  Never a silent fallback: anything else is QOC_ERR_UNSUPPORTED.
-static int shard_guard(qoc_handle* h) {
+// Preconditions shared by every qoc_shard_* entry point: one pulse and, on the general path, the two-level sweeps.  The running
+// state penalty makes the costate recurrence affine: the three-call form (forward / affine / backward) carries it, the caller
+// exchanging the affine terms c_p next to the S_p; the one-call phase 2 does not (allow_pen = false).  Never a silent fallback:
+// anything else is QOC_ERR_UNSUPPORTED.
+static int shard_guard(qoc_handle* h, bool allow_pen = true) {
   if (h->prob.batch != 1) { h->err = "time sharding handles one pulse (batch == 1)"; return QOC_ERR_INVALID; }
   if (h->nch > 1) { h->err = "time sharding with more than 8 state columns is not supported yet"; return QOC_ERR_UNSUPPORTED; }
-  if (has_penalty(h) || (h->row_mask64 != 0ull && h->col_mask != 0u && h->prob.mu != 0.0)) {
-    h->err = "the qoc_shard_* phase API does not carry the running state penalty (affine costate term)";
+  if (!allow_pen && has_penalty(h)) {
+    h->err = "qoc_shard_phase2_device does not carry the running state penalty: use forward / affine / backward";
     return QOC_ERR_UNSUPPORTED;
   }
   if (h->gpath && !h->gs2) { h->err = "time sharding on the general path needs the two-level sweeps (nt >= 4)"; return QOC_ERR_UNSUPPORTED; }
@@ -1620,6 +1622,7 @@ extern "C" int qoc_shard_phase1_device(qoc_handle* h, const double* d_u, double*
   cudaStream_t st = (cudaStream_t)stream;
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
   h->launches = 0;
+  h->shard_fwd_done = false;
   int rc = launch_k1(h, d_u, true, st);
   if (rc != QOC_OK) return rc;
   if (h->gpath) {
@@ -1667,11 +1670,72 @@ extern "C" int qoc_shard_forward_device(qoc_handle* h, const double* d_x_start, 
   cudaStream_t st = (cudaStream_t)stream;
   QOC_CUDA(h, cudaSetDevice(h->prob.device));
   // general path: boundary walk + segment sweeps of the two-level form, forward only from the external state
-  int rc = h->gpath ? gpath_sweep2(h, 1, true, false, nullptr, d_x_start, nullptr, nullptr, st)
-                    : launch_k2(h, 1, true, nullptr, d_x_start, nullptr, st);
+  // (with a running penalty both forms also leave the segments' affine terms c_s and sum_k L(x_k) behind)
+  int rc;
+  if (h->gpath) rc = gpath_sweep2(h, 1, true, false, nullptr, d_x_start, nullptr, nullptr, st);
+  else {
+    if (has_penalty(h)) QOC_CUDA(h, cudaMemsetAsync(h->dJpen, 0, 8, st));
+    rc = launch_k2(h, 1, true, nullptr, d_x_start, nullptr, st);
+    if (rc == QOC_OK && has_penalty(h)) rc = launch_k3(h, false, true, nullptr, st, 1);
+  }
   if (rc != QOC_OK) return rc;
+  h->shard_fwd_done = true;
   if (d_x_end)
     QOC_CUDA(h, cudaMemcpyAsync(d_x_end, h->dxf, (size_t)2 * h->prob.d * h->prob.m * 8, cudaMemcpyDeviceToDevice, st));
+  return QOC_OK;
+}
+
+// sum_k L(x_k) over the nt_local + 1 local states: what the pre-pass accumulated over x_0 .. x_{nt-1} (mu already applied on the
+// shared-memory path, not on the general path) plus L(x_nt)
+__global__ void __launch_bounds__(256) shard_jpen_kernel(const double* Jpen, const double* xf, int d, int m, const unsigned char* pen_row,
+                                                         unsigned long long row_mask, unsigned col_mask, double mu, int scale_acc,
+                                                         double* out) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x;
+  double s = 0.0;
+  for (int e = tid; e < d * m; e += 256) {
+    const int c = e / d, r = e - c * d;
+    const bool on = (pen_row ? pen_row[r] != 0 : (r < 64 && ((row_mask >> r) & 1ull))) && ((col_mask >> c) & 1u);
+    if (on) s += xf[2 * e] * xf[2 * e] + xf[2 * e + 1] * xf[2 * e + 1];
+  }
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    out[0] = (scale_acc ? mu * Jpen[0] : Jpen[0]) + mu * t;
+  }
+}
+
+// Running penalty under time sharding: the local costate recurrence is affine in the costate entering from the right,
+//   lambda_start = S_p' lambda_end + c_p,
+// c_p being what the backward boundary walk returns for lambda_end = 0 (the segments' c_s are there since the forward call;
+// dL_dx of the last local state is added by the walk itself, as for any terminal costate: src/gradient_computations.jl:47-49).
+// One boundary-scan launch; also hands out the local sum_k L(x_k) over the nt_local + 1 local states.
+extern "C" int qoc_shard_affine_device(qoc_handle* h, double* d_c_out, double* d_Jpen_out, void* stream) {
+  if (!h || !d_c_out) return QOC_ERR_INVALID;
+  { const int gr = shard_guard(h); if (gr != QOC_OK) return gr; }
+  if (!has_penalty(h)) { h->err = "qoc_shard_affine_device: the problem has no running penalty"; return QOC_ERR_INVALID; }
+  if (!h->shard_fwd_done || !h->states_valid) { h->err = "qoc_shard_affine_device needs qoc_shard_forward_device first"; return QOC_ERR_STALE_CACHE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const qoc_problem& p = h->prob;
+  QOC_CUDA(h, cudaSetDevice(p.device));
+  const size_t sb = (size_t)2 * p.d * p.m * 8;
+  double* zero = h->dbnd + (size_t)2 * p.d * p.m;      // lambda_end = 0 (the lambda_end half of the boundary scratch)
+  QOC_CUDA(h, cudaMemsetAsync(zero, 0, sb, st));
+  int rc;
+  if (h->gpath) rc = gpath_sweep2(h, 2, false, false, zero, nullptr, nullptr, nullptr, st, true);
+  else rc = launch_k2(h, 2, false, zero, nullptr, nullptr, st);
+  if (rc != QOC_OK) return rc;
+  QOC_CUDA(h, cudaMemcpyAsync(d_c_out, h->dlam0, sb, cudaMemcpyDeviceToDevice, st));
+  if (d_Jpen_out) {
+    // sum over the local states: the pre-pass has x_0 .. x_{nt-1} (+ mu folded in or not, see below), x_nt is added here
+    shard_jpen_kernel<<<1, 256, 0, st>>>(h->dJpen, h->dxf, p.d, p.m, h->gpath ? h->dpenrow : nullptr, h->row_mask64, h->col_mask, p.mu,
+                                         h->gpath ? 1 : 0, d_Jpen_out);
+    h->launches++;
+    QOC_CUDA(h, cudaGetLastError());
+  }
   return QOC_OK;
 }
 
@@ -1700,37 +1764,50 @@ extern "C" int qoc_shard_backward_device(qoc_handle* h, const double* d_lambda_e
   return QOC_OK;
 }
 
+// Boundary algebra over the all-gathered rank propagators on the device: x_start -> h->dbnd, lambda_end -> h->dbnd + 2 d m, J.
+// C_all / xs: the affine terms of the running penalty and the boundary-state scratch (NULL: no penalty, or the first of the two
+// calls of the penalty route, which only needs x_start).
+static int launch_shard_boundary(qoc_handle* h, const double* d_S_all, int nranks, int rank, const double* d_C_all, double* d_xs,
+                                 double* d_J, cudaStream_t st) {
+  const qoc_problem& p = h->prob;
+  ShardBoundary q;
+  memset(&q, 0, sizeof q);
+  q.d = p.d; q.m = p.m; q.nranks = nranks; q.rank = rank; q.cost = p.cost; q.n = p.n;
+  q.S_all = d_S_all; q.x0 = h->dx0; q.T = h->dT; q.x_start = h->dbnd; q.lam_end = h->dbnd + (size_t)2 * p.d * p.m; q.J = d_J ? d_J : h->dJ;
+  q.pen = has_penalty(h) ? 1 : 0; q.C_all = d_C_all; q.xs = d_xs;
+  q.pen_row = h->dpenrow; q.row_mask = h->row_mask64; q.col_mask = h->col_mask; q.mu = p.mu;
+  const size_t b_smem = (size_t)2 * p.d * p.m * 16;
+  if (b_smem > 40 * 1024) QOC_CUDA(h, cudaFuncSetAttribute(shard_boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
+  shard_boundary_kernel<<<1, 256, b_smem, st>>>(q);
+  QOC_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return QOC_OK;
+}
+
 // Phase 2 of the time-sharded evaluation in one call: boundary algebra over the all-gathered rank propagators (on the
 // device, redundantly on every rank), then the local boundary scan and sweeps.  Needs a built-in cost.
 extern "C" int qoc_shard_phase2_device(qoc_handle* h, const double* d_S_all, int nranks, int rank, double* d_J, double* d_dJdu,
                                        void* stream) {
   if (!h || !d_S_all || nranks <= 0 || rank < 0 || rank >= nranks) return QOC_ERR_INVALID;
-  { const int gr = shard_guard(h); if (gr != QOC_OK) return gr; }
+  { const int gr = shard_guard(h, false); if (gr != QOC_OK) return gr; }
   if (h->prob.cost == QOC_COST_NONE) { h->err = "qoc_shard_phase2_device needs a built-in cost"; return QOC_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   const qoc_problem& p = h->prob;
   QOC_CUDA(h, cudaSetDevice(p.device));
-  ShardBoundary q;
-  q.d = p.d; q.m = p.m; q.nranks = nranks; q.rank = rank; q.cost = p.cost; q.n = p.n;
-  q.S_all = d_S_all; q.x0 = h->dx0; q.T = h->dT; q.x_start = h->dbnd; q.lam_end = h->dbnd + (size_t)2 * p.d * p.m; q.J = d_J ? d_J : h->dJ;
-  {
-    const size_t b_smem = (size_t)2 * p.d * p.m * 16;
-    if (b_smem > 40 * 1024) QOC_CUDA(h, cudaFuncSetAttribute(shard_boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b_smem));
-    shard_boundary_kernel<<<1, 256, b_smem, st>>>(q);
-    QOC_CUDA(h, cudaGetLastError());
-  }
-  h->launches += 1;
+  { const int rb = launch_shard_boundary(h, d_S_all, nranks, rank, nullptr, nullptr, d_J, st); if (rb != QOC_OK) return rb; }
+  const double* lam_end_bnd = h->dbnd + (size_t)2 * p.d * p.m;
+  const double* x_start_bnd = h->dbnd;
   int rc;
   if (h->gpath && h->stream_jac) {
-    if ((rc = gpath_sweep2(h, 4, false, false, q.lam_end, q.x_start, nullptr, d_dJdu, st)) != QOC_OK) return rc;
+    if ((rc = gpath_sweep2(h, 4, false, false, lam_end_bnd, x_start_bnd, nullptr, d_dJdu, st)) != QOC_OK) return rc;
     return gpath_k1(h, h->k1_u, true, st, true, d_dJdu);
   }
-  if (h->gpath) return gpath_sweep2(h, 4, false, true, q.lam_end, q.x_start, nullptr, d_dJdu, st);
+  if (h->gpath) return gpath_sweep2(h, 4, false, true, lam_end_bnd, x_start_bnd, nullptr, d_dJdu, st);
   if (h->new_k2) {
-    if ((rc = launch_k2(h, 4, false, q.lam_end, q.x_start, nullptr, st)) != QOC_OK) return rc;
+    if ((rc = launch_k2(h, 4, false, lam_end_bnd, x_start_bnd, nullptr, st)) != QOC_OK) return rc;
   } else {
-    if ((rc = launch_k2(h, 1, true, nullptr, q.x_start, nullptr, st)) != QOC_OK) return rc;
-    if ((rc = launch_k2(h, 2, false, q.lam_end, nullptr, nullptr, st)) != QOC_OK) return rc;
+    if ((rc = launch_k2(h, 1, true, nullptr, x_start_bnd, nullptr, st)) != QOC_OK) return rc;
+    if ((rc = launch_k2(h, 2, false, lam_end_bnd, nullptr, nullptr, st)) != QOC_OK) return rc;
   }
   return launch_k3(h, true, true, d_dJdu, st);
 }
@@ -1841,7 +1918,14 @@ struct qoc_sharded {
   std::vector<double**> d_dst;      // per rank: device array of n pointers (slot p of every rank's S_all)
   std::vector<unsigned*> d_flags, d_done;   // per rank: n arrival flags (written by the peers), n block counters of its publish kernel
   std::vector<unsigned**> d_dstflag;        // per rank: device array of n pointers (flag p of every rank)
-  unsigned epoch = 0;
+  // running state penalty under time sharding: second exchange of (c_p, sum_k L) records of 2 d m + 2 doubles
+  bool pen = false;
+  std::vector<double*> dC_loc, dC_all, dXs;
+  std::vector<double**> d_dstc;     // per rank: device array of n pointers (record p of every rank's C_all)
+  std::vector<cudaEvent_t> ev_pub2;
+  int arrived2 = 0;
+  unsigned long long arrived2_gen = 0;
+  unsigned epoch = 0;               // advances by two per evaluation: epoch - 1 marks the S_p exchange, epoch the c_p exchange
   bool peer = true;                 // every pair of distinct devices has a peer mapping
   bool flags = false;               // exchange by peer stores + flags (every rank on its own device, all pairs mapped); else events:
                                     // ranks that share a device must not park a spinning kernel in front of each other's
@@ -1934,6 +2018,8 @@ extern "C" int qoc_sharded_destroy(qoc_sharded* s) {
     if (p < (int)s->d_flags.size() && s->d_flags[p]) cudaFree(s->d_flags[p]);
     if (p < (int)s->d_done.size() && s->d_done[p]) cudaFree(s->d_done[p]);
     if (p < (int)s->d_dstflag.size() && s->d_dstflag[p]) cudaFree(s->d_dstflag[p]);
+    if (p < (int)s->dC_loc.size()) { cudaFree(s->dC_loc[p]); cudaFree(s->dC_all[p]); cudaFree(s->dXs[p]); cudaFree(s->d_dstc[p]); }
+    if (p < (int)s->ev_pub2.size()) cudaEventDestroy(s->ev_pub2[p]);
     if (p < (int)s->ev_pub.size()) { cudaEventDestroy(s->ev_pub[p]); cudaEventDestroy(s->ev_t0[p]); cudaEventDestroy(s->ev_t1[p]); }
     if (p < (int)s->h.size() && s->h[p]) qoc_destroy(s->h[p]);
   }
@@ -2017,6 +2103,26 @@ extern "C" int qoc_create_sharded(const qoc_problem* prob, const double* A0, con
            cudaMalloc(&s->d_dstflag[p], sizeof(unsigned*) * n_ranks) == cudaSuccess;
     if (!ok) return fail(QOC_ERR_CUDA, "device allocation failed");
   }
+  s->pen = shard_kind == QOC_SHARD_TIME && has_penalty(s->h[0]);
+  if (s->pen) {
+    const size_t rec = (size_t)2 * prob->d * prob->m + 2;
+    s->dC_loc.assign(n_ranks, nullptr); s->dC_all.assign(n_ranks, nullptr); s->dXs.assign(n_ranks, nullptr); s->d_dstc.assign(n_ranks, nullptr);
+    for (int p = 0; p < n_ranks; p++) {
+      if (cudaSetDevice(s->dev[p]) != cudaSuccess) return fail(QOC_ERR_CUDA, "cudaSetDevice failed");
+      if (cudaMalloc(&s->dC_loc[p], rec * 8) != cudaSuccess || cudaMalloc(&s->dC_all[p], rec * 8 * n_ranks) != cudaSuccess ||
+          cudaMalloc(&s->dXs[p], rec * 8 * n_ranks) != cudaSuccess || cudaMalloc(&s->d_dstc[p], sizeof(double*) * n_ranks) != cudaSuccess)
+        return fail(QOC_ERR_CUDA, "device allocation failed");
+    }
+    s->ev_pub2.resize(n_ranks);
+    for (int p = 0; p < n_ranks; p++) {
+      cudaSetDevice(s->dev[p]);
+      cudaEventCreateWithFlags(&s->ev_pub2[p], cudaEventDisableTiming);
+      std::vector<double*> dst(n_ranks);
+      for (int q = 0; q < n_ranks; q++) dst[q] = s->dC_all[q] + (size_t)p * rec;
+      if (cudaMemcpy(s->d_dstc[p], dst.data(), sizeof(double*) * n_ranks, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(QOC_ERR_CUDA, "upload of the peer table failed");
+    }
+  }
   s->ev_pub.resize(n_ranks); s->ev_t0.resize(n_ranks); s->ev_t1.resize(n_ranks);
   for (int p = 0; p < n_ranks; p++) {
     cudaSetDevice(s->dev[p]);
@@ -2070,13 +2176,42 @@ static int sharded_rank_A(qoc_sharded* s, int p, const double* u) {
     int bx = (int)((d2 / 2 + 255) / 256);
     if (bx > 16) bx = 16;
     shard_publish_kernel<<<dim3(bx, s->n), 256, 0, h->stream>>>(s->dS_loc[p], (int)(d2 / 2), s->d_dst[p], s->d_dstflag[p], s->d_done[p],
-                                                              s->epoch);
+                                                              s->epoch - 1);
     QOC_CUDA(h, cudaGetLastError());
   } else {
     for (int q = 0; q < s->n; q++)
       QOC_CUDA(h, cudaMemcpyPeerAsync(s->dS_all[q] + (size_t)p * d2, s->dev[q], s->dS_loc[p], s->dev[p], d2 * 8, h->stream));
   }
   if (!s->flags) QOC_CUDA(h, cudaEventRecord(s->ev_pub[p], h->stream));
+  return QOC_OK;
+}
+
+// running penalty, between the halves: once every S_q has landed, x_start, the local forward sweep, the affine term c_p of the
+// local costate recurrence and the local sum of L; (c_p, sum L) published to every rank like the S_p were
+static int sharded_rank_B1(qoc_sharded* s, int p) {
+  const qoc_problem& gp = s->prob;
+  qoc_handle* h = s->h[p];
+  int rc;
+  QOC_CUDA(h, cudaSetDevice(s->dev[p]));
+  if (s->flags) {
+    shard_wait_kernel<<<1, 32, 0, h->stream>>>(s->d_flags[p], s->n, s->epoch - 1, h->dstatus);
+    QOC_CUDA(h, cudaGetLastError());
+  } else
+  for (int q = 0; q < s->n; q++)
+    if (q != p) QOC_CUDA(h, cudaStreamWaitEvent(h->stream, s->ev_pub[q], 0));
+  if ((rc = launch_shard_boundary(h, s->dS_all[p], s->n, p, nullptr, nullptr, s->dJ[p], h->stream)) != QOC_OK) return rc;
+  if ((rc = qoc_shard_forward_device(h, h->dbnd, nullptr, h->stream)) != QOC_OK) return rc;
+  const size_t rec = (size_t)2 * gp.d * gp.m + 2;
+  if ((rc = qoc_shard_affine_device(h, s->dC_loc[p], s->dC_loc[p] + rec - 2, h->stream)) != QOC_OK) return rc;
+  if (s->peer) {
+    shard_publish_kernel<<<dim3(1, s->n), 256, 0, h->stream>>>(s->dC_loc[p], (int)(rec / 2), s->d_dstc[p], s->d_dstflag[p], s->d_done[p],
+                                                             s->epoch);
+    QOC_CUDA(h, cudaGetLastError());
+  } else {
+    for (int q = 0; q < s->n; q++)
+      QOC_CUDA(h, cudaMemcpyPeerAsync(s->dC_all[q] + (size_t)p * rec, s->dev[q], s->dC_loc[p], s->dev[p], rec * 8, h->stream));
+  }
+  if (!s->flags) QOC_CUDA(h, cudaEventRecord(s->ev_pub2[p], h->stream));
   return QOC_OK;
 }
 
@@ -2092,13 +2227,25 @@ static int sharded_rank_B(qoc_sharded* s, int p, double* J_out, double* dJdu_out
     if (dJdu_out) QOC_CUDA(h, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * per, s->dg[p], n * per * 8, cudaMemcpyDeviceToHost, h->stream));
   } else {
     const size_t n = (size_t)(s->hi[p] - s->lo[p]) * gp.nc;
+    if (s->pen) {
+      // the c_p of every rank have landed (second exchange): boundary costates through (S_q', c_q), J with the partial sums of L
+      if (s->flags) {
+        shard_wait_kernel<<<1, 32, 0, h->stream>>>(s->d_flags[p], s->n, s->epoch, h->dstatus);
+        QOC_CUDA(h, cudaGetLastError());
+      } else
+      for (int q = 0; q < s->n; q++)
+        if (q != p) QOC_CUDA(h, cudaStreamWaitEvent(h->stream, s->ev_pub2[q], 0));
+      if ((rc = launch_shard_boundary(h, s->dS_all[p], s->n, p, s->dC_all[p], s->dXs[p], s->dJ[p], h->stream)) != QOC_OK) return rc;
+      if ((rc = qoc_shard_backward_device(h, h->dbnd + (size_t)2 * gp.d * gp.m, s->dg[p], nullptr, h->stream)) != QOC_OK) return rc;
+    } else {
     if (s->flags) {   // behind a kernel that spins on the peers' flags: no event, no host rendezvous
-      shard_wait_kernel<<<1, 32, 0, h->stream>>>(s->d_flags[p], s->n, s->epoch, h->dstatus);
+      shard_wait_kernel<<<1, 32, 0, h->stream>>>(s->d_flags[p], s->n, s->epoch - 1, h->dstatus);
       QOC_CUDA(h, cudaGetLastError());
     } else
     for (int q = 0; q < s->n; q++)
       if (q != p) QOC_CUDA(h, cudaStreamWaitEvent(h->stream, s->ev_pub[q], 0));
     if ((rc = qoc_shard_phase2_device(h, s->dS_all[p], s->n, p, s->dJ[p], s->dg[p], h->stream)) != QOC_OK) return rc;
+    }
     if (dJdu_out) QOC_CUDA(h, cudaMemcpyAsync(dJdu_out + (size_t)s->lo[p] * gp.nc, s->dg[p], n * 8, cudaMemcpyDeviceToHost, h->stream));
     if (p == 0 && J_out) QOC_CUDA(h, cudaMemcpyAsync(J_out, s->dJ[0], 8, cudaMemcpyDeviceToHost, h->stream));
   }
@@ -2143,6 +2290,20 @@ static void sharded_worker(qoc_sharded* s, int p) {
       else s->cv.wait(lk, [&] { return s->arrived_gen == seen; });
       for (int q = 0; q < s->n; q++) any_bad |= s->rc_rank[q] != QOC_OK;
     }
+    if (s->pen) {
+      rc = any_bad ? QOC_OK : sharded_rank_B1(s, p);
+      if ((any_bad || rc != QOC_OK) && s->flags) {   // release the peers that will spin on this rank's second flag
+        cudaSetDevice(s->dev[p]);
+        shard_flag_kernel<<<1, 32, 0, s->h[p]->stream>>>(s->d_dstflag[p], s->n, s->epoch);
+      }
+      if (rc != QOC_OK) { std::lock_guard<std::mutex> lk(s->mu); s->rc_rank[p] = rc; any_bad = true; }
+      if (!s->flags) {
+        std::unique_lock<std::mutex> lk(s->mu);
+        if (++s->arrived2 == s->n) { s->arrived2_gen = seen; s->cv.notify_all(); }
+        else s->cv.wait(lk, [&] { return s->arrived2_gen == seen; });
+        for (int q = 0; q < s->n; q++) any_bad |= s->rc_rank[q] != QOC_OK;
+      }
+    }
     if (!any_bad) {
       rc = sharded_rank_B(s, p, s->job_J, s->job_g);
       if (rc != QOC_OK) { std::lock_guard<std::mutex> lk(s->mu); s->rc_rank[p] = rc; }
@@ -2160,14 +2321,14 @@ extern "C" int qoc_sharded_eval(qoc_sharded* s, const double* u, double* J_out, 
   const qoc_problem& gp = s->prob;
   const int P = s->n;
   s->rc_rank.assign(P, QOC_OK);
-  s->epoch += 1;
+  s->epoch += 2;
   if (s->threads) {
     if (s->workers.empty())
       for (int p = 0; p < P; p++) s->workers.emplace_back(sharded_worker, s, p);
     {
       std::lock_guard<std::mutex> lk(s->mu);
       s->job_u = u; s->job_J = J_out; s->job_g = dJdu_out;
-      s->arrived = 0; s->done = 0;
+      s->arrived = 0; s->arrived2 = 0; s->done = 0;
       s->done_a.store(0, std::memory_order_relaxed);
       s->gen++;
       s->gen_a.store(s->gen, std::memory_order_release);
@@ -2190,6 +2351,7 @@ extern "C" int qoc_sharded_eval(qoc_sharded* s, const double* u, double* J_out, 
       s->rc_rank[p] = sharded_rank_A(s, p, u);
       bad |= s->rc_rank[p] != QOC_OK;
     }
+    for (int p = 0; p < P && !bad && s->pen; p++) { s->rc_rank[p] = sharded_rank_B1(s, p); bad |= s->rc_rank[p] != QOC_OK; }
     for (int p = 0; p < P && !bad; p++) s->rc_rank[p] = sharded_rank_B(s, p, J_out, dJdu_out);
   }
   for (int p = 0; p < P; p++)

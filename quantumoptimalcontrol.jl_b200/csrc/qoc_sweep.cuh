@@ -465,6 +465,17 @@ struct ShardBoundary {
   double* x_start;   // c128 d x m
   double* lam_end;   // c128 d x m
   double* J;
+  // running state penalty (src/penalty_fcns.jl:1-11): the rank recurrence is affine, lambda_start(p) = S_p' lambda_end(p) + c_p.
+  // C_all: P records of 2 d m + 2 doubles (c_p, then the rank's sum_k L(x_k) over its nt_p + 1 states); xs: P x (d x m c128)
+  // scratch for the boundary states.  A boundary state is the last state of rank p - 1 and the first of rank p: its L and
+  // dL_dx are taken out once.  C_all == NULL (first call, before the forward sweeps): only x_start is meaningful.
+  int pen;
+  const double* C_all;
+  double* xs;
+  const unsigned char* pen_row;   // [d] byte mask (general path) or NULL -> row_mask
+  unsigned long long row_mask;
+  unsigned col_mask;
+  double mu;
 };
 
 __global__ void __launch_bounds__(256) shard_boundary_kernel(ShardBoundary q) {
@@ -491,8 +502,17 @@ __global__ void __launch_bounds__(256) shard_boundary_kernel(ShardBoundary q) {
     __syncthreads();
   };
   double2* cur = xa; double2* nxt = xb;
+  const bool pen = q.pen && q.C_all != nullptr;
+  auto penalised = [&](int r, int c) {
+    return (q.pen_row ? q.pen_row[r] != 0 : (r < 64 && ((q.row_mask >> r) & 1ull))) && ((q.col_mask >> c) & 1u);
+  };
+  double lsub = 0.0;   // this thread's share of sum_{p >= 1} |x_start(p)[pen]|^2
   for (int p = 0; p < q.nranks; p++) {
     if (p == q.rank) for (int e = tid; e < dm; e += 256) reinterpret_cast<double2*>(q.x_start)[e] = cur[e];
+    if (pen) for (int e = tid; e < dm; e += 256) {
+      reinterpret_cast<double2*>(q.xs)[(size_t)p * dm + e] = cur[e];   // re-read below by the same thread
+      if (p >= 1 && penalised(e % d, e / d)) lsub += cur[e].x * cur[e].x + cur[e].y * cur[e].y;
+    }
     matvec(q.S_all + (size_t)p * 2 * d * d, false, cur, nxt);
     double2* t = cur; cur = nxt; nxt = t;
   }
@@ -503,6 +523,19 @@ __global__ void __launch_bounds__(256) shard_boundary_kernel(ShardBoundary q) {
   __syncthreads();
   CostCoef cc;
   cost_from_overlaps(q.cost, q.n, m, ov, cc);
+  if (pen) {
+    __shared__ double lred;
+    if (tid == 0) lred = 0.0;
+    __syncthreads();
+    for (int off = 16; off > 0; off >>= 1) lsub += __shfl_xor_sync(0xffffffffu, lsub, off);
+    if ((tid & 31) == 0) atomicAdd(&lred, lsub);
+    __syncthreads();
+    if (tid == 0 && q.J) {
+      double Jp = 0.0;
+      for (int p = 0; p < q.nranks; p++) Jp += q.C_all[(size_t)p * (2 * dm + 2) + 2 * dm];
+      *q.J = cc.J + Jp - q.mu * lred;
+    }
+  } else
   if (tid == 0 && q.J) *q.J = cc.J;
   for (int e = tid; e < dm; e += 256) {
     const double2 t = reinterpret_cast<const double2*>(q.T)[e];
@@ -520,6 +553,19 @@ __global__ void __launch_bounds__(256) shard_boundary_kernel(ShardBoundary q) {
     if (p == q.rank) for (int e = tid; e < dm; e += 256) reinterpret_cast<double2*>(q.lam_end)[e] = cur[e];
     if (p == q.rank) break;
     matvec(q.S_all + (size_t)p * 2 * d * d, true, cur, nxt);
+    if (pen) {   // + c_p - dL_dx(x_start(p)): the costate leaving rank p - 1, before dL_dx of ITS last state (added by its sweep)
+      const double2* cp = reinterpret_cast<const double2*>(q.C_all + (size_t)p * (2 * dm + 2));
+      for (int e = tid; e < dm; e += 256) {
+        double2 v = nxt[e];
+        v.x += cp[e].x; v.y += cp[e].y;
+        if (penalised(e % d, e / d)) {
+          const double2 x = reinterpret_cast<const double2*>(q.xs)[(size_t)p * dm + e];
+          v.x = fma(-2.0 * q.mu, x.x, v.x); v.y = fma(-2.0 * q.mu, x.y, v.y);
+        }
+        nxt[e] = v;
+      }
+      __syncthreads();
+    }
     double2* t = cur; cur = nxt; nxt = t;
   }
 }

@@ -12,8 +12,10 @@ GPUs, gloo in the CPU tests) for the plumbing.  Two natural axes (SURVEY.md sect
                           local forward / backward sweeps and the local gradient columns
         exchange          all-gather of the nc x Nt/P gradient segments
     This replaces the reference's serial loops src/gradient_computations.jl:27-29, :52-58, :65-74.
-    (The running state penalty makes the segment recurrence affine and needs a second exchange; it is supported
-    single-GPU only, as SURVEY.md section 7 plans.)
+    With a running state penalty (src/penalty_fcns.jl:1-11) the costate recurrence is affine, lambda_start = S_p' lambda_end + c_p:
+        phase 2a          local forward sweep from x_start(p); affine term c_p and the local sum_k L(x_k)
+        exchange          all-gather of (c_p, sum_k L) -- the second exchange of SURVEY.md section 7
+        phase 2b          lambda_end(p) walked down from the last rank through (S_q', c_q), local backward sweep
 
 The compute is delegated to a *segment engine* (phase1 / forward / backward).  The product engine is
 CudaSegmentEngine (C ABI, device pointers, no host round trip); the CPU tests plug in an oracle-backed engine to
@@ -52,12 +54,14 @@ def time_partition(nt: int, world: int, rank: int):
 class CudaSegmentEngine:
     """Local time segment on one B200 through the C ABI (qoc_shard_*_device).  Tensors stay in HBM."""
 
-    def __init__(self, A0, A, nt_local, m, device_index=0, order=0):
+    def __init__(self, A0, A, nt_local, m, device_index=0, order=0, penalty=None):
         self.d, self.m, self.nc, self.nt = A0.shape[0], m, len(A), nt_local
         self.device = torch.device("cuda", device_index)
         self.cache = GrapeCache(A0, np.zeros((self.d, m), dtype=np.complex128), (self.nc, nt_local), batch=1,
                                 device=device_index, dUkdp_order=order, store_costates=False)
-        self.cache._ensure(A0, A, np.zeros((self.d, m), dtype=np.complex128))
+        pen = penalty[0] if isinstance(penalty, tuple) else penalty   # (L, dL_dx) of setup_state_penalty, or L alone
+        self.cache._ensure(A0, A, np.zeros((self.d, m), dtype=np.complex128), pen)
+        self.penalty = pen
         self.lib = _lib.load()
 
     def _check(self, rc):
@@ -103,6 +107,14 @@ class CudaSegmentEngine:
         self._check(self.lib.qoc_shard_forward_device(self.cache.handle, self._ptr(xs), self._ptr(xe),
                                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return xe.t()
+
+    def affine(self):
+        """Running penalty: (c_p as a (d, m) tensor, local sum_k L(x_k) as a (1,) tensor) after forward()."""
+        c = torch.empty((self.m, self.d), dtype=torch.complex128, device=self.device)
+        Jp = torch.empty(1, dtype=torch.float64, device=self.device)
+        self._check(self.lib.qoc_shard_affine_device(self.cache.handle, self._ptr(c), self._ptr(Jp),
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return c.t(), Jp
 
     def backward(self, lam_end):
         le = lam_end.t().contiguous()
@@ -196,17 +208,19 @@ class TimeShardedEvaluator:
     def evaluate(self, u_full):
         """u_full: (nc, Nt) on every rank (only the local columns are used).  -> (J, dJdu (nc, Nt) numpy)."""
         u_full = np.asarray(u_full, dtype=np.float64)
-        if isinstance(self.cost, _BuiltinCost) and hasattr(self.engine, "phase2"):
+        pen = getattr(self.engine, "penalty", None)
+        if pen is None and isinstance(self.cost, _BuiltinCost) and hasattr(self.engine, "phase2"):
             return self._evaluate_device(u_full)
         u_loc = u_full[:, self.lo:self.hi]
         # phase 1 + exchange of the boundary propagators
         S = self._all_gather(self.engine.phase1(u_loc))
         # boundary algebra (redundant on every rank; P small products of d x d by d x m)
         x = self.x0
-        x_start = None
+        x_start, x_starts = None, []
         for p in range(self.world):
             if p == self.rank:
                 x_start = x
+            x_starts.append(x)
             x = S[p] @ x
         x_N = x
         if isinstance(self.cost, _BuiltinCost):
@@ -216,13 +230,39 @@ class TimeShardedEvaluator:
             xh = x_N.cpu().numpy()
             J = float(Jf(xh))
             lam = torch.as_tensor(np.asarray(dJf(xh), dtype=np.complex128)).to(self.device)
-        lam_end = None
-        for p in range(self.world - 1, -1, -1):
-            if p == self.rank:
-                lam_end = lam
-            lam = S[p].conj().t() @ lam
-        # phase 2: local sweeps
-        self.engine.forward(x_start)
+        if pen is None:
+            lam_end = None
+            for p in range(self.world - 1, -1, -1):
+                if p == self.rank:
+                    lam_end = lam
+                lam = S[p].conj().t() @ lam
+            # phase 2: local sweeps
+            self.engine.forward(x_start)
+        else:
+            # phase 2a: forward sweep, then the affine term of the local costate recurrence and the local sum of L
+            self.engine.forward(x_start)
+            c_loc, Jp_loc = self.engine.affine()
+            d, m = c_loc.shape
+            pack = torch.cat([torch.view_as_real(c_loc.contiguous()).reshape(-1), Jp_loc.reshape(1).to(torch.float64)])
+            packs = self._all_gather(pack)   # the second exchange: 2 d m + 1 doubles per rank
+            cs = [torch.view_as_complex(q[:-1].reshape(d, m, 2)) for q in packs]
+            rows = torch.as_tensor(np.asarray(pen.rows), device=self.device, dtype=torch.long)
+            cols = torch.as_tensor(np.asarray(pen.cols), device=self.device, dtype=torch.long)
+            # a boundary state x_start(q), q >= 1, is the last state of rank q - 1 and the first of rank q: L and dL_dx once
+            J += float(sum(q[-1] for q in packs))
+            for q in range(1, self.world):
+                J -= float(pen.mu * torch.sum(torch.abs(x_starts[q][rows][:, cols]) ** 2))
+            # lam = the costate entering a rank from the right BEFORE dL_dx of its last state (the engine adds that, as the
+            # reference does for lambda_N: src/gradient_computations.jl:47-49)
+            lam_end = None
+            for p in range(self.world - 1, -1, -1):
+                if p == self.rank:
+                    lam_end = lam
+                    break
+                lam = S[p].conj().t() @ lam + cs[p]
+                dl = torch.zeros_like(lam)
+                dl[rows[:, None], cols[None, :]] = 2 * pen.mu * x_starts[p][rows][:, cols]
+                lam = lam - dl
         g_loc, _ = self.engine.backward(lam_end)
         # gradient segments: ranks may own different numbers of slices -> pad to the longest
         nmax = max(time_partition(self.nt_total, self.world, r)[1] - time_partition(self.nt_total, self.world, r)[0]
@@ -282,7 +322,7 @@ class InProcessSharded:
     into the caller's host arrays.  kind: "batch" (pulses block-partitioned, no exchange) or "time" (one pulse, contiguous
     time segments).  devices: CUDA ordinals, one per rank (an ordinal may repeat: virtual ranks on one GPU)."""
 
-    def __init__(self, A0, A, x0, cost, u_size, devices, kind="time", batch=1, dUkdp_order=0):
+    def __init__(self, A0, A, x0, cost, u_size, devices, kind="time", batch=1, dUkdp_order=0, penalty=None):
         from .grape import _c128, _dptr
         if not isinstance(cost, _BuiltinCost):
             raise QOCError(_lib.ERR_INVALID, "the in-library sharded evaluation needs a built-in cost")
@@ -296,6 +336,14 @@ class InProcessSharded:
         pr.d, pr.m, pr.nc, pr.nt, pr.batch = A0c.shape[0], x0c.shape[1], len(A), int(u_size[1]), int(batch)
         pr.order, pr.cost, pr.n, pr.device = int(dUkdp_order), cost.kind, cost.n, 0
         self.nc, self.nt, self.batch, self.kind = pr.nc, pr.nt, pr.batch, kind
+        pen = penalty[0] if isinstance(penalty, tuple) else penalty   # setup_state_penalty(...): J then includes sum_k L(x_k)
+        if pen is not None and len(pen.rows) and len(pen.cols):
+            rows = np.ascontiguousarray(pen.rows, dtype=np.int32)
+            cols = np.ascontiguousarray(pen.cols, dtype=np.int32)
+            pr.n_pen_rows, pr.n_pen_cols = len(rows), len(cols)
+            pr.pen_rows = rows.ctypes.data_as(C.POINTER(C.c_int32))
+            pr.pen_cols = cols.ctypes.data_as(C.POINTER(C.c_int32))
+            pr.mu = pen.mu
         devs = (C.c_int * len(devices))(*[int(x) for x in devices])
         h = C.c_void_p()
         rc = lib.qoc_create_sharded(C.byref(pr), _dptr(A0c), _dptr(Aflat), _dptr(x0c), _dptr(cost.T), len(devices), devs,

@@ -19,8 +19,11 @@ class OracleSegmentEngine:
     """phase1 / forward / backward of one time segment computed by the numpy oracle (test double)."""
     device = torch.device("cpu")
 
-    def __init__(self, A0, A, order=0):
+    def __init__(self, A0, A, order=0, penalty=None):
         self.A0, self.A, self.order = A0, A, order
+        self.penalty = penalty[0] if isinstance(penalty, tuple) else penalty   # q.setup_state_penalty(...)[0]: rows, cols, mu
+        if self.penalty is not None:
+            self.L, self.dL = o.setup_state_penalty(self.penalty.rows, self.penalty.cols, self.penalty.mu)
 
     def phase1(self, u_local):
         self.u = np.asarray(u_local)
@@ -37,10 +40,20 @@ class OracleSegmentEngine:
             self.x.append(U @ self.x[-1])
         return torch.as_tensor(self.x[-1])
 
+    def affine(self):
+        """c_p = lambda_start for lambda_end = 0 (the recurrence of src/gradient_computations.jl:47-57 on the local states),
+        and the local sum of L over the nt_local + 1 local states."""
+        lam = self.dL(self.x[-1])
+        for k in range(len(self.Uk) - 1, -1, -1):
+            lam = self.Uk[k].conj().T @ lam + self.dL(self.x[k])
+        return torch.as_tensor(lam), torch.as_tensor([sum(self.L(xk) for xk in self.x)], dtype=torch.float64)
+
     def backward(self, lam_end):
         lam = lam_end.numpy()
         nt = len(self.Uk)
         g = np.zeros((len(self.A), nt))
+        if self.penalty is not None:   # as the reference does for lambda_N (:47-49)
+            lam = lam + self.dL(self.x[-1])
         for k in range(nt - 1, -1, -1):
             X = o.generator(self.A0, self.A, self.u[:, k])
             dU = [o.expm_frechet_sps(X, Aj)[1] for Aj in self.A] if self.order == 0 else \
@@ -48,7 +61,12 @@ class OracleSegmentEngine:
             for j in range(len(self.A)):
                 g[j, k] = o.compute_u_sensitivity(self.x[k], lam, dU[j])
             lam = self.Uk[k].conj().T @ lam
+            if self.penalty is not None:
+                lam = lam + self.dL(self.x[k])
         return torch.as_tensor(g), torch.as_tensor(lam)
+
+
+PEN = ([5, 6, 7], [0, 2], 0.37)   # rows, columns, mu of the running penalty in the time_pen case
 
 
 def _free_port():
@@ -72,6 +90,14 @@ def _worker(rank, world, port, mode, q_out):
                 ev = sharding.TimeShardedEvaluator(OracleSegmentEngine(cfg["A0"], cfg["A"], order), cfg["x0"], cost, 37)
                 J, g = ev.evaluate(cfg["u"])
                 q_out.put((rank, "time", order, J, g, (ev.lo, ev.hi)))
+        elif mode == "time_pen":
+            cfg = o.config_synthetic(8, 37, nc=2, m=3, seed=4)
+            for order in (0, 3):
+                pen = q.setup_state_penalty(*PEN)
+                ev = sharding.TimeShardedEvaluator(OracleSegmentEngine(cfg["A0"], cfg["A"], order, pen), cfg["x0"],
+                                                   o.setup_infidelity(cfg["T"], cfg["n"]), 37)
+                J, g = ev.evaluate(cfg["u"])
+                q_out.put((rank, "time_pen", order, J, g, (ev.lo, ev.hi)))
         else:
             cfg = o.config_zz_batch(5)
             ub = cfg["u_batch"]
@@ -99,7 +125,7 @@ def _run(mode, world=2):
     for p in procs:
         p.start()
     res = []
-    for _ in range(world * (2 if mode == "time" else 1)):
+    for _ in range(world * (2 if mode in ("time", "time_pen") else 1)):
         res.append(q_out.get(timeout=180))
     for p in procs:
         p.join(timeout=60)
@@ -125,6 +151,22 @@ def test_time_sharded_world2_gloo():
         assert sorted(r[0] for r in got) == [0, 1]
         assert sorted(r[5] for r in got) == [(0, 18), (18, 37)]
         for r in got:  # every rank holds the full, identical answer
+            assert abs(r[3] - Jo) < 1e-12
+            assert np.abs(r[4] - go).max() < 1e-11 * max(1.0, np.abs(go).max())
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_time_sharded_running_penalty_gloo(world):
+    """The second exchange (affine terms c_p, partial sums of L): src/gradient_computations.jl:47-57 split over the ranks."""
+    cfg = o.config_synthetic(8, 37, nc=2, m=3, seed=4)
+    res = _run("time_pen", world)
+    for order in (0, 3):
+        Jo, go, _ = o.evaluate(cfg, order=order, penalty=PEN)
+        J0, g0, _ = o.evaluate(cfg, order=order)
+        assert abs(Jo - J0) > 1e-3 and np.abs(go - g0).max() > 1e-4   # the penalty matters in this case
+        got = [r for r in res if r[2] == order]
+        assert sorted(r[0] for r in got) == list(range(world))
+        for r in got:
             assert abs(r[3] - Jo) < 1e-12
             assert np.abs(r[4] - go).max() < 1e-11 * max(1.0, np.abs(go).max())
 

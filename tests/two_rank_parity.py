@@ -41,6 +41,23 @@ def main():
             print(f"rank {rank} {cfg['name']} nt={nt} order={order} vs {name}: |dJ|={dJ:.2e} rel|dg|={dg:.2e}", flush=True)
             assert dJ <= 1e-10 * max(1.0, abs(Jr)) and dg <= 1e-8
         cache.close()
+    # running state penalty: the second exchange (affine terms c_p) over NCCL, on-chip path and general path
+    for cfg, order, pen in ((o.config_synthetic(16, 1001, nc=2, m=3, seed=5), 0, ([9, 12, 15], [0, 2], 0.37)),
+                            (o.config_synthetic(32, 403), 3, ([1, 30, 31], [0, 3], 0.9)),
+                            (o.config_synthetic(6, 999, nc=2, m=4, seed=2), 0, ([4, 5], [0, 1, 2], 1.5))):
+        u = cfg["u"]
+        nc, nt = u.shape
+        lo, hi = sharding.time_partition(nt, world, rank)
+        L = q.setup_state_penalty(*pen)
+        cost = q.setup_infidelity(cfg["T"], cfg["n"]) if cfg["cost"] == o.COST_INFIDELITY else q.setup_infidelity_abs_trace(cfg["T"])
+        eng = sharding.CudaSegmentEngine(cfg["A0"], cfg["A"], hi - lo, cfg["x0"].shape[1], lr, order=order, penalty=L)
+        ev = sharding.TimeShardedEvaluator(eng, cfg["x0"], cost[1], nt)
+        J, g = ev.evaluate(u)
+        Jo, go, _ = o.evaluate(cfg, order=order, penalty=pen)
+        dJ, dg = abs(J - Jo), np.abs(g - go).max() / np.abs(go).max()
+        print(f"rank {rank} {cfg['name']} nt={nt} order={order} running penalty vs oracle: |dJ|={dJ:.2e} rel|dg|={dg:.2e}", flush=True)
+        assert dJ <= 1e-10 * max(1.0, abs(Jo)) and dg <= 1e-8
+        eng.cache.close()
     dist.barrier()
     if rank == 0:
         print("TWO_RANK_PARITY_OK", flush=True)
