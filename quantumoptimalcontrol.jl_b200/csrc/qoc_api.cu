@@ -73,7 +73,10 @@ struct qoc_handle {
   // (d = 256, Nt = 1e5, nc = 2: 106 GB + 213 GB), dL holds ONE chunk; the gradient pass re-runs K1 chunk by chunk after the
   // sweeps and contracts each chunk's Jacobians with the stored x_k, lambda_{k+1} at once.  Costs one extra expm per slice
   // ((pi + s + 4/3) M of (pi + s + 4/3 + nc G) M).  QOC_STREAM_JAC=1 forces it (tests), =0 forbids it.
-  bool pen_any = false;           // a running state penalty is configured
+  bool pen_any = false;           // a running state penalty is configured (column chunks: on the CURRENT chunk, see use_cols)
+  bool pen_global = false;        // ... on any column
+  unsigned col_mask_chunk[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // penalised columns of every chunk (chunk-local bit positions)
+  double* dJc = nullptr;          // [nch][batch] column chunks with a penalty: the chunks' sum_k L(x_k)
   std::vector<unsigned char> penrow_host;
   bool pen_hi = false;            // a penalised row >= 64: only the two-level sweeps (byte mask) can carry it
   unsigned char* dpenrow = nullptr;   // [d] 1 = penalised row (general path, two-level sweeps)
@@ -236,7 +239,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
   cudaSetDevice(h->prob.device);
   double* bufs[] = {h->dA0p, h->dAp, h->du, h->dU, h->dL, h->dQ, h->dx0, h->dT, h->dxs, h->dle, h->dX,
-                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg, h->dQ2, h->dB, h->dc, h->ddc, h->dbnd};
+                    h->dLAM, h->dxf, h->dlam0, h->dJ, h->dg, h->dflops, h->dlamf, h->dS, h->dcs, h->dJpen, h->gW, h->dumax, h->dPg, h->dQ2, h->dB, h->dc, h->ddc, h->dbnd, h->dJc};
   if (h->nch > 1 && !h->cols.empty()) {   // the primary pointers may currently alias any chunk: free through the table only
     for (auto& cb : h->cols) {
       double* cbufs[] = {cb.dx0, cb.dT, cb.dxs, cb.dle, cb.dX, cb.dLAM, cb.dxf, cb.dlam0, cb.dlamf, cb.dcs, cb.dg};
@@ -272,10 +275,6 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
   if (p_local.n <= 0) p_local.n = m_total;
   if (m_total > 8) {   // column chunks of equal width <= 8 (the last one zero-padded)
     if (m_total > 64) { g_create_error = "m > 64 state columns not supported"; return QOC_ERR_UNSUPPORTED; }
-    if (prob->n_pen_rows > 0 && prob->n_pen_cols > 0 && prob->mu != 0.0) {
-      g_create_error = "the running state penalty is not supported with more than 8 state columns yet";
-      return QOC_ERR_UNSUPPORTED;
-    }
     nch = (m_total + 7) / 8;
     p_local.m = (m_total + nch - 1) / nch;
   }
@@ -337,11 +336,13 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     h->penrow_host.resize(p.d, 0);
     h->penrow_host[p.pen_rows[i]] = 1;
   }
-  h->pen_any = p.n_pen_rows > 0 && p.n_pen_cols > 0 && p.mu != 0.0;
-  for (int i = 0; i < p.n_pen_cols; i++) {
-    if (p.pen_cols[i] < 0 || p.pen_cols[i] >= p.m) { g_create_error = "penalty column index out of range"; delete h; return QOC_ERR_INVALID; }
-    h->col_mask |= 1u << p.pen_cols[i];
+  h->pen_global = p.n_pen_rows > 0 && p.n_pen_cols > 0 && p.mu != 0.0;
+  for (int i = 0; i < p.n_pen_cols; i++) {   // (p.m is the chunk width when there are more than 8 columns)
+    if (p.pen_cols[i] < 0 || p.pen_cols[i] >= m_total) { g_create_error = "penalty column index out of range"; delete h; return QOC_ERR_INVALID; }
+    h->col_mask_chunk[p.pen_cols[i] / p.m] |= 1u << (p.pen_cols[i] % p.m);
   }
+  h->col_mask = h->col_mask_chunk[0];
+  h->pen_any = h->pen_global && h->col_mask != 0u;
   h->prob.pen_rows = nullptr;
   h->prob.pen_cols = nullptr;
   h->cfg = cfg;
@@ -447,7 +448,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     h->k1_grid = (int)(h->nseg < target ? h->nseg : target);
     // second-generation sweeps (no running penalty)
     const char* old_sw = getenv("QOC_OLD_SWEEPS");
-    const bool pen = h->row_mask != 0u && h->col_mask != 0u && p.mu != 0.0;
+    const bool pen = h->pen_global;
     {
       // small-dimension sweeps (with or without the running penalty: they carry the affine recurrence and its pre-pass)
       const char* off3 = getenv("QOC_NO_K3S");
@@ -579,7 +580,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     CR(cudaMalloc(&h->gW, (size_t)h->gnw * h->gchunk * slotB));
     CR(cudaMalloc(&h->dumax, 8 * 8));
     CR(cudaMalloc(&h->dpiv, (size_t)h->gchunk * p.d * 4));
-    if (h->pen_any) {
+    if (h->pen_global) {
       h->penrow_host.resize(p.d, 0);
       CR(cudaMalloc(&h->dpenrow, p.d));
       CR(cudaMemcpy(h->dpenrow, h->penrow_host.data(), p.d, cudaMemcpyHostToDevice));
@@ -607,6 +608,7 @@ extern "C" int qoc_create(const qoc_problem* prob, const double* A0, const doubl
     if (T) CR(cudaMemcpy(h->dT, T, dmB, cudaMemcpyHostToDevice));
     else CR(cudaMemset(h->dT, 0, dmB));
   } else {
+    if (h->pen_global) CR(cudaMalloc(&h->dJc, (size_t)h->nch * p.batch * 8));
     h->cols.resize(h->nch);
     h->cols[0] = qoc_handle::ColBufs{h->dx0, h->dT, h->dxs, h->dle, h->dX, h->dLAM, h->dxf, h->dlam0, h->dlamf, h->dcs, h->dg};
     for (int c = 1; c < h->nch; c++) {
@@ -1172,9 +1174,14 @@ static void use_cols(qoc_handle* h, int c) {
   const qoc_handle::ColBufs& cb = h->cols[c];
   h->dx0 = cb.dx0; h->dT = cb.dT; h->dxs = cb.dxs; h->dle = cb.dle; h->dX = cb.dX; h->dLAM = cb.dLAM;
   h->dxf = cb.dxf; h->dlam0 = cb.dlam0; h->dlamf = cb.dlamf; h->dcs = cb.dcs; h->dg = cb.dg;
+  // the running penalty is separable over columns: every chunk carries its own columns of it
+  h->col_mask = h->col_mask_chunk[c];
+  h->pen_any = h->pen_global && h->col_mask != 0u;
 }
 struct ChunkCost {
-  int d, mc, nch, cost, n, want_lam;
+  int d, mc, nch, cost, n, want_lam, batch;
+  const double* Jc;   // [nch][batch] the chunks' running-penalty sums (NULL: no penalty)
+  unsigned pen_chunks; // bit c: chunk c has penalised columns
   const double* xf[8];
   const double* T[8];
   double* lamf[8];
@@ -1198,9 +1205,15 @@ __global__ void __launch_bounds__(256) chunk_cost_kernel(ChunkCost q) {
   if (lane == 0) { atomicAdd(&ov[0], orr); atomicAdd(&ov[1], oii); }
   __syncthreads();
   CostCoef cc;
-  cost_from_overlaps(q.cost, q.n, 1, ov, cc);
-  if (tid == 0 && q.J) q.J[b] = cc.J;
-  if (!q.want_lam) return;
+  cc.J = 0.0;
+  if (q.cost != QOC_COST_NONE) cost_from_overlaps(q.cost, q.n, 1, ov, cc);
+  if (tid == 0 && q.J) {
+    double J = cc.J;
+    if (q.Jc)
+      for (int c = 0; c < q.nch; c++) if ((q.pen_chunks >> c) & 1u) J += q.Jc[(size_t)c * q.batch + b];
+    q.J[b] = J;
+  }
+  if (!q.want_lam || q.cost == QOC_COST_NONE) return;
   for (int c = 0; c < q.nch; c++) {
     const double2* t = reinterpret_cast<const double2*>(q.T[c]);
     double2* l = reinterpret_cast<double2*>(q.lamf[c]) + (size_t)b * dm;
@@ -1223,14 +1236,21 @@ static int chunked_forward(qoc_handle* h, bool store_states, bool want_lam, doub
   const int cost = h->prob.cost;
   int rc = QOC_OK;
   h->prob.cost = QOC_COST_NONE;
-  for (int c = 0; c < h->nch && rc == QOC_OK; c++) { use_cols(h, c); rc = run_sweeps(h, false, nullptr, nullptr, nullptr, store_states, st); }
+  unsigned pen_chunks = 0;
+  for (int c = 0; c < h->nch && rc == QOC_OK; c++) {
+    use_cols(h, c);
+    // (a chunk with penalised columns leaves its sum_k L(x_k) in its own slot: with the cost off, that is all its "J" is)
+    if (has_penalty(h)) pen_chunks |= 1u << c;
+    rc = run_sweeps(h, false, nullptr, has_penalty(h) ? h->dJc + (size_t)c * h->prob.batch : nullptr, nullptr, store_states, st);
+  }
   h->prob.cost = cost;
   use_cols(h, 0);
   if (rc != QOC_OK) return rc;
-  if (cost != QOC_COST_NONE) {
+  if (cost != QOC_COST_NONE || pen_chunks) {
     ChunkCost q;
     memset(&q, 0, sizeof q);
     q.d = h->prob.d; q.mc = h->prob.m; q.nch = h->nch; q.cost = cost; q.n = h->prob.n; q.want_lam = want_lam ? 1 : 0;
+    q.batch = h->prob.batch; q.Jc = pen_chunks ? h->dJc : nullptr; q.pen_chunks = pen_chunks;
     for (int c = 0; c < h->nch; c++) { q.xf[c] = h->cols[c].dxf; q.T[c] = h->cols[c].dT; q.lamf[c] = h->cols[c].dlamf; }
     q.J = d_J ? d_J : h->dJ;
     chunk_cost_kernel<<<h->prob.batch, 256, 0, st>>>(q);
@@ -1424,7 +1444,7 @@ extern "C" int qoc_propagate(qoc_handle* h, const double* u, double* J_out, doub
   // search) does not pay for the Jacobians; qoc_gradient re-runs K1 with them on the cached u when they are missing.
   // qoc_set_eager_jacobians(h, 1) produces them here (they share the Pade powers) when f_grad always follows f.
   if ((rc = launch_k1(h, h->du, h->eager_jac, h->stream)) != QOC_OK) return rc;
-  const bool builtin = p.cost != QOC_COST_NONE || has_penalty(h);  // J (or its penalty part) is formed on the device
+  const bool builtin = p.cost != QOC_COST_NONE || h->pen_global;  // J (or its penalty part) is formed on the device
   if (h->nch > 1) {
     if ((rc = chunked_forward(h, false, false, nullptr, h->stream)) != QOC_OK) return rc;
     if (x_final_out && (rc = chunked_copy(h, x_final_out, true, 0, 0, h->stream)) != QOC_OK) return rc;

@@ -82,10 +82,39 @@ def test_full_propagator_is_unitary_and_batched():
     cb.close()
 
 
-def test_unsupported_combinations_fail_loudly():
-    cfg = full_propagator_case("zz9")
-    pen = q.setup_state_penalty([6, 7, 8], [0, 1, 3, 4], 0.2)
-    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape)
-    with pytest.raises(q.QOCError) as ei:
-        q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cache, penalty=pen)
-    assert ei.value.status == _lib.ERR_UNSUPPORTED
+PEN_CASES = {
+    # rows, columns (spanning the chunks; "bus27": chunk 0 has none), mu
+    "zz9": ([6, 7, 8], [0, 1, 3, 4, 8], 0.2),            # chunks of 5: columns 0-4 | 5-8
+    "bus27": ([20, 25, 26], [9, 13, 26], 0.4),           # chunks of 7: only chunks 1 and 3 carry it
+    "synth16": ([3, 15], [0, 7, 8, 15], 0.9),            # first and last column of both chunks (all 16 columns of a
+                                                         # unitary would make L constant: rows of x_k have unit norm)
+    "synth32": ([1, 31], [5, 6, 11], 0.7),               # general path, chunks of 6
+}
+
+
+@pytest.mark.parametrize("name", ["zz9", "bus27", "synth16", "synth32"])
+@pytest.mark.parametrize("order", [0, 3])
+def test_full_propagator_with_running_penalty(name, order):
+    """setup_state_penalty on a full propagator (the leakage penalty of examples/ipopt_callbacks_exp.jl:18 with m = d): the
+    penalty is separable over columns, every chunk carries its own columns of L and dL_dx."""
+    cfg = full_propagator_case(name)
+    pen = PEN_CASES[name]
+    Jo, go, co = o.evaluate(cfg, order=order, penalty=pen)
+    J0, g0, _ = o.evaluate(cfg, order=order)
+    assert abs(Jo - J0) > 1e-3 and np.abs(go - g0).max() > 1e-6 * np.abs(go).max()
+    L, dL = q.setup_state_penalty(*pen)
+    cost = q.setup_infidelity(cfg["T"], cfg["n"])
+    cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=order)
+    J, g = q.evaluate(cache, cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], cost[1], dUkdp_order=order, penalty=(L, dL))
+    assert abs(J - Jo) <= TOL_J * max(1.0, abs(Jo))
+    assert np.abs(g - go).max() <= TOL_G * np.abs(go).max()
+    # reference-style split calls, host-closure cost: cache.J is then the running sum of the penalty alone
+    c2 = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, dUkdp_order=order)
+    Jf, dJf = o.setup_infidelity(cfg["T"], cfg["n"])
+    q.propagate(cfg["A0"], cfg["A"], cfg["u"], cfg["x0"], c2, penalty=(L, dL))
+    assert abs(c2.J - sum(L(xk) for xk in co["x"])) <= TOL_J
+    g2 = q.grape_sensitivity(cfg["A0"], cfg["A"], dJf, cfg["u"], cfg["x0"], c2, dUkdp_order=order, dL_dx=dL)
+    assert np.abs(g2 - go).max() <= TOL_G * np.abs(go).max()
+    assert np.abs(c2.lam - co["lam"]).max() < 1e-10
+    cache.close()
+    c2.close()
