@@ -10,6 +10,7 @@ from qoc_b200 import sharding
 
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+FEATS = sys.argv[3].split(",") if len(sys.argv) > 3 else ["zcal", "shard", "stream", "batch", "shardpen", "chunkpen"]
 fails = 0
 worst = {}
 t0 = time.time()
@@ -35,10 +36,11 @@ def check(tag, info, J, g, Jo, go, tol_g=1e-8):
 
 
 for it in range(n):
-    feat = rng.choice(["zcal", "shard", "stream", "batch"])
+    feat = rng.choice(FEATS)
     order = int(rng.choice([0, 3]))
     scale = float(rng.choice([0.05, 0.3, 1.0, 3.0]))
     os.environ.pop("QOC_STREAM_JAC", None)
+    os.environ.pop("QOC_SHARD_THREADS", None)
     if feat == "zcal":
         d = int(rng.integers(4, 41)); nc = int(rng.integers(1, 3)); nt = int(rng.integers(2, 30))
         cfg = problem(d, nc, 4, nt, scale)
@@ -60,6 +62,39 @@ for it in range(n):
         J, g = sh.evaluate(cfg["u"])
         check(feat, dict(d=d, nc=nc, m=m, nt=nt, P=P, order=order, scale=scale), J, g, Jo, go)
         sh.close()
+    elif feat == "shardpen":   # running penalty under in-library time sharding (second exchange), every sweep family
+        d = int(rng.integers(2, 41)); nc = int(rng.integers(1, 3)); m = int(rng.integers(1, min(d, 8) + 1)); P = int(rng.integers(2, 5))
+        nt = int(rng.integers(4 * P, 120))
+        cfg = problem(d, nc, m, nt, scale)
+        rows = sorted(rng.choice(d, size=int(rng.integers(1, d + 1)), replace=False).tolist())
+        cols = sorted(rng.choice(m, size=int(rng.integers(1, m + 1)), replace=False).tolist())
+        pen = (rows, cols, float(rng.uniform(0.1, 2.0)))
+        Jo, go, _ = o.evaluate(cfg, order=order, penalty=pen)
+        if rng.random() < 0.3:
+            os.environ["QOC_STREAM_JAC"] = "1"
+        os.environ["QOC_SHARD_THREADS"] = str(int(rng.integers(0, 2)))
+        sh = sharding.InProcessSharded(cfg["A0"], cfg["A"], cfg["x0"], q.setup_infidelity(cfg["T"], cfg["n"])[1], cfg["u"].shape, [0] * P,
+                                       kind="time", dUkdp_order=order, penalty=q.setup_state_penalty(*pen))
+        for rep in range(2):
+            J, g = sh.evaluate(cfg["u"])
+            check(feat, dict(d=d, nc=nc, m=m, nt=nt, P=P, order=order, scale=scale, pen=pen, rep=rep), J, g, Jo, go)
+        sh.close()
+    elif feat == "chunkpen":   # running penalty with more than 8 state columns (column chunks), single pulses and batches
+        d = int(rng.integers(9, 41)); nc = int(rng.integers(1, 3)); m = int(rng.integers(9, d + 1)); nt = int(rng.integers(2, 40))
+        nb = int(rng.integers(1, 4))
+        cfg = problem(d, nc, m, nt, scale)
+        rows = sorted(rng.choice(d, size=int(rng.integers(1, d + 1)), replace=False).tolist())
+        cols = sorted(rng.choice(m, size=int(rng.integers(1, m + 1)), replace=False).tolist())
+        pen = (rows, cols, float(rng.uniform(0.1, 2.0)))
+        ub = rng.uniform(-0.5, 0.5, (nb, nc, nt))
+        cache = q.setup_grape_cache(cfg["A0"], cfg["x0"], cfg["u"].shape, batch=nb, dUkdp_order=order, store_costates=False)
+        Jb, gb = q.evaluate(cache, cfg["A0"], cfg["A"], ub if nb > 1 else ub[0], cfg["x0"], q.setup_infidelity(cfg["T"], cfg["n"])[1],
+                            dUkdp_order=order, penalty=q.setup_state_penalty(*pen))
+        Jb, gb = np.atleast_1d(Jb), (gb if nb > 1 else gb[None])
+        for b in range(nb):
+            Jo, go, _ = o.evaluate(cfg, order=order, u=ub[b], penalty=pen)
+            check(feat, dict(d=d, nc=nc, m=m, nt=nt, nb=nb, b=b, order=order, scale=scale, pen=pen), Jb[b], gb[b], Jo, go)
+        cache.close()
     elif feat == "stream":
         d = int(rng.integers(29, 41)); nc = int(rng.integers(1, 3)); m = int(rng.integers(1, 6)); nt = int(rng.integers(4, 40))
         cfg = problem(d, nc, m, nt, scale)
