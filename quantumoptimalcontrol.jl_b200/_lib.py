@@ -71,13 +71,21 @@ def lib_path() -> str:
     return _build.LIB
 
 
+def _dev_override():
+    """Developer aid for A/B builds of the library with other -D switches: QOC_LIB_PATH=<.so> loads that file as is."""
+    import os
+    return os.environ.get("QOC_LIB_PATH")
+
+
 def load(build_if_missing: bool = True):
     """Load libqoc_b200.so (building it with nvcc if absent).  Raises if it cannot be had: loudly, no fallback."""
     global _lib
     if _lib is not None:
         return _lib
     path = lib_path()
-    if _build.needs_build():   # missing, or built from other sources than the ones in the tree (content hash)
+    if _dev_override():
+        path = _dev_override()
+    elif _build.needs_build():   # missing, or built from other sources than the ones in the tree (content hash)
         if not build_if_missing:
             raise FileNotFoundError(path + " missing or stale: run `python __graft_entry__.py build`")
         _build.build()

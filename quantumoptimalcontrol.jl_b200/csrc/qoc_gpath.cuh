@@ -49,6 +49,15 @@ struct GGemm {
 #ifndef QOC_GEMM_NST64
 #define QOC_GEMM_NST64 3
 #endif
+#ifndef QOC_GEMM_MINBX
+#define QOC_GEMM_MINBX 2    // ... of its extra-output instantiation (137 registers uncapped: one CTA per SM)
+#endif
+#ifndef QOC_GEMM_NSTS
+#define QOC_GEMM_NSTS 3     // ring depth of the small tiles (2 measured worse: 84 registers, d = 32 9.1 -> 10.3 ms)
+#endif
+#ifndef QOC_GEMM_MINB
+#define QOC_GEMM_MINB 4     // __launch_bounds__ minimum CTAs per SM of the 32 x 32 tile (8 warps): 64 registers instead of 70, four
+#endif                      // CTAs per SM instead of three (d = 32, 8000 slices: 9.1 -> 8.2 ms; on the 40 / 48 tiles it only hurt)
 #ifndef QOC_GEMM_KCS
 #define QOC_GEMM_KCS 16
 #endif
@@ -76,7 +85,7 @@ template <int WM, int WN, int NWM, int NWN>
 struct GemmShape {
   // k-chunk: 32 wide for the 64 x 64 tile (3 x 72 KB of ring: one CTA per SM anyway, half as many barriers per flop), 16 otherwise
   static constexpr int NTH = 32 * NWM * NWN, TM = 8 * WM * NWM, TN = 8 * WN * NWN, KC = (WM * NWM == 8 && WN * NWN == 8) ? QOC_GEMM_KC64 : QOC_GEMM_KCS,
-                       NST = (WM * NWM == 8 && WN * NWN == 8) ? QOC_GEMM_NST64 : 3;
+                       NST = (WM * NWM == 8 && WN * NWN == 8) ? QOC_GEMM_NST64 : QOC_GEMM_NSTS;
   static constexpr int AS = KC + 4, BS = TN + 4;
   static constexpr int A_PLANE = TM * AS, B_PLANE = KC * BS, STAGE = 2 * A_PLANE + 2 * B_PLANE;   // doubles
   static constexpr size_t SMEM = (size_t)NST * STAGE * 8;
@@ -89,7 +98,7 @@ struct GemmShape {
 // nothing to overlap them when only one CTA fits an SM (the 64 x 64 tile: 16 warps x ~100 registers): at d = 64, where a
 // tile is only four chunks long, that was half the kernel.
 template <int WM, int WN, int NWM, int NWN, bool XTRA>   // XTRA: the epilogue also writes the extra outputs (more registers)
-__global__ void __launch_bounds__(32 * NWM * NWN) g_gemm2_kernel(GGemm g, int ntm, int ntn, int nitems) {
+__global__ void __launch_bounds__(32 * NWM * NWN, (NWM * NWN == 8) ? (XTRA ? QOC_GEMM_MINBX : QOC_GEMM_MINB) : 1) g_gemm2_kernel(GGemm g, int ntm, int ntn, int nitems) {
   typedef GemmShape<WM, WN, NWM, NWN> G;
   constexpr int NTH = G::NTH, TM = G::TM, TN = G::TN, KC = G::KC, NST = G::NST, AS = G::AS, BS = G::BS;
   extern __shared__ __align__(16) unsigned char gsm_raw[];
