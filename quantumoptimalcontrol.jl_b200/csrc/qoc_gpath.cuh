@@ -52,6 +52,12 @@ struct GGemm {
 #ifndef QOC_GEMM_MINBX
 #define QOC_GEMM_MINBX 2    // ... of its extra-output instantiation (137 registers uncapped: one CTA per SM)
 #endif
+#ifndef QOC_GEMM_MINBX40
+#define QOC_GEMM_MINBX40 3  // extra-output instantiations of the 40 / 48 tiles: 167 -> 128 and 184 -> 166 registers, i.e. three and two
+#endif                      // CTAs per SM like their plain forms instead of two and ONE (d = 48: 10.8 -> 9.7 ms, d = 96: 14.7 -> 13.1,
+#ifndef QOC_GEMM_MINBX48    // cavity-40: 4.30 -> 4.11)
+#define QOC_GEMM_MINBX48 2
+#endif
 #ifndef QOC_GEMM_NSTS
 #define QOC_GEMM_NSTS 3     // ring depth of the small tiles (2 measured worse: 84 registers, d = 32 9.1 -> 10.3 ms)
 #endif
@@ -98,7 +104,7 @@ struct GemmShape {
 // nothing to overlap them when only one CTA fits an SM (the 64 x 64 tile: 16 warps x ~100 registers): at d = 64, where a
 // tile is only four chunks long, that was half the kernel.
 template <int WM, int WN, int NWM, int NWN, bool XTRA>   // XTRA: the epilogue also writes the extra outputs (more registers)
-__global__ void __launch_bounds__(32 * NWM * NWN, (NWM * NWN == 8) ? (XTRA ? QOC_GEMM_MINBX : QOC_GEMM_MINB) : 1) g_gemm2_kernel(GGemm g, int ntm, int ntn, int nitems) {
+__global__ void __launch_bounds__(32 * NWM * NWN, (NWM * NWN == 8) ? (XTRA ? QOC_GEMM_MINBX : QOC_GEMM_MINB) : (XTRA && NWM * NWN == 5) ? QOC_GEMM_MINBX40 : (XTRA && NWM * NWN == 6) ? QOC_GEMM_MINBX48 : 1) g_gemm2_kernel(GGemm g, int ntm, int ntn, int nitems) {
   typedef GemmShape<WM, WN, NWM, NWN> G;
   constexpr int NTH = G::NTH, TM = G::TM, TN = G::TN, KC = G::KC, NST = G::NST, AS = G::AS, BS = G::BS;
   extern __shared__ __align__(16) unsigned char gsm_raw[];
