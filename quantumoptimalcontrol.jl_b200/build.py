@@ -11,7 +11,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libqoc_b200.so")
 SOURCES = [os.path.join(CSRC, "qoc_api.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("qoc_tiles.cuh", "qoc_k1.cuh", "qoc_k1s.cuh", "qoc_k23.cuh", "qoc_gpath.cuh", "qoc_sweep.cuh", "qoc_basis.cuh")] + [
+# every header of csrc/ (globbed: a header missing from a hand-kept list would let an edited kernel run against a stale binary)
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
     os.path.join(os.path.dirname(HERE), "include", "qoc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "--cudart", "static"]

@@ -20,6 +20,9 @@
 
 namespace qoc {
 
+#ifndef K3S_MINB
+#define K3S_MINB 1   // (246 registers, eight warps per SM; capping at 128 / 80 registers spills: 1.17 / 1.45 ms instead of 0.86)
+#endif
 constexpr int K3S_WPB = 8;     // warps per CTA
 constexpr int K3S_M = 4;       // state columns (compile-time bound)
 constexpr int K3S_D = 9;
@@ -70,6 +73,15 @@ __device__ __forceinline__ void k3s_load_col_conj(const K3SLane& L, const double
     a[k] = ok ? make_double2(__ldg(re + k * L.S), -__ldg(im + k * L.S)) : make_double2(0.0, 0.0);
   }
 }
+// the nine lanes of a group pull one slot (bytes) towards L2, 128-byte line by line: no registers held, unlike a register prefetch
+__device__ __forceinline__ void k3s_prefetch_l2(const void* base, int bytes, int r) {
+  const char* q = reinterpret_cast<const char*>(base);
+  for (int o = r * 128; o < bytes; o += 9 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+}
+#ifndef K3S_PF
+#define K3S_PF 1   // how many slices ahead the backward pass prefetches U_k, dU_k/du_j and x_k into L2 (zz batch, K3S alone:
+                   // none 0.858 ms, one slice ahead 0.806, two 0.880, three 0.957: further ahead the lines are evicted again)
+#endif
 // sum over the nine lanes of a group, result valid in the group's lane 0
 __device__ __forceinline__ double k3s_group_sum(double v, int r) {
   const unsigned F = 0xffffffffu;
@@ -80,7 +92,7 @@ __device__ __forceinline__ double k3s_group_sum(double v, int r) {
   return v;
 }
 
-__global__ void __launch_bounds__(K3S_WPB * 32, 1) k3s_kernel(K23Params p, int S) {
+__global__ void __launch_bounds__(K3S_WPB * 32, K3S_MINB) k3s_kernel(K23Params p, int S) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -180,6 +192,13 @@ __global__ void __launch_bounds__(K3S_WPB * 32, 1) k3s_kernel(K23Params p, int S
       const bool live = it < len;
       const int k = k1 - 1 - it;                         // slice index within the pulse
       const size_t sl = live ? sl0 + (len - 1 - it) : sl0;
+      if (K3S_PF > 0 && on && it + K3S_PF < len) {   // the operands of the step K3S_PF slices further down: towards L2 now
+        const size_t sp = sl - K3S_PF;
+        k3s_prefetch_l2(p.U + sp * slot_d, (int)(slot_d * 8), L.r);
+        if (contract)
+          for (int j = 0; j < nc; j++) k3s_prefetch_l2(p.L + (sp * nc + j) * slot_d, (int)(slot_d * 8), L.r);
+        k3s_prefetch_l2(p.X + ((size_t)b * (p.nt + 1) + (k - K3S_PF)) * 2 * dm, 2 * dm * 8, L.r);
+      }
       // operands of this step straight from HBM / L2: conj column of U_k, x_k, and (below) the Jacobian rows
       double2 uc[K3S_D];
       double2 xk[K3S_M];
