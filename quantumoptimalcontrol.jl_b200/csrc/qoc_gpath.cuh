@@ -843,6 +843,16 @@ __device__ __forceinline__ void gs_mv(const double* Ure, const double* Uim, int 
     }
   }
 }
+// the CTA pulls the planar slot of the NEXT step towards L2 while this step's mat-vec runs (the steps of a sweep are a latency
+// chain: one L2 / HBM round trip per k-batch of operand fragments, nothing else in flight)
+#ifndef GS_PF
+#define GS_PF 1
+#endif
+__device__ __forceinline__ void gs_prefetch_slot(const double* slot, long long doubles, int tid, int nth) {
+  if (!GS_PF) return;
+  const char* q = reinterpret_cast<const char*>(slot);
+  for (long long o = (long long)tid * 128; o < doubles * 8; o += (long long)nth * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+}
 template <bool ADJ>
 __device__ __forceinline__ void gs_mv_any(const double* U, int d, int S, int m, const double* xs, double* ys, int warp, int lane) {
   const double* Uim = U + (size_t)d * S;
@@ -944,6 +954,7 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
     __syncthreads();
     for (int s = 0; s < g.spp; s++) {
       gs_to_global(g.xs_start + ((size_t)b * g.spp + s) * 2 * dm, cur, d, m, tid, nth);
+      if (s + 1 < g.spp) gs_prefetch_slot(g.Q + ((size_t)b * g.spp + s + 1) * g.slot, g.slot, tid, nth);
       gs_mv_any<false>(g.Q + ((size_t)b * g.spp + s) * g.slot, d, g.S, m, cur, nxt, warp, lane);
       __syncthreads();
       double* t = cur; cur = nxt; nxt = t;
@@ -995,6 +1006,7 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_scan_kernel(GS g) {
   { double* t = cur; cur = nxt; nxt = t; }
   for (int s = g.spp - 1; s >= 0; s--) {
     gs_to_global(g.lam_end + ((size_t)b * g.spp + s) * 2 * dm, cur, d, m, tid, nth);
+    if (s > 0) gs_prefetch_slot(g.Q + ((size_t)b * g.spp + s - 1) * g.slot, g.slot, tid, nth);
     gs_mv_any<true>(g.Q + ((size_t)b * g.spp + s) * g.slot, d, g.S, m, cur, nxt, warp, lane);
     __syncthreads();
     if (pen) {   // + c_seg
@@ -1035,6 +1047,7 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_seg_kernel(GS g, int nseg_total
         gs_to_global(g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, cur, d, m, tid, nth);
         if (g.pen_prepass) ps += gs_penalty_sum(cur, g, tid, nth);
         if (k + 1 < k1) {
+          if (k + 1 < k1) gs_prefetch_slot(g.U + ((size_t)b * g.nt + k + 1) * g.slot, g.slot, tid, nth);
           gs_mv_any<false>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
           __syncthreads();
           double* t = cur; cur = nxt; nxt = t;
@@ -1053,7 +1066,8 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_seg_kernel(GS g, int nseg_total
         __syncthreads();
         for (int k = k1 - 1; k >= k0; k--) {
           gs_from_global(b2, g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, d, m, tid, nth);
-          gs_mv_any<true>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
+          if (k > k0) gs_prefetch_slot(g.U + ((size_t)b * g.nt + k - 1) * g.slot, g.slot, tid, nth);
+        gs_mv_any<true>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
           __syncthreads();
           gs_add_penalty(nxt, b2, g, tid, nth);
           __syncthreads();
@@ -1069,6 +1083,7 @@ __global__ void __launch_bounds__(GS_NW * 32) gs_seg_kernel(GS g, int nseg_total
       for (int k = k1 - 1; k >= k0; k--) {
         gs_to_global(g.LAM + ((size_t)b * (g.nt + 1) + k + 1) * 2 * dm, cur, d, m, tid, nth);
         if (pen) gs_from_global(b2, g.X + ((size_t)b * (g.nt + 1) + k) * 2 * dm, d, m, tid, nth);
+        if (k > k0) gs_prefetch_slot(g.U + ((size_t)b * g.nt + k - 1) * g.slot, g.slot, tid, nth);
         gs_mv_any<true>(g.U + ((size_t)b * g.nt + k) * g.slot, d, g.S, m, cur, nxt, warp, lane);
         __syncthreads();
         if (pen) { gs_add_penalty(nxt, b2, g, tid, nth); __syncthreads(); }   // + dL_dx(x_k)  (:55-57)
