@@ -760,7 +760,6 @@ static int gpath_build_Q(qoc_handle* h, cudaStream_t st) {
   const int L = h->gL, spp = h->spp, d = p.d;
   const long long slot = h->slot_d;
   const int len_last = p.nt - (spp - 1) * L;          // 1..L
-  const int tiles = (d + 31) / 32;
   struct Grp { int inner, count, len; long long first; };   // segments si in [first, first + inner) of every pulse
   Grp grp[2] = {{spp - 1, (spp - 1) * p.batch, L, 0}, {1, p.batch, len_last, spp - 1}};
   if (len_last == L) { grp[0] = Grp{spp, spp * p.batch, L, 0}; grp[1].count = 0; }
@@ -899,7 +898,6 @@ static int gpath_k1(qoc_handle* h, const double* d_u, bool want_jac, cudaStream_
   const double* b = q == 13 ? kB13 : q == 7 ? kB7 : kB5;
   enum { A = 0, X, A2, A4, A6, W1, Z1, Wm, V, U, R, M2, M4, M6, T1, T2, Lw, Lv, Dd, Ss, RH, TMP, TMPR, NI, L0 };
   GRun g{h, st, 0, (d + 31) / 32};
-  const GOp A0op{h->dA0p, 0};
   for (size_t c0 = 0; c0 < nsl; c0 += h->gchunk) {
     const int nb = (int)((nsl - c0 < (size_t)h->gchunk) ? nsl - c0 : h->gchunk);
     g.nb = nb;

@@ -484,15 +484,17 @@ __global__ void __launch_bounds__(256) g_gj_panel_kernel(int d, int S, int k0, i
     // pivot search over the rows that have not pivoted yet (i >= k)
     double best = -1.0;
     int bi = k;
-    for (int i = k + tid; i < d; i += 256) {
-      const double2 v = pan[(size_t)i * NBP + kk];
-      const double m = v.x * v.x + v.y * v.y;
-      if (m > best) { best = m; bi = i; }
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    if (k + warp * 32 < d) {   // (warp-uniform: a warp none of whose threads has a candidate row skips the reduction)
+      for (int i = k + tid; i < d; i += 256) {
+        const double2 v = pan[(size_t)i * NBP + kk];
+        const double m = v.x * v.x + v.y * v.y;
+        if (m > best) { best = m; bi = i; }
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
     }
     if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
     __syncthreads();

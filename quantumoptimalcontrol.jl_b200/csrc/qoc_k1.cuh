@@ -637,7 +637,6 @@ __device__ __forceinline__ int build_generator(const K1Params& p, K1Ctx<C>& c, c
                                                const double (&uj)[8], bool need_x, SvcScratch* sc) {
   typedef GenMap<C> GM;
   static_assert(GM::RPT <= 2 && GM::G <= 22, "generator mapping");
-  constexpr int S = C::S;
   const int d = c.d, nc = p.nc;
   const int cp = c.tid % GM::S2, r0 = c.tid / GM::S2;
   const bool act = r0 < GM::G;

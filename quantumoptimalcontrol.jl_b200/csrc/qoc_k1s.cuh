@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(K1S_MAXWPB * 32, 1) k1s_kernel(K1Params p, int
   load_u(it);
   while (__any_sync(FULL, it.valid())) {
     const bool on = it.valid();                       // this group has a slice in this round
-    const bool first_of_seg = (it.k == it.k0), last_of_seg = (it.k + 1 >= it.k1);
+    const bool first_of_seg = (it.k == it.k0);
     const size_t slice = on ? (size_t)it.b * p.nt + it.k : 0;
     const int seg = on ? it.seg : 0;
     // ---- generator X = A0 + sum_j u_j E_j, 1-norm, degree and scaling ----

@@ -594,7 +594,6 @@ __global__ void __launch_bounds__((C::NT + 1 + K3N_CW) * 32, (C::NT <= 2) ? 2 : 
   const int dm = d * m;
   const int sb = RP * W;
   const bool contract = p.want_grad != 0;
-  const int RT = NT * 32;
 
   double* base = reinterpret_cast<double*>(smem_raw);
   double* ringp = base;                                       // SW_NST slots (U_k)
