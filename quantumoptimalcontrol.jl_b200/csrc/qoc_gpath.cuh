@@ -587,94 +587,6 @@ static inline size_t g_gj_panel_smem(int d) {
   return ((size_t)d * NBP + 64) * 16;
 }
 
-// d <= 32: the whole elimination by ONE WARP per slice, lane = row, the row in registers (32 complex numbers), no shared
-// memory and no barrier.  Same arithmetic, pivot rule (largest |.|^2 among the rows that have not pivoted, lowest row on a
-// tie) and pivot list as g_gj_panel_kernel with a single panel, so g_gj_perm_kernel finishes it unchanged.  Rows are not
-// moved between lanes: a lane carries the POSITION of its row (pos), the interchange k <-> p swaps two positions, and a row
-// is written back to the position it ended up in.  The panel kernel is instruction-issue bound at these sizes (3 CTA
-// barriers and ~430 instructions per warp for every pivot step: 243 us for 2048 slices of d = 32).
-__global__ void __launch_bounds__(256, 1) g_gj_warp_kernel(int d, int S, double* M, long long stride, int* piv, int* status, int nsl) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int sl = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (sl >= nsl) return;
-  double* re = M + (long long)sl * stride;
-  double* im = re + (size_t)d * S;
-  int* pv = piv + (size_t)sl * d;
-  const bool rowok = lane < d;
-  double2 row[32];
-#pragma unroll
-  for (int c = 0; c < 32; c += 2) {   // S is a multiple of 4 and the slots are 16-byte aligned: two columns per load
-    double2 r2 = make_double2(0.0, 0.0), i2 = make_double2(0.0, 0.0);
-    if (rowok && c < d) {
-      r2 = *reinterpret_cast<const double2*>(re + (size_t)lane * S + c);
-      i2 = *reinterpret_cast<const double2*>(im + (size_t)lane * S + c);
-    }
-    row[c] = make_double2(c < d ? r2.x : 0.0, c < d ? i2.x : 0.0);
-    row[c + 1] = make_double2(c + 1 < d ? r2.y : 0.0, c + 1 < d ? i2.y : 0.0);
-  }
-  int pos = lane;
-  bool ok = true;
-#pragma unroll 1
-  for (int kk = 0; kk < d; kk++) {
-    // my entry in column kk
-    double2 f = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int c = 0; c < 32; c++) if (c == kk) f = row[c];
-    // pivot: largest |.|^2 among the positions >= kk, the lowest position on a tie
-    double best = (rowok && pos >= kk) ? f.x * f.x + f.y * f.y : -1.0;
-    int bp = (rowok && pos >= kk) ? pos : 0x7fffffff;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ob = __shfl_xor_sync(FULL, best, off);
-      const int op = __shfl_xor_sync(FULL, bp, off);
-      if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; }
-    }
-    if (!(best > 0.0)) ok = false;
-    const int p = bp;                                                  // position of the pivot row (uniform)
-    const int lp = __ffs(__ballot_sync(FULL, rowok && pos == p)) - 1;   // the lane that holds it
-    if (lane == 0) pv[kk] = p;
-    // interchange kk <-> p: two positions trade places
-    if (rowok) {
-      if (pos == p) pos = kk;
-      else if (pos == kk) pos = p;
-    }
-    const int src = lp < 0 ? 0 : lp;
-    const double2 pvv = make_double2(__shfl_sync(FULL, f.x, src), __shfl_sync(FULL, f.y, src));
-    const double den = 1.0 / (pvv.x * pvv.x + pvv.y * pvv.y);
-    const double pir = pvv.x * den, pii = -pvv.y * den;   // 1 / pivot
-    const bool is_piv = lane == src;
-    const double gr = f.x * pir - f.y * pii, gi = f.x * pii + f.y * pir;   // multiplier of an ordinary row
-#pragma unroll
-    for (int c = 0; c < 32; c++) {
-      const double2 pr = make_double2(__shfl_sync(FULL, row[c].x, src), __shfl_sync(FULL, row[c].y, src));
-      double2 val;
-      if (is_piv) {
-        if (c == kk) val = make_double2(pir, pii);
-        else val = make_double2(pr.x * pir - pr.y * pii, pr.x * pii + pr.y * pir);
-      } else {
-        if (c == kk) val = make_double2(-gr, -gi);
-        else val = make_double2(row[c].x - (gr * pr.x - gi * pr.y), row[c].y - (gr * pr.y + gi * pr.x));
-      }
-      if (rowok && c < d) row[c] = val;
-    }
-  }
-  // rows back, each to the position it ended up in
-  if (rowok) {
-#pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      if (c + 1 < d) {
-        *reinterpret_cast<double2*>(re + (size_t)pos * S + c) = make_double2(row[c].x, row[c + 1].x);
-        *reinterpret_cast<double2*>(im + (size_t)pos * S + c) = make_double2(row[c].y, row[c + 1].y);
-      } else if (c < d) {
-        re[(size_t)pos * S + c] = row[c].x;
-        im[(size_t)pos * S + c] = row[c].y;
-      }
-    }
-  }
-  if (lane == 0 && !ok) atomicExch(status, 8);
-}
-
 // N^-1 for `nsl` slices: cur (holds N, destroyed) and oth are two workspace slots; returns the buffer that holds the inverse.
 static inline double* g_inverse_blocked(int d, int S, long long slot_d, int nsl, double* cur, double* oth, int* piv, int* status,
                                         cudaStream_t st, int* launches) {
@@ -687,15 +599,6 @@ static inline double* g_inverse_blocked(int d, int S, long long slot_d, int nsl,
   if (psm > 40 * 1024 && psm > attr_set) {
     cudaFuncSetAttribute(g_gj_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
     attr_set = psm;
-  }
-  // (opt-in until it has been through the GPU parity suite: QOC_GJ_WARP=1)
-  static const int warp_form = [] { const char* e = getenv("QOC_GJ_WARP"); return (e && e[0] == '1') ? 1 : 0; }();
-  if (d <= 32 && warp_form) {   // one warp per slice, rows in registers (g_gj_warp_kernel)
-    g_gj_warp_kernel<<<(nsl + 7) / 8, 256, 0, st>>>(d, S, cur, slot_d, piv, status, nsl);
-    (*launches)++;
-    g_gj_perm_kernel<<<nsl, 256, (size_t)d * 4, st>>>(d, S, cur, oth, slot_d, piv);
-    (*launches)++;
-    return oth;
   }
   for (int k0 = 0; k0 < d; k0 += nbw) {
     const int nb = (d - k0 < nbw) ? d - k0 : nbw;
